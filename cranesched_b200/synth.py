@@ -1,0 +1,418 @@
+"""Deterministic synthetic pending queues + node tables.
+
+The same generated tables feed the CUDA path and (in tests/bench) the oracle.
+Seeds are `0xC0FFEE00 + config_id`; `now` = 1_700_000_000. Request views are
+derived the way the reference derives them at submit time
+(CtldPublicDefs.cpp:1655-1682: cpus_per_task / mem_per_cpu -> req_task_res_view,
+gres_per_node -> req_node_res_view; JobScheduler.cpp:6075-6110:
+ntasks_per_node bounds and req_total_res_view = node*node_num + task*ntasks).
+Node totals follow CranedMetaContainer.cpp:318-346 (cores {0..n-1},
+cpu = n, mem_sw = mem, configured gres slots).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .abi import (CORE_WORDS, GRES_ENTRIES, RES_IN_NODE, RES_VIEW, Cluster, Config,
+                  Pending, Running)
+
+NOW = 1_700_000_000
+GiB = 1 << 30
+DAY = 24 * 3600
+SEED_BASE = 0xC0FFEE00
+
+
+def _rng(config_id: int, salt: int = 0) -> np.random.Generator:
+    return np.random.Generator(np.random.PCG64(SEED_BASE + config_id + (salt << 32)))
+
+
+def node_row(cores: int, mem: int, gres: dict[int, int] | None = None) -> np.ndarray:
+    """res_total of one node: cores {0..n-1}; gres = {entry: n_slots}."""
+    r = np.zeros((), RES_IN_NODE)
+    r["cpu_raw"] = cores * 256
+    r["mem"] = mem
+    r["mem_sw"] = mem
+    for w in range(CORE_WORDS):
+        k = min(max(cores - 64 * w, 0), 64)
+        r["core"][w] = (1 << k) - 1 if k < 64 else 0xFFFFFFFFFFFFFFFF
+    for e, n in (gres or {}).items():
+        r["gres"][e] = (1 << n) - 1
+    return r
+
+
+def make_cluster(groups, gres_entry_name=()) -> Cluster:
+    """groups: list of (count, node_row) -> one disjoint partition per group."""
+    rows, off, nodes = [], [0], []
+    base = 0
+    for count, row in groups:
+        rows.append(np.repeat(row[None], count))
+        nodes.append(np.arange(base, base + count, dtype=np.uint32))
+        base += count
+        off.append(base)
+    res_total = np.concatenate(rows)
+    m = len(res_total)
+    return Cluster(res_total, np.ones(m, np.uint8), np.zeros(m, np.uint8),
+                   np.array(off, np.uint32), np.concatenate(nodes),
+                   len(gres_entry_name), tuple(gres_entry_name))
+
+
+def _views(n, cpus_raw, mem_per_task, node_num, ntasks, gres_total=None, gres_spec=None,
+           mem_per_node=None):
+    req_node = np.zeros(n, RES_VIEW)
+    req_task = np.zeros(n, RES_VIEW)
+    req_task["cpu_raw"] = cpus_raw
+    req_task["mem"] = mem_per_task
+    req_task["mem_sw"] = mem_per_task
+    if mem_per_node is not None:
+        req_node["mem"] = mem_per_node
+        req_node["mem_sw"] = mem_per_node
+    if gres_total is not None:
+        req_node["gres_total"] = gres_total
+    if gres_spec is not None:
+        req_node["gres_spec"] = gres_spec
+    req_total = np.zeros(n, RES_VIEW)
+    nn = node_num.astype(np.int64)
+    nt = ntasks.astype(np.int64)
+    for f in ("cpu_raw", "mem", "mem_sw"):
+        req_total[f] = (req_node[f].astype(np.int64) * nn + req_task[f].astype(np.int64) * nt).astype(req_total[f].dtype)
+    for f in ("gres_total", "gres_spec"):
+        req_total[f] = (req_node[f].astype(np.int64) * nn[:, None]
+                        + req_task[f].astype(np.int64) * nt[:, None]).astype(np.uint16)
+    return req_node, req_task, req_total
+
+
+def _log_uniform(rng, lo, hi, n):
+    return np.exp(rng.uniform(np.log(lo), np.log(hi), n)).astype(np.int64)
+
+
+def _pending(n, partition, time_limit, submit, node_num, ntasks, views, part_prio, qos_prio,
+             account=None, qos=None, user=None, exclusive=None, ntpn=None, mandated=None,
+             incl=None, excl=None):
+    z32 = np.zeros(n, np.uint32)
+    ntpn_min, ntpn_max = ntpn if ntpn is not None else (np.ones(n, np.uint32), np.ones(n, np.uint32))
+    req_node, req_task, req_total = views
+    kw = {}
+    if incl is not None:
+        kw.update(incl_off=incl[0], incl_nodes=incl[1])
+    if excl is not None:
+        kw.update(excl_off=excl[0], excl_nodes=excl[1])
+    return Pending(
+        partition, time_limit, submit, node_num, ntasks, ntpn_min, ntpn_max,
+        exclusive if exclusive is not None else np.zeros(n, np.uint8),
+        part_prio, qos_prio,
+        account if account is not None else z32, qos if qos is not None else z32,
+        user if user is not None else z32,
+        mandated if mandated is not None else np.zeros(n, np.float64),
+        req_node, req_task, req_total, **kw)
+
+
+# ---------------------------------------------------------------------------
+# Config 1: 1k x 128, cpu+mem, single partition, FIFO
+# ---------------------------------------------------------------------------
+def config1(n_jobs=1000, n_nodes=128):
+    rng = _rng(1)
+    cluster = make_cluster([(n_nodes, node_row(64, 256 * GiB))])
+    cpus = rng.choice([1, 2, 4, 8], n_jobs)
+    node_num = np.ones(n_jobs, np.uint32)
+    views = _views(n_jobs, cpus * 256, cpus.astype(np.uint64) * 2 * GiB, node_num, node_num)
+    pend = _pending(n_jobs, np.zeros(n_jobs, np.uint32), rng.integers(60, 3601, n_jobs),
+                    np.full(n_jobs, NOW - 100, np.int64), node_num, node_num, views,
+                    np.full(n_jobs, 1000, np.uint32), np.full(n_jobs, 1000, np.uint32))
+    cfg = Config(priority_type=0, scheduled_batch_size=100_000)
+    return cfg, cluster, Running.empty(), pend, NOW
+
+
+# ---------------------------------------------------------------------------
+# Config 2: 100k x 10k, cpu+mem+gres(GPU), 4 partitions, multifactor+backfill
+# ---------------------------------------------------------------------------
+CONFIG2_WEIGHTS = dict(weight_age=500, weight_fair_share=10000, weight_job_size=0,
+                       weight_partition=1000, weight_qos=1_000_000, favor_small=True,
+                       max_age_s=7 * DAY)  # etc/config.yaml:96-106
+
+
+def config2(n_jobs=100_000, n_nodes=10_000, seed_id=2, limit=None):
+    rng = _rng(seed_id)
+    frac = np.array([0.4, 0.3, 0.2, 0.1])
+    counts = np.maximum((frac * n_nodes).astype(int), 1)
+    groups = [
+        (counts[0], node_row(64, 256 * GiB)),
+        (counts[1], node_row(128, 512 * GiB)),
+        (counts[2], node_row(64, 512 * GiB, {0: 8})),    # gpu:a100 x8
+        (counts[3], node_row(96, 1024 * GiB, {1: 8})),   # gpu:h100 x8
+    ]
+    cluster = make_cluster(groups, gres_entry_name=(0, 0))
+    part = rng.choice(4, n_jobs, p=counts / counts.sum()).astype(np.uint32)
+    node_num = rng.choice([1, 2, 4, 8], n_jobs, p=[0.85, 0.08, 0.05, 0.02]).astype(np.uint32)
+    cpus = rng.choice([1, 2, 4, 8, 16, 32], n_jobs)
+    mem_per_cpu = rng.integers(2, 5, n_jobs).astype(np.uint64) * GiB
+    gpus = rng.choice([1, 2, 4, 8], n_jobs)
+    typed = rng.random(n_jobs) < 0.5
+    is_gpu = part >= 2
+    gres_total = np.zeros((n_jobs, 8), np.uint16)
+    gres_spec = np.zeros((n_jobs, GRES_ENTRIES), np.uint16)
+    gres_total[is_gpu, 0] = gpus[is_gpu]
+    ent = (part - 2).clip(0, 1)
+    sel = is_gpu & typed
+    gres_spec[np.flatnonzero(sel), ent[sel]] = gpus[sel]
+    views = _views(n_jobs, cpus * 256, cpus.astype(np.uint64) * mem_per_cpu, node_num, node_num,
+                   gres_total, gres_spec)
+    part_prio = np.array([1000, 2000, 3000, 4000], np.uint32)[part]
+    pend = _pending(n_jobs, part, _log_uniform(rng, 60, 48 * 3600, n_jobs),
+                    NOW - rng.integers(0, 7 * DAY + 1, n_jobs), node_num, node_num, views,
+                    part_prio, rng.choice([1000, 2000, 5000], n_jobs).astype(np.uint32),
+                    account=rng.integers(0, 64, n_jobs).astype(np.uint32),
+                    qos=rng.integers(0, 3, n_jobs).astype(np.uint32),
+                    user=rng.integers(0, 512, n_jobs).astype(np.uint32))
+    cfg = Config(priority_type=1, scheduled_batch_size=limit or n_jobs, **CONFIG2_WEIGHTS)
+    return cfg, cluster, Running.empty(), pend, NOW
+
+
+# ---------------------------------------------------------------------------
+# Config 3: 1M x 50k, 16 partitions (QoS/account ids carried; limit lifted)
+# ---------------------------------------------------------------------------
+def config3(n_jobs=1_000_000, n_nodes=50_000, n_parts=16, seed_id=3):
+    rng = _rng(seed_id)
+    per = n_nodes // n_parts
+    kinds = [node_row(64, 256 * GiB), node_row(128, 512 * GiB),
+             node_row(64, 512 * GiB, {0: 8}), node_row(96, 1024 * GiB, {1: 8})]
+    groups = [(per, kinds[p % 4]) for p in range(n_parts)]
+    cluster = make_cluster(groups, gres_entry_name=(0, 0))
+    part = rng.integers(0, n_parts, n_jobs).astype(np.uint32)
+    node_num = rng.choice([1, 2, 4, 8], n_jobs, p=[0.85, 0.08, 0.05, 0.02]).astype(np.uint32)
+    cpus = rng.choice([1, 2, 4, 8, 16, 32], n_jobs)
+    mem_per_cpu = rng.integers(2, 5, n_jobs).astype(np.uint64) * GiB
+    gpus = rng.choice([1, 2, 4, 8], n_jobs)
+    kind = part % 4
+    is_gpu = kind >= 2
+    typed = rng.random(n_jobs) < 0.5
+    gres_total = np.zeros((n_jobs, 8), np.uint16)
+    gres_spec = np.zeros((n_jobs, GRES_ENTRIES), np.uint16)
+    gres_total[is_gpu, 0] = gpus[is_gpu]
+    sel = is_gpu & typed
+    gres_spec[np.flatnonzero(sel), (kind[sel] - 2)] = gpus[sel]
+    views = _views(n_jobs, cpus * 256, cpus.astype(np.uint64) * mem_per_cpu, node_num, node_num,
+                   gres_total, gres_spec)
+    pend = _pending(n_jobs, part, _log_uniform(rng, 60, 48 * 3600, n_jobs),
+                    NOW - rng.integers(0, 7 * DAY + 1, n_jobs), node_num, node_num, views,
+                    (1000 * (1 + part % 4)).astype(np.uint32),
+                    rng.choice([1000, 2000, 5000], n_jobs).astype(np.uint32),
+                    account=rng.integers(0, 64, n_jobs).astype(np.uint32),
+                    qos=rng.integers(0, 8, n_jobs).astype(np.uint32),
+                    user=rng.integers(0, 512, n_jobs).astype(np.uint32))
+    cfg = Config(priority_type=1, scheduled_batch_size=n_jobs, **CONFIG2_WEIGHTS)
+    return cfg, cluster, Running.empty(), pend, NOW
+
+
+# ---------------------------------------------------------------------------
+# Config 4: 500k x 20k heterogeneous gres (GPU/NPU), two gres names per job
+# ---------------------------------------------------------------------------
+def config4(n_jobs=500_000, n_nodes=20_000, seed_id=4):
+    rng = _rng(seed_id)
+    # dictionary: gpu:{a100,h100,l40} = entries 0..2 (name 0); npu:{910b,310p} = 3..4 (name 1)
+    names = (0, 0, 0, 1, 1)
+    per = n_nodes // 5
+    groups = [
+        (per, node_row(64, 512 * GiB, {0: 8})),
+        (per, node_row(96, 1024 * GiB, {1: 8, 3: 8})),
+        (per, node_row(64, 256 * GiB, {2: 4, 0: 4})),
+        (per, node_row(128, 1024 * GiB, {3: 16})),
+        (n_nodes - 4 * per, node_row(64, 512 * GiB, {4: 8, 2: 8})),
+    ]
+    cluster = make_cluster(groups, gres_entry_name=names)
+    part = rng.integers(0, 5, n_jobs).astype(np.uint32)
+    node_num = rng.choice([1, 2, 4], n_jobs, p=[0.9, 0.07, 0.03]).astype(np.uint32)
+    cpus = rng.choice([1, 2, 4, 8, 16], n_jobs)
+    gres_total = np.zeros((n_jobs, 8), np.uint16)
+    gres_spec = np.zeros((n_jobs, GRES_ENTRIES), np.uint16)
+    part_entries = {0: [0], 1: [1, 3], 2: [2, 0], 3: [3], 4: [4, 2]}
+    for p, ents in part_entries.items():
+        idx = np.flatnonzero(part == p)
+        for e in ents:
+            use = rng.random(len(idx)) < (0.8 if e == ents[0] else 0.4)
+            cnt = rng.choice([1, 2, 4], len(idx)).astype(np.uint16)
+            typed = rng.random(len(idx)) < 0.5
+            gres_total[idx[use], names[e]] += cnt[use]
+            gres_spec[idx[use & typed], e] += cnt[use & typed]
+    views = _views(n_jobs, cpus * 256, cpus.astype(np.uint64) * 2 * GiB, node_num, node_num,
+                   gres_total, gres_spec)
+    pend = _pending(n_jobs, part, _log_uniform(rng, 60, 24 * 3600, n_jobs),
+                    NOW - rng.integers(0, 7 * DAY + 1, n_jobs), node_num, node_num, views,
+                    np.full(n_jobs, 1000, np.uint32),
+                    rng.choice([1000, 2000, 5000], n_jobs).astype(np.uint32))
+    cfg = Config(priority_type=1, scheduled_batch_size=n_jobs, **CONFIG2_WEIGHTS)
+    return cfg, cluster, Running.empty(), pend, NOW
+
+
+# ---------------------------------------------------------------------------
+# Config 5: backfill stress, 200k x 5k, one partition, wide walltimes
+# ---------------------------------------------------------------------------
+def config5(n_jobs=200_000, n_nodes=5_000, seed_id=5):
+    rng = _rng(seed_id)
+    cluster = make_cluster([(n_nodes, node_row(64, 256 * GiB))])
+    node_num = np.minimum(rng.zipf(2.0, n_jobs), 64).astype(np.uint32)
+    cpus = rng.choice([1, 2, 4, 8, 16, 32, 64], n_jobs)
+    views = _views(n_jobs, cpus * 256, cpus.astype(np.uint64) * 2 * GiB, node_num, node_num)
+    pend = _pending(n_jobs, np.zeros(n_jobs, np.uint32), _log_uniform(rng, 11, 7 * DAY, n_jobs),
+                    NOW - rng.integers(0, 7 * DAY + 1, n_jobs), node_num, node_num, views,
+                    np.full(n_jobs, 1000, np.uint32),
+                    rng.choice([1000, 2000, 5000], n_jobs).astype(np.uint32))
+    cfg = Config(priority_type=1, scheduled_batch_size=n_jobs, **CONFIG2_WEIGHTS)
+    return cfg, cluster, Running.empty(), pend, NOW
+
+
+# ---------------------------------------------------------------------------
+# Feature-rich small random case for parity tests: running jobs, fractional
+# cpus, typed/untyped gres over two names, include/exclude lists, exclusive
+# jobs, dead/drained nodes, unknown partitions, mandated priorities.
+# ---------------------------------------------------------------------------
+def random_case(seed, n_jobs=300, n_nodes=48, n_parts=3, n_running=40, fifo=False,
+                frac_cpu=True, lists=True, exclusive=True, limit=None,
+                max_jobs_per_node=1000, short=False):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    names = (0, 0, 1)  # gpu:a, gpu:b, npu:x
+    kinds = [node_row(16, 64 * GiB), node_row(32, 128 * GiB, {0: 4, 1: 4}),
+             node_row(24, 96 * GiB, {0: 2, 2: 8}), node_row(8, 32 * GiB, {1: 8})]
+    sizes = rng.multinomial(n_nodes - n_parts, np.ones(n_parts) / n_parts) + 1
+    rows, off, base = [], [0], 0
+    for p in range(n_parts):
+        k = rng.integers(0, len(kinds), sizes[p])
+        rows.append(np.stack([kinds[i] for i in k]))
+        base += sizes[p]
+        off.append(base)
+    res_total = np.concatenate(rows)
+    alive = (rng.random(n_nodes) > 0.05).astype(np.uint8)
+    drain = (rng.random(n_nodes) < 0.05).astype(np.uint8)
+    cluster = Cluster(res_total, alive, drain, np.array(off, np.uint32),
+                      np.arange(n_nodes, dtype=np.uint32), len(names), names)
+    node_part = np.repeat(np.arange(n_parts), sizes)
+
+    def gres_req(n, parts):
+        tot = np.zeros((n, 8), np.uint16)
+        spec = np.zeros((n, GRES_ENTRIES), np.uint16)
+        for i in range(n):
+            if rng.random() < 0.5:
+                continue
+            for g, ents in ((0, (0, 1)), (1, (2,))):
+                if rng.random() < 0.5:
+                    continue
+                t = 0
+                for e in ents:
+                    if rng.random() < 0.4:
+                        c = int(rng.integers(1, 4))
+                        spec[i, e] = c
+                        t += c
+                tot[i, g] = t + (int(rng.integers(0, 3)) if rng.random() < 0.6 else 0)
+                if tot[i, g] == 0:
+                    tot[i, g] = 1
+        return tot, spec
+
+    # running jobs: carve allocations out of node totals with a host-side
+    # first-fit so that they are consistent (alloc <= what is left).
+    left = res_total.copy()
+    r_start, r_end, r_nn, r_pp, r_qp, r_acc, r_cpu, r_mem = [], [], [], [], [], [], [], []
+    r_off, r_node, r_res = [0], [], []
+    for _ in range(n_running):
+        nn = int(rng.choice([1, 1, 1, 2]))
+        nodes = rng.choice(n_nodes, nn, replace=False)
+        ok_nodes, rowsj = [], []
+        for nd in nodes:
+            cores = int(rng.integers(1, 5))
+            row = np.zeros((), RES_IN_NODE)
+            avail_bits = [b for b in range(64) if int(left[nd]["core"][0]) >> b & 1]
+            mem = int(rng.integers(1, 9)) * GiB
+            if len(avail_bits) < cores or int(left[nd]["mem"]) < mem:
+                continue
+            if frac_cpu and rng.random() < 0.2:
+                row["cpu_raw"] = cores * 256 - 128  # fractional: no cores bound
+            else:
+                row["cpu_raw"] = cores * 256
+                m = 0
+                for b in avail_bits[:cores]:
+                    m |= 1 << b
+                row["core"][0] = m
+            row["mem"] = mem
+            row["mem_sw"] = mem
+            for e in range(len(names)):
+                have = int(left[nd]["gres"][e])
+                if have and rng.random() < 0.4:
+                    low = have & -have
+                    row["gres"][e] = low
+            if int(left[nd]["cpu_raw"]) < int(row["cpu_raw"]):
+                continue
+            left[nd]["cpu_raw"] -= row["cpu_raw"]
+            left[nd]["mem"] -= row["mem"]
+            left[nd]["mem_sw"] -= row["mem_sw"]
+            left[nd]["core"][0] &= ~row["core"][0]
+            left[nd]["gres"] &= ~row["gres"]
+            ok_nodes.append(nd)
+            rowsj.append(row)
+        if not ok_nodes:
+            continue
+        order = np.argsort(ok_nodes)
+        for o in order:
+            r_node.append(ok_nodes[o])
+            r_res.append(rowsj[o])
+        r_off.append(len(r_node))
+        st = NOW - int(rng.integers(1, 5000))
+        r_start.append(st)
+        r_end.append(NOW + int(rng.integers(-10, 20000)))
+        r_nn.append(len(ok_nodes))
+        r_pp.append(int(rng.choice([1000, 2000])))
+        r_qp.append(int(rng.choice([1000, 5000])))
+        r_acc.append(int(rng.integers(0, 6)))
+        r_cpu.append(sum(int(r["cpu_raw"]) for r in rowsj))
+        r_mem.append(sum(int(r["mem"]) for r in rowsj))
+    running = Running(r_start, r_end, r_nn, r_pp, r_qp, r_acc, r_cpu, r_mem, r_off,
+                      np.array(r_node, np.uint32),
+                      np.array(r_res, RES_IN_NODE) if r_res else np.zeros(0, RES_IN_NODE))
+
+    part = rng.integers(0, n_parts, n_jobs).astype(np.uint32)
+    part[rng.random(n_jobs) < 0.02] = n_parts + 3  # "Partition Not Found"
+    node_num = rng.choice([1, 1, 1, 2, 3, 5], n_jobs).astype(np.uint32)
+    cpus_raw = rng.choice([1, 1, 2, 2, 4, 8, 16], n_jobs) * 256
+    if frac_cpu:
+        fr = rng.random(n_jobs) < 0.15
+        cpus_raw[fr] = rng.choice([64, 128, 384, 640], int(fr.sum()))
+    tpn = np.ones(n_jobs, np.uint32)
+    multi = rng.random(n_jobs) < 0.2
+    tpn[multi] = rng.integers(2, 4, int(multi.sum()))
+    ntasks = node_num * tpn
+    gt, gs = gres_req(n_jobs, part)
+    mem_task = rng.integers(1, 9, n_jobs).astype(np.uint64) * GiB // 2
+    mem_node = np.where(rng.random(n_jobs) < 0.2, rng.integers(0, 4, n_jobs), 0).astype(np.uint64) * GiB
+    views = _views(n_jobs, cpus_raw, mem_task, node_num, ntasks, gt, gs, mem_node)
+    excl_flag = ((rng.random(n_jobs) < 0.05) & exclusive).astype(np.uint8)
+    incl = excl = None
+    if lists:
+        io, inodes, eo, enodes = [0], [], [0], []
+        for i in range(n_jobs):
+            p = part[i]
+            cand = np.flatnonzero(node_part == p) if p < n_parts else np.zeros(0, int)
+            if len(cand) and rng.random() < 0.08:
+                k = int(rng.integers(int(node_num[i]), len(cand) + 1)) if len(cand) >= node_num[i] else len(cand)
+                inodes += sorted(rng.choice(cand, max(k, 1), replace=False).tolist())
+            io.append(len(inodes))
+            if len(cand) and rng.random() < 0.08:
+                k = int(rng.integers(1, max(2, len(cand) // 2)))
+                enodes += sorted(rng.choice(cand, k, replace=False).tolist())
+            eo.append(len(enodes))
+        incl = (np.array(io, np.uint32), np.array(inodes, np.uint32))
+        excl = (np.array(eo, np.uint32), np.array(enodes, np.uint32))
+    mand = np.where(rng.random(n_jobs) < 0.03, rng.uniform(1, 2e6, n_jobs), 0.0)
+    tl = _log_uniform(rng, 11, 3600 if short else 9 * DAY, n_jobs)
+    pend = _pending(n_jobs, part, tl, NOW - rng.integers(0, 9 * DAY, n_jobs), node_num, ntasks,
+                    views, rng.choice([1000, 2000, 3000], n_jobs).astype(np.uint32),
+                    rng.choice([1000, 2000, 5000], n_jobs).astype(np.uint32),
+                    account=rng.integers(0, 6, n_jobs).astype(np.uint32),
+                    qos=rng.integers(0, 3, n_jobs).astype(np.uint32),
+                    user=rng.integers(0, 20, n_jobs).astype(np.uint32),
+                    exclusive=excl_flag, ntpn=(tpn, tpn.copy()), mandated=mand,
+                    incl=incl, excl=excl)
+    cfg = Config(priority_type=0 if fifo else 1, scheduled_batch_size=limit or n_jobs,
+                 max_jobs_per_node=max_jobs_per_node,
+                 weight_age=500, weight_fair_share=10000, weight_job_size=300,
+                 weight_partition=1000, weight_qos=1_000_000, favor_small=bool(seed & 1))
+    return cfg, cluster, running, pend, NOW
+
+
+CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5}
