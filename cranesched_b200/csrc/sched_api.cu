@@ -1,0 +1,708 @@
+// sched_api.cu — C-ABI of the B200 scheduling hot path (include/crane_sched.h).
+//
+// Host side of the drop-in boundary behind SchedulerAlgo::NodeSelect
+// (reference: src/CraneCtld/JobScheduler.cpp:1141, 5543-5868). This file only
+// validates, lays tables out in HBM and launches kernels; every scheduling
+// decision is taken on the device (sched_kernels.cuh). There is no CPU path:
+// without a CUDA device crane_sched_create() fails with CRANE_ENODEV.
+//
+// Built two ways:
+//   nvcc -gencode arch=compute_100a,code=sm_100a  -> libcrane_sched.so (product)
+//   g++ -DCRANE_EMU (tests/cuda_emu)               -> tests/_emu/libcrane_sched_emu.so
+//     a kernel-emulation harness used only by the CPU-side unit tests.
+#ifdef CRANE_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/crane_sched.h"
+#include "sched_kernels.cuh"
+
+using namespace crane;
+
+namespace {
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 16;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+constexpr size_t kMaxDynSmem = 220 * 1024;
+
+}  // namespace
+
+struct crane_sched {
+  crane_sched_config_t cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8]{};
+  std::string err;
+  crane_sched_timing_t timing{};
+  int commit_threads = 512;
+
+  // cluster (host copies)
+  bool have_cluster = false;
+  uint32_t n_nodes = 0, n_parts = 0, n_slots = 0, max_part_slots = 0, words_per_row = 0;
+  std::vector<uint32_t> h_part_base, h_slot_node, h_node_slot;
+  GresDict dict{};
+  uint32_t tl_cap = 0;
+
+  // cluster (device)
+  DBuf<uint32_t> d_part_base, d_slot_node, d_node_slot;
+  DBuf<Row> d_slot_total;
+  // timelines
+  DBuf<uint32_t> d_tl_n;
+  DBuf<int64_t> d_tl_time;
+  DBuf<Row> d_tl_seg, d_tl_pm, d_avail0, d_scratch;
+  DBuf<double> d_cost0;
+  DBuf<uint8_t> d_skip;
+
+  // pending (device)
+  uint32_t n_pending = 0, n_running = 0, n_accounts = 0;
+  uint64_t total_alloc = 0;
+  bool have_lists_incl = false, have_lists_excl = false, have_mandated = false;
+  std::vector<uint32_t> h_alloc_off;
+  DBuf<uint32_t> d_partition, d_node_num, d_ntpn, d_part_prio, d_qos_prio, d_account, d_alloc_off;
+  DBuf<int64_t> d_time_limit, d_submit;
+  DBuf<uint8_t> d_exclusive;
+  DBuf<double> d_mandated;
+  DBuf<View> d_req_node, d_req_task, d_req_total;
+  DBuf<uint32_t> d_incl_off, d_incl_nodes, d_excl_off, d_excl_nodes;
+  // running (device)
+  DBuf<int64_t> d_rn_start, d_rn_end, d_rn_cpu, d_rn_slot_end;
+  DBuf<uint32_t> d_rn_node_num, d_rn_part_prio, d_rn_qos_prio, d_rn_account, d_rn_slot_off, d_rn_acc_off, d_rn_acc_job;
+  DBuf<uint64_t> d_rn_mem;
+  DBuf<Row> d_rn_slot_res;
+  DBuf<uint8_t> d_acc_present;
+  // work buffers
+  DBuf<Bounds> d_bounds;
+  DBuf<double> d_acc_service, d_prio;
+  DBuf<uint64_t> d_keys_a, d_keys_b;
+  DBuf<uint32_t> d_vals_a, d_vals_b, d_hist, d_part_count, d_part_job_off, d_bitmap;
+  DBuf<JobQ> d_jobq;
+  uint32_t* d_queue = nullptr;  // points into vals_a / vals_b after the sorts
+  // outputs (device)
+  DBuf<uint8_t> d_reason;
+  DBuf<double> d_out_prio;
+  DBuf<int64_t> d_out_start, d_out_end;
+  DBuf<uint32_t> d_out_nalloc, d_out_node, d_out_ntasks;
+  DBuf<Row> d_out_res;
+  bool uploaded = false, ran = false;
+};
+
+namespace {
+
+int fail(crane_sched* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(h, e__ == 2 ? CRANE_ENOMEM : CRANE_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+template <class T>
+int h2d(crane_sched* h, DBuf<T>& dst, const T* src, size_t n) {
+  CU(dst.ensure(n ? n : 1));
+  if (n) CU(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  return CRANE_OK;
+}
+#define H2D(buf, src, n)                      \
+  do {                                        \
+    int rc__ = h2d(h, buf, src, (size_t)(n)); \
+    if (rc__ != CRANE_OK) return rc__;        \
+  } while (0)
+
+// stable LSD radix sort over bits [0, nbits) of d_keys_a with payload
+// d_vals_a; result pointers returned in keys/vals.
+int radix_sort(crane_sched* h, uint32_t n, int nbits, uint64_t** keys, uint32_t** vals) {
+  uint64_t* ka = h->d_keys_a.p;
+  uint64_t* kb = h->d_keys_b.p;
+  uint32_t* va = h->d_vals_a.p;
+  uint32_t* vb = h->d_vals_b.p;
+  uint32_t nblocks = (n + kSortTile - 1) / kSortTile;
+  CU(h->d_hist.ensure((size_t)256 * nblocks));
+  for (int shift = 0; shift < nbits; shift += 8) {
+    CRANE_LAUNCH(k_sort_hist, nblocks, 256, 0, h->stream, ka, n, shift, h->d_hist.p, nblocks);
+    CRANE_LAUNCH(k_sort_scan, 1, 1024, 0, h->stream, h->d_hist.p, 256u * nblocks);
+    CRANE_LAUNCH(k_sort_scatter, nblocks, 32, 0, h->stream, ka, va, kb, vb, n, shift, h->d_hist.p, nblocks);
+    h->timing.kernel_launches += 3;
+    std::swap(ka, kb);
+    std::swap(va, vb);
+  }
+  *keys = ka;
+  *vals = va;
+  return CRANE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* crane_sched_last_error(const crane_sched_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+int crane_sched_create(const crane_sched_config_t* cfg, int device, crane_sched_t** out) {
+  if (!cfg || !out) return CRANE_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return CRANE_ENODEV;
+  if (cfg->max_jobs_per_node < 2 || cfg->max_jobs_per_node > 65000) return CRANE_EINVAL;
+  if (cfg->cost_policy != 0) return CRANE_ENOSYS;
+  crane_sched* h = new crane_sched();
+  h->cfg = *cfg;
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return CRANE_ENODEV;
+  }
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  if (const char* s = getenv("CRANE_COMMIT_THREADS")) {
+    int t = atoi(s);
+    if (t >= 64 && t <= 512 && t % 32 == 0) h->commit_threads = t;
+  }
+#ifdef CRANE_EMU
+  if (!getenv("CRANE_COMMIT_THREADS")) h->commit_threads = 128;
+#endif
+  cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  h->tl_cap = cfg->max_jobs_per_node + 1;
+  *out = h;
+  return CRANE_OK;
+}
+
+void crane_sched_destroy(crane_sched_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+#define REL(b) h->b.release()
+  REL(d_part_base); REL(d_slot_node); REL(d_node_slot); REL(d_slot_total); REL(d_tl_n); REL(d_tl_time);
+  REL(d_tl_seg); REL(d_tl_pm); REL(d_avail0); REL(d_scratch); REL(d_cost0); REL(d_skip); REL(d_partition);
+  REL(d_node_num); REL(d_ntpn); REL(d_part_prio); REL(d_qos_prio); REL(d_account); REL(d_alloc_off);
+  REL(d_time_limit); REL(d_submit); REL(d_exclusive); REL(d_mandated); REL(d_req_node); REL(d_req_task);
+  REL(d_req_total); REL(d_incl_off); REL(d_incl_nodes); REL(d_excl_off); REL(d_excl_nodes); REL(d_rn_start);
+  REL(d_rn_end); REL(d_rn_cpu); REL(d_rn_slot_end); REL(d_rn_node_num); REL(d_rn_part_prio); REL(d_rn_qos_prio);
+  REL(d_rn_account); REL(d_rn_slot_off); REL(d_rn_acc_off); REL(d_rn_acc_job); REL(d_rn_mem); REL(d_rn_slot_res);
+  REL(d_acc_present); REL(d_bounds); REL(d_acc_service); REL(d_prio); REL(d_keys_a); REL(d_keys_b); REL(d_vals_a);
+  REL(d_vals_b); REL(d_hist); REL(d_part_count); REL(d_part_job_off); REL(d_bitmap); REL(d_jobq); REL(d_reason);
+  REL(d_out_prio); REL(d_out_start); REL(d_out_end); REL(d_out_nalloc); REL(d_out_node); REL(d_out_ntasks);
+  REL(d_out_res);
+#undef REL
+  for (auto& e : h->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
+  if (!h || !c) return CRANE_EINVAL;
+  if (!c->res_total || !c->alive || !c->drain || !c->part_off || (!c->part_nodes && c->n_nodes))
+    return fail(h, CRANE_EINVAL, "cluster: null table");
+  if (c->n_gres_entries > CRANE_GRES_ENTRIES) return fail(h, CRANE_EINVAL, "cluster: too many gres entries");
+  for (uint32_t e = 0; e < c->n_gres_entries; ++e) {
+    if (c->gres_entry_name[e] >= CRANE_GRES_NAMES) return fail(h, CRANE_EINVAL, "cluster: gres name id out of range");
+    if (e && c->gres_entry_name[e] < c->gres_entry_name[e - 1])
+      return fail(h, CRANE_EINVAL, "cluster: gres entries must be grouped by ascending name id");
+  }
+  CU(cudaSetDevice(h->device));
+  h->have_cluster = false;
+  h->n_nodes = c->n_nodes;
+  h->n_parts = c->n_partitions;
+  h->dict.n_entries = c->n_gres_entries;
+  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) h->dict.entry_name[e] = c->gres_entry_name[e];
+  h->h_node_slot.assign(c->n_nodes, 0xffffffffu);
+  h->h_part_base.assign(c->n_partitions + 1, 0);
+  h->h_slot_node.clear();
+  std::vector<uint8_t> seen(c->n_nodes, 0);
+  std::vector<Row> slot_total;
+  uint32_t max_mp = 0;
+  for (uint32_t p = 0; p < c->n_partitions; ++p) {
+    h->h_part_base[p] = (uint32_t)h->h_slot_node.size();
+    uint32_t prev = 0;
+    for (uint32_t k = c->part_off[p]; k < c->part_off[p + 1]; ++k) {
+      uint32_t n = c->part_nodes[k];
+      if (n >= c->n_nodes) return fail(h, CRANE_EINVAL, "cluster: node index %u out of range", n);
+      if (k > c->part_off[p] && n <= prev) return fail(h, CRANE_EINVAL, "cluster: partition %u node list must be ascending", p);
+      prev = n;
+      // a node shared by two partitions couples their timelines (shared
+      // NodeState, JobScheduler.cpp:5622); that is SURVEY.md §8f rank 3.
+      if (seen[n]) return fail(h, CRANE_ENOSYS, "cluster: node %u is in more than one partition (overlapping partitions are not built yet)", n);
+      seen[n] = 1;
+      if (!c->alive[n] || c->drain[n]) continue;  // JobScheduler.cpp:5629
+      const Row& t = c->res_total[n];
+      if (t.cpu_raw < 0 || t.cpu_raw > (int64_t)1 << 40) return fail(h, CRANE_EINVAL, "cluster: node %u cpu out of range", n);
+      for (uint32_t e = c->n_gres_entries; e < CRANE_GRES_ENTRIES; ++e)
+        if (t.gres[e]) return fail(h, CRANE_EINVAL, "cluster: node %u has slots for an undeclared gres entry", n);
+      h->h_node_slot[n] = (uint32_t)h->h_slot_node.size();
+      h->h_slot_node.push_back(n);
+      slot_total.push_back(t);
+    }
+    uint32_t mp = (uint32_t)h->h_slot_node.size() - h->h_part_base[p];
+    max_mp = std::max(max_mp, mp);
+  }
+  h->h_part_base[c->n_partitions] = (uint32_t)h->h_slot_node.size();
+  h->n_slots = (uint32_t)h->h_slot_node.size();
+  h->max_part_slots = max_mp;
+  h->words_per_row = std::max<uint32_t>(1, (max_mp + 31) / 32);
+  if (max_mp > 65535 || commit_smem_bytes(max_mp, h->words_per_row) > kMaxDynSmem)
+    return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
+
+  H2D(h->d_part_base, h->h_part_base.data(), h->h_part_base.size());
+  H2D(h->d_slot_node, h->h_slot_node.data(), h->h_slot_node.size());
+  H2D(h->d_node_slot, h->h_node_slot.data(), h->h_node_slot.size());
+  H2D(h->d_slot_total, slot_total.data(), slot_total.size());
+  CU(cudaMemcpyToSymbolAsync(c_dict, &h->dict, sizeof(GresDict), 0, cudaMemcpyHostToDevice, h->stream));
+  size_t ns = std::max<uint32_t>(h->n_slots, 1);
+  CU(h->d_tl_n.ensure(ns));
+  CU(h->d_tl_time.ensure(ns * h->tl_cap));
+  CU(h->d_tl_seg.ensure(ns * h->tl_cap));
+  CU(h->d_tl_pm.ensure(ns * h->tl_cap));
+  CU(h->d_avail0.ensure(ns));
+  CU(h->d_scratch.ensure(ns));
+  CU(h->d_cost0.ensure(ns));
+  CU(h->d_skip.ensure(ns));
+  CU(h->d_part_count.ensure(h->n_parts + 2));
+  CU(h->d_part_job_off.ensure(h->n_parts + 2));
+  CU(cudaStreamSynchronize(h->stream));
+  h->have_cluster = true;
+  h->uploaded = false;
+  return CRANE_OK;
+}
+
+int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_pending_t* pd) {
+  if (!h || !pd) return CRANE_EINVAL;
+  if (!h->have_cluster) return fail(h, CRANE_EINVAL, "upload: set_cluster first");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->ev[0], h->stream));
+  const uint32_t N = pd->n;
+  const uint32_t R = rn ? rn->n : 0;
+  if (N && (!pd->partition || !pd->time_limit || !pd->submit_time || !pd->node_num || !pd->ntasks ||
+            !pd->ntasks_per_node_min || !pd->ntasks_per_node_max || !pd->exclusive || !pd->partition_priority ||
+            !pd->qos_priority || !pd->account || !pd->req_node || !pd->req_task || !pd->req_total))
+    return fail(h, CRANE_EINVAL, "pending: null column");
+  // ---- validation + alloc_off (prefix sum of node_num) --------------------
+  h->h_alloc_off.resize((size_t)N + 1);
+  uint64_t acc = 0;
+  uint32_t max_account = 0;
+  for (uint32_t i = 0; i < N; ++i) {
+    h->h_alloc_off[i] = (uint32_t)acc;
+    if (pd->node_num[i] == 0) return fail(h, CRANE_EINVAL, "pending[%u]: node_num == 0", i);
+    if (pd->time_limit[i] < 1) return fail(h, CRANE_EINVAL, "pending[%u]: time_limit < 1", i);
+    uint32_t t = pd->ntasks_per_node_min[i];
+    // general task distribution (ntasks_per_node_max > min; top-k heap of
+    // JobScheduler.cpp:5193-5205) is SURVEY.md §8f rank 2
+    if (t == 0 || t != pd->ntasks_per_node_max[i] || (uint64_t)t * pd->node_num[i] != pd->ntasks[i])
+      return fail(h, CRANE_ENOSYS, "pending[%u]: only ntasks_per_node_min == max and ntasks == node_num*ntasks_per_node are built", i);
+    if (pd->req_node[i].cpu_raw < 0 || pd->req_task[i].cpu_raw < 0)
+      return fail(h, CRANE_EINVAL, "pending[%u]: negative cpu request", i);
+    acc += pd->node_num[i];
+    if (acc > 0xfffffff0ull) return fail(h, CRANE_EINVAL, "pending: sum(node_num) overflows");
+    max_account = std::max(max_account, pd->account[i]);
+  }
+  h->h_alloc_off[N] = (uint32_t)acc;
+  h->total_alloc = acc;
+  if ((pd->incl_off && !pd->incl_nodes && pd->incl_off[N]) || (pd->excl_off && !pd->excl_nodes && pd->excl_off[N]))
+    return fail(h, CRANE_EINVAL, "pending: node list CSR without node array");
+  for (uint32_t k = 0; k < R; ++k) max_account = std::max(max_account, rn->account[k]);
+  if (max_account > (1u << 24)) return fail(h, CRANE_EINVAL, "account ids must be dense (< 2^24)");
+  const uint32_t A = (N + R) ? max_account + 1 : 0;
+
+  // ---- pending columns -----------------------------------------------------
+  H2D(h->d_partition, pd->partition, N);
+  H2D(h->d_time_limit, pd->time_limit, N);
+  H2D(h->d_submit, pd->submit_time, N);
+  H2D(h->d_node_num, pd->node_num, N);
+  H2D(h->d_ntpn, pd->ntasks_per_node_min, N);
+  H2D(h->d_exclusive, pd->exclusive, N);
+  H2D(h->d_part_prio, pd->partition_priority, N);
+  H2D(h->d_qos_prio, pd->qos_priority, N);
+  H2D(h->d_account, pd->account, N);
+  h->have_mandated = pd->mandated_priority != nullptr;
+  if (h->have_mandated) H2D(h->d_mandated, pd->mandated_priority, N);
+  H2D(h->d_req_node, reinterpret_cast<const View*>(pd->req_node), N);
+  H2D(h->d_req_task, reinterpret_cast<const View*>(pd->req_task), N);
+  H2D(h->d_req_total, reinterpret_cast<const View*>(pd->req_total), N);
+  H2D(h->d_alloc_off, h->h_alloc_off.data(), N + 1);
+  h->have_lists_incl = pd->incl_off != nullptr;
+  h->have_lists_excl = pd->excl_off != nullptr;
+  if (h->have_lists_incl) {
+    for (uint32_t k = 0; k < pd->incl_off[N]; ++k)
+      if (pd->incl_nodes[k] >= h->n_nodes) return fail(h, CRANE_EINVAL, "pending: included node out of range");
+    H2D(h->d_incl_off, pd->incl_off, N + 1);
+    H2D(h->d_incl_nodes, pd->incl_nodes, pd->incl_off[N]);
+  }
+  if (h->have_lists_excl) {
+    H2D(h->d_excl_off, pd->excl_off, N + 1);
+    H2D(h->d_excl_nodes, pd->excl_nodes, pd->excl_off[N]);
+  }
+
+  // ---- running jobs: columns + regrouping by node slot and by account ------
+  // (flattening of RnJobInScheduler::allocated_res; order inside a node /
+  // account is input order, deviation D6)
+  std::vector<uint32_t> slot_off((size_t)h->n_slots + 1, 0), acc_off((size_t)A + 1, 0), acc_job(R);
+  std::vector<uint8_t> acc_present(std::max<uint32_t>(A, 1), 0);
+  std::vector<int64_t> slot_end;
+  std::vector<Row> slot_res;
+  for (uint32_t i = 0; i < N; ++i) acc_present[pd->account[i]] = 1;
+  if (R) {
+    if (!rn->start_time || !rn->end_time || !rn->node_num || !rn->partition_priority || !rn->qos_priority ||
+        !rn->account || !rn->view_cpu_raw || !rn->view_mem || !rn->alloc_off)
+      return fail(h, CRANE_EINVAL, "running: null column");
+    const uint32_t E = rn->alloc_off[R];
+    if (E && (!rn->alloc_node || !rn->alloc_res)) return fail(h, CRANE_EINVAL, "running: null allocation table");
+    for (uint32_t j = 0; j < R; ++j) {
+      acc_present[rn->account[j]] = 1;
+      acc_off[rn->account[j] + 1]++;
+      for (uint32_t k = rn->alloc_off[j]; k < rn->alloc_off[j + 1]; ++k) {
+        uint32_t n = rn->alloc_node[k];
+        if (n >= h->n_nodes) return fail(h, CRANE_EINVAL, "running[%u]: node out of range", j);
+        uint32_t g = h->h_node_slot[n];
+        if (g != 0xffffffffu) slot_off[g + 1]++;  // nodes outside node_state_map are ignored (JS.cpp:5719)
+      }
+    }
+    for (uint32_t g = 0; g < h->n_slots; ++g) slot_off[g + 1] += slot_off[g];
+    for (uint32_t a = 0; a < A; ++a) acc_off[a + 1] += acc_off[a];
+    slot_end.resize(slot_off[h->n_slots]);
+    slot_res.resize(slot_off[h->n_slots]);
+    std::vector<uint32_t> fill_s(slot_off.begin(), slot_off.end() - 1), fill_a(acc_off.begin(), acc_off.end() - 1);
+    for (uint32_t j = 0; j < R; ++j) {
+      acc_job[fill_a[rn->account[j]]++] = j;
+      for (uint32_t k = rn->alloc_off[j]; k < rn->alloc_off[j + 1]; ++k) {
+        uint32_t g = h->h_node_slot[rn->alloc_node[k]];
+        if (g == 0xffffffffu) continue;
+        uint32_t dst = fill_s[g]++;
+        slot_end[dst] = rn->end_time[j];
+        slot_res[dst] = rn->alloc_res[k];
+      }
+    }
+    H2D(h->d_rn_start, rn->start_time, R);
+    H2D(h->d_rn_end, rn->end_time, R);
+    H2D(h->d_rn_node_num, rn->node_num, R);
+    H2D(h->d_rn_part_prio, rn->partition_priority, R);
+    H2D(h->d_rn_qos_prio, rn->qos_priority, R);
+    H2D(h->d_rn_account, rn->account, R);
+    H2D(h->d_rn_cpu, rn->view_cpu_raw, R);
+    H2D(h->d_rn_mem, rn->view_mem, R);
+    H2D(h->d_rn_slot_off, slot_off.data(), slot_off.size());
+    H2D(h->d_rn_slot_end, slot_end.data(), slot_end.size());
+    H2D(h->d_rn_slot_res, slot_res.data(), slot_res.size());
+    H2D(h->d_rn_acc_off, acc_off.data(), acc_off.size());
+    H2D(h->d_rn_acc_job, acc_job.data(), acc_job.size());
+  }
+  H2D(h->d_acc_present, acc_present.data(), acc_present.size());
+  // staging vectors above are pageable: the copies have completed on return,
+  // but make it explicit before they go out of scope
+  CU(cudaStreamSynchronize(h->stream));
+  h->n_pending = N;
+  h->n_running = R;
+  h->n_accounts = A;
+
+  // ---- work + output buffers ----------------------------------------------
+  size_t n1 = std::max<uint32_t>(N, 1);
+  CU(h->d_bounds.ensure(1));
+  CU(h->d_acc_service.ensure(std::max<uint32_t>(A, 1)));
+  CU(h->d_prio.ensure(n1));
+  CU(h->d_keys_a.ensure(n1));
+  CU(h->d_keys_b.ensure(n1));
+  CU(h->d_vals_a.ensure(n1));
+  CU(h->d_vals_b.ensure(n1));
+  uint32_t nq = std::min<uint32_t>(N, h->cfg.scheduled_batch_size);
+  CU(h->d_jobq.ensure(std::max<uint32_t>(nq, 1)));
+  CU(h->d_bitmap.ensure((size_t)std::max<uint32_t>(nq, 1) * h->words_per_row));
+  CU(h->d_reason.ensure(n1));
+  CU(h->d_out_prio.ensure(n1));
+  CU(h->d_out_start.ensure(n1));
+  CU(h->d_out_end.ensure(n1));
+  CU(h->d_out_nalloc.ensure(n1));
+  size_t ta = std::max<uint64_t>(h->total_alloc, 1);
+  CU(h->d_out_node.ensure(ta));
+  CU(h->d_out_ntasks.ensure(ta));
+  CU(h->d_out_res.ensure(ta));
+  CU(cudaEventRecord(h->ev[1], h->stream));
+  h->uploaded = true;
+  h->ran = false;
+  return CRANE_OK;
+}
+
+int crane_sched_run(crane_sched_t* h, int64_t now) {
+  if (!h) return CRANE_EINVAL;
+  if (!h->uploaded) return fail(h, CRANE_EINVAL, "run: upload first");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const uint32_t N = h->n_pending, R = h->n_running;
+  h->timing.kernel_launches = 0;
+
+  PendingDev pd{};
+  pd.n = N;
+  pd.partition = h->d_partition.p;
+  pd.time_limit = h->d_time_limit.p;
+  pd.submit_time = h->d_submit.p;
+  pd.node_num = h->d_node_num.p;
+  pd.ntasks_per_node_min = h->d_ntpn.p;
+  pd.exclusive = h->d_exclusive.p;
+  pd.partition_priority = h->d_part_prio.p;
+  pd.qos_priority = h->d_qos_prio.p;
+  pd.account = h->d_account.p;
+  pd.mandated_priority = h->have_mandated ? h->d_mandated.p : nullptr;
+  pd.req_node = h->d_req_node.p;
+  pd.req_task = h->d_req_task.p;
+  pd.req_total = h->d_req_total.p;
+  pd.incl_off = h->have_lists_incl ? h->d_incl_off.p : nullptr;
+  pd.incl_nodes = h->d_incl_nodes.p;
+  pd.excl_off = h->have_lists_excl ? h->d_excl_off.p : nullptr;
+  pd.excl_nodes = h->d_excl_nodes.p;
+  pd.alloc_off = h->d_alloc_off.p;
+
+  RunningDev rn{};
+  rn.n = R;
+  rn.start_time = h->d_rn_start.p;
+  rn.end_time = h->d_rn_end.p;
+  rn.node_num = h->d_rn_node_num.p;
+  rn.partition_priority = h->d_rn_part_prio.p;
+  rn.qos_priority = h->d_rn_qos_prio.p;
+  rn.account = h->d_rn_account.p;
+  rn.view_cpu_raw = h->d_rn_cpu.p;
+  rn.view_mem = h->d_rn_mem.p;
+  rn.slot_off = h->d_rn_slot_off.p;
+  rn.slot_end = h->d_rn_slot_end.p;
+  rn.slot_res = h->d_rn_slot_res.p;
+  rn.n_accounts = h->n_accounts;
+  rn.acc_off = h->d_rn_acc_off.p;
+  rn.acc_job = h->d_rn_acc_job.p;
+  rn.acc_present = h->d_acc_present.p;
+
+  ClusterDev cl{};
+  cl.n_slots = h->n_slots;
+  cl.n_parts = h->n_parts;
+  cl.max_part_slots = h->max_part_slots;
+  cl.part_base = h->d_part_base.p;
+  cl.slot_node = h->d_slot_node.p;
+  cl.node_slot = h->d_node_slot.p;
+  cl.slot_total = h->d_slot_total.p;
+
+  TimelineDev tl{};
+  tl.cap = h->tl_cap;
+  tl.n = h->d_tl_n.p;
+  tl.time = h->d_tl_time.p;
+  tl.seg = h->d_tl_seg.p;
+  tl.pm = h->d_tl_pm.p;
+  tl.avail0 = h->d_avail0.p;
+  tl.cost0 = h->d_cost0.p;
+  tl.skip = h->d_skip.p;
+
+  PlaceDev out{};
+  out.reason = h->d_reason.p;
+  out.priority = h->d_out_prio.p;
+  out.start_time = h->d_out_start.p;
+  out.end_time = h->d_out_end.p;
+  out.n_alloc = h->d_out_nalloc.p;
+  out.alloc_node = h->d_out_node.p;
+  out.alloc_ntasks = h->d_out_ntasks.p;
+  out.alloc_res = h->d_out_res.p;
+
+  // ---- node state / timelines (R2,R3,R4) -----------------------------------
+  CU(cudaEventRecord(h->ev[2], st));
+  if (h->total_alloc) {  // allocation slots of jobs without a placement read as zero
+    CU(cudaMemsetAsync(h->d_out_node.p, 0, sizeof(uint32_t) * h->total_alloc, st));
+    CU(cudaMemsetAsync(h->d_out_ntasks.p, 0, sizeof(uint32_t) * h->total_alloc, st));
+    CU(cudaMemsetAsync(h->d_out_res.p, 0, sizeof(Row) * h->total_alloc, st));
+  }
+  if (h->n_slots) {
+    CRANE_LAUNCH(k_node_init, (h->n_slots + 127) / 128, 128, 0, st, cl, rn, tl, now, h->cfg.max_jobs_per_node);
+    h->timing.kernel_launches++;
+  }
+  CU(cudaEventRecord(h->ev[3], st));
+
+  // ---- priority + queue (R5,R6) --------------------------------------------
+  uint32_t nq_cap = std::min<uint32_t>(N, h->cfg.scheduled_batch_size);
+  CU(cudaMemsetAsync(h->d_part_count.p, 0, sizeof(uint32_t) * (h->n_parts + 2), st));
+  if (N) {
+    PrioCfg pc{};
+    pc.type = h->cfg.priority_type;
+    pc.favor_small = h->cfg.favor_small;
+    pc.w_age = h->cfg.weight_age;
+    pc.w_fs = h->cfg.weight_fair_share;
+    pc.w_size = h->cfg.weight_job_size;
+    pc.w_part = h->cfg.weight_partition;
+    pc.w_qos = h->cfg.weight_qos;
+    pc.max_age = h->cfg.max_age_s;
+    uint64_t* keys = h->d_keys_a.p;
+    uint32_t* vals = h->d_vals_a.p;
+    if (pc.type != 0) {
+      CRANE_LAUNCH(k_bounds_init, 1, 32, 0, st, h->d_bounds.p);
+      uint32_t nb = std::min<uint32_t>((N + R + 255) / 256, 592);
+      CRANE_LAUNCH(k_bounds, nb, 256, 0, st, pd, rn, now, (uint64_t)h->cfg.max_age_s, h->d_bounds.p);
+      h->timing.kernel_launches += 2;
+      if (h->n_accounts) {
+        CU(cudaMemsetAsync(h->d_acc_service.p, 0, sizeof(double) * h->n_accounts, st));
+        CRANE_LAUNCH(k_service, (h->n_accounts + 127) / 128, 128, 0, st, rn, now, h->d_bounds.p, h->d_acc_service.p);
+        h->timing.kernel_launches++;
+      }
+    }
+    CRANE_LAUNCH(k_priority, (N + 255) / 256, 256, 0, st, pd, pc, now, h->d_bounds.p, h->d_acc_service.p,
+                 h->d_prio.p, h->d_keys_a.p, h->d_vals_a.p);
+    h->timing.kernel_launches++;
+    if (pc.type != 0) {
+      int rc = radix_sort(h, N, 64, &keys, &vals);
+      if (rc != CRANE_OK) return rc;
+    }
+    // keys2 go to the buffer not holding `vals`
+    uint64_t* key2 = h->d_keys_a.p;
+    uint32_t* order = vals;
+    if (order != h->d_vals_a.p) {
+      // radix_sort works on the (keys_a, vals_a) pair: bring the order back
+      CU(cudaMemcpyAsync(h->d_vals_a.p, order, sizeof(uint32_t) * N, cudaMemcpyDeviceToDevice, st));
+      order = h->d_vals_a.p;
+    }
+    CRANE_LAUNCH(k_queue_keys, (N + 255) / 256, 256, 0, st, pd, order, h->d_prio.p, h->cfg.scheduled_batch_size,
+                 h->n_parts, key2, out, h->d_part_count.p);
+    CRANE_LAUNCH(k_part_offsets, 1, 32, 0, st, h->d_part_count.p, h->n_parts, h->d_part_job_off.p);
+    h->timing.kernel_launches += 2;
+    int bits = 8;
+    while ((1ull << bits) < (uint64_t)h->n_parts + 2) bits += 8;
+    uint64_t* k2s;
+    uint32_t* queue;
+    int rc = radix_sort(h, N, bits, &k2s, &queue);
+    if (rc != CRANE_OK) return rc;
+    h->d_queue = queue;
+    if (nq_cap) {
+      // n_queued <= nq_cap lives on the device (part_job_off[n_parts]); the
+      // kernels below bound themselves with it.
+      CRANE_LAUNCH(k_build_jobq, (nq_cap + 127) / 128, 128, 0, st, pd, queue, h->d_part_job_off.p + h->n_parts, h->d_jobq.p);
+      h->timing.kernel_launches++;
+    }
+  } else {
+    CRANE_LAUNCH(k_part_offsets, 1, 32, 0, st, h->d_part_count.p, h->n_parts, h->d_part_job_off.p);
+    h->timing.kernel_launches++;
+  }
+  CU(cudaEventRecord(h->ev[4], st));
+
+  // ---- capability bitmap (R7 predicate + R8) -------------------------------
+  if (nq_cap && h->n_parts) {
+    uint32_t wpb = 8;
+    uint32_t nb = std::min<uint32_t>((nq_cap + wpb - 1) / wpb, 148 * 8);
+    CRANE_LAUNCH(k_feas_bitmap, nb, wpb * 32, 0, st, cl, pd, h->d_jobq.p, h->d_part_job_off.p + h->n_parts, h->words_per_row, h->d_bitmap.p);
+    h->timing.kernel_launches++;
+  }
+  CU(cudaEventRecord(h->ev[5], st));
+
+  // ---- sequential commit (R7,R9,R10,R11) -----------------------------------
+  if (nq_cap && h->n_parts) {
+    CommitArgs ca{};
+    ca.cl = cl;
+    ca.tl = tl;
+    ca.jobq = h->d_jobq.p;
+    ca.part_job_off = h->d_part_job_off.p;
+    ca.bitmap = h->d_bitmap.p;
+    ca.words_per_row = h->words_per_row;
+    ca.out = out;
+    ca.scratch_alloc = h->d_scratch.p;
+    ca.now = now;
+    ca.max_window = h->cfg.max_time_window_s;
+    ca.max_jobs = h->cfg.max_jobs_per_node;
+    size_t smem = commit_smem_bytes(h->max_part_slots, h->words_per_row);
+    CRANE_LAUNCH(k_commit, h->n_parts, h->commit_threads, smem, st, ca);
+    h->timing.kernel_launches++;
+  }
+  CU(cudaEventRecord(h->ev[6], st));
+  CU(cudaGetLastError());
+  h->ran = true;
+  return CRANE_OK;
+}
+
+int crane_sched_fetch(crane_sched_t* h, crane_placements_t* out) {
+  if (!h || !out) return CRANE_EINVAL;
+  if (!h->ran) return fail(h, CRANE_EINVAL, "fetch: run first");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const uint32_t N = h->n_pending;
+  if (N && (!out->reason || !out->priority || !out->start_time || !out->end_time || !out->n_alloc || !out->alloc_off))
+    return fail(h, CRANE_EINVAL, "placements: null column");
+  if (h->total_alloc && (!out->alloc_node || !out->alloc_ntasks || !out->alloc_res))
+    return fail(h, CRANE_EINVAL, "placements: null allocation table");
+  // slots of jobs without a placement stay zero
+  if (N) {
+    CU(cudaMemcpyAsync(out->reason, h->d_reason.p, N, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->priority, h->d_out_prio.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->start_time, h->d_out_start.p, sizeof(int64_t) * N, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->end_time, h->d_out_end.p, sizeof(int64_t) * N, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->n_alloc, h->d_out_nalloc.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
+  }
+  if (h->total_alloc) {
+    CU(cudaMemcpyAsync(out->alloc_node, h->d_out_node.p, sizeof(uint32_t) * h->total_alloc, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->alloc_ntasks, h->d_out_ntasks.p, sizeof(uint32_t) * h->total_alloc, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->alloc_res, h->d_out_res.p, sizeof(Row) * h->total_alloc, cudaMemcpyDeviceToHost, st));
+  }
+  memcpy(out->alloc_off, h->h_alloc_off.data(), sizeof(uint32_t) * ((size_t)N + 1));
+  CU(cudaEventRecord(h->ev[7], st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing.h2d_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->timing.init_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->timing.priority_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->timing.feas_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]); h->timing.commit_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]); h->timing.d2h_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[2], h->ev[6]); h->timing.total_ms = ms;
+  return CRANE_OK;
+}
+
+int crane_sched_node_select(crane_sched_t* h, int64_t now, const crane_running_t* running,
+                            const crane_pending_t* pending, crane_placements_t* out) {
+  int rc = crane_sched_upload(h, running, pending);
+  if (rc != CRANE_OK) return rc;
+  rc = crane_sched_run(h, now);
+  if (rc != CRANE_OK) return rc;
+  return crane_sched_fetch(h, out);
+}
+
+int crane_sched_get_timing(const crane_sched_t* h, crane_sched_timing_t* t) {
+  if (!h || !t) return CRANE_EINVAL;
+  *t = h->timing;
+  return CRANE_OK;
+}
+
+int crane_sched_debug_bitmap(crane_sched_t* h, uint32_t* dst, size_t cap_words, uint32_t* rows,
+                             uint32_t* words_per_row) {
+  if (!h || !h->ran) return CRANE_EINVAL;
+  CU(cudaSetDevice(h->device));
+  uint32_t nq = 0;
+  CU(cudaMemcpy(&nq, h->d_part_job_off.p + h->n_parts, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (rows) *rows = nq;
+  if (words_per_row) *words_per_row = h->words_per_row;
+  size_t n = std::min(cap_words, (size_t)nq * h->words_per_row);
+  if (dst && n) CU(cudaMemcpy(dst, h->d_bitmap.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return CRANE_OK;
+}
+
+}  // extern "C"

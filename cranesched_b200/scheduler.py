@@ -1,0 +1,137 @@
+"""Host-side mirror of the reference interface for the scheduling hot path.
+
+`GpuScheduler.node_select(now, running, pending)` has the argument meaning and
+error behaviour of `SchedulerAlgo::NodeSelect(now, running_jobs, pending_jobs)`
+(reference: src/CraneCtld/JobScheduler.h:254-257): per-job failure is a pending
+reason, never an exception; malformed input / missing device raises.
+
+The work happens in the C-ABI library cranesched_b200/csrc/libcrane_sched.so
+(hand-written sm_100a kernels). There is no CPU path: if the library is missing
+or no CUDA device is present, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcrane_sched.so")
+_libs: dict[str, C.CDLL] = {}
+
+
+class CraneSchedError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"crane_sched error {code}: {msg}")
+        self.code = code
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} not found: build it with `python -m cranesched_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    P = C.POINTER
+    lib.crane_sched_create.restype = C.c_int
+    lib.crane_sched_create.argtypes = [P(abi.SchedConfig), C.c_int, P(C.c_void_p)]
+    lib.crane_sched_destroy.restype = None
+    lib.crane_sched_destroy.argtypes = [C.c_void_p]
+    lib.crane_sched_last_error.restype = C.c_char_p
+    lib.crane_sched_last_error.argtypes = [C.c_void_p]
+    lib.crane_sched_set_cluster.restype = C.c_int
+    lib.crane_sched_set_cluster.argtypes = [C.c_void_p, P(abi.ClusterC)]
+    lib.crane_sched_node_select.restype = C.c_int
+    lib.crane_sched_node_select.argtypes = [C.c_void_p, C.c_int64, P(abi.RunningC), P(abi.PendingC), P(abi.PlacementsC)]
+    lib.crane_sched_upload.restype = C.c_int
+    lib.crane_sched_upload.argtypes = [C.c_void_p, P(abi.RunningC), P(abi.PendingC)]
+    lib.crane_sched_run.restype = C.c_int
+    lib.crane_sched_run.argtypes = [C.c_void_p, C.c_int64]
+    lib.crane_sched_fetch.restype = C.c_int
+    lib.crane_sched_fetch.argtypes = [C.c_void_p, P(abi.PlacementsC)]
+    lib.crane_sched_get_timing.restype = C.c_int
+    lib.crane_sched_get_timing.argtypes = [C.c_void_p, P(abi.TimingC)]
+    lib.crane_sched_debug_bitmap.restype = C.c_int
+    lib.crane_sched_debug_bitmap.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_uint32), P(C.c_uint32)]
+    _libs[path] = lib
+    return lib
+
+
+EXPORTS = ("crane_sched_create", "crane_sched_destroy", "crane_sched_last_error",
+           "crane_sched_set_cluster", "crane_sched_node_select", "crane_sched_upload",
+           "crane_sched_run", "crane_sched_fetch", "crane_sched_get_timing",
+           "crane_sched_debug_bitmap")
+
+
+class GpuScheduler:
+    """One handle per GPU; owns the device-resident node, job and timeline tables."""
+
+    def __init__(self, cfg: abi.Config, device: int = 0, lib_path: str | None = None):
+        self._lib = load_library(lib_path)
+        self._h = C.c_void_p()
+        c_cfg = cfg.as_c()
+        rc = self._lib.crane_sched_create(C.byref(c_cfg), device, C.byref(self._h))
+        if rc != 0:
+            raise CraneSchedError(rc, "crane_sched_create failed (no CUDA device?)" if rc == abi.ENODEV else "crane_sched_create")
+        self.cfg = cfg
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            self._lib.crane_sched_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise CraneSchedError(rc, (self._lib.crane_sched_last_error(self._h) or b"").decode())
+
+    def set_cluster(self, cluster: abi.Cluster):
+        c = cluster.as_c()
+        self._check(self._lib.crane_sched_set_cluster(self._h, C.byref(c)))
+        self.cluster = cluster
+
+    # --- the NodeSelect call, host buffers in / host buffers out ------------
+    def node_select(self, now: int, running: abi.Running, pending: abi.Pending,
+                    out: abi.Placements | None = None) -> abi.Placements:
+        out = out if out is not None else abi.Placements.for_pending(pending)
+        c_rn, c_pd, c_out = running.as_c(), pending.as_c(), out.as_c()
+        self._check(self._lib.crane_sched_node_select(self._h, now, C.byref(c_rn), C.byref(c_pd), C.byref(c_out)))
+        return out
+
+    # --- the same call split at the PCIe boundary ----------------------------
+    def upload(self, running: abi.Running, pending: abi.Pending):
+        c_rn, c_pd = running.as_c(), pending.as_c()
+        self._keep = [running, pending]
+        self._check(self._lib.crane_sched_upload(self._h, C.byref(c_rn), C.byref(c_pd)))
+
+    def run(self, now: int):
+        self._check(self._lib.crane_sched_run(self._h, now))
+
+    def fetch(self, out: abi.Placements) -> abi.Placements:
+        c_out = out.as_c()
+        self._check(self._lib.crane_sched_fetch(self._h, C.byref(c_out)))
+        return out
+
+    def timing(self) -> dict:
+        t = abi.TimingC()
+        self._check(self._lib.crane_sched_get_timing(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in abi.TimingC._fields_}
+
+    def debug_bitmap(self):
+        import numpy as np
+        rows, wpr = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.crane_sched_debug_bitmap(self._h, None, 0, C.byref(rows), C.byref(wpr)))
+        buf = np.zeros((rows.value, wpr.value), np.uint32)
+        if buf.size:
+            self._check(self._lib.crane_sched_debug_bitmap(self._h, buf.ctypes.data, buf.size, C.byref(rows), C.byref(wpr)))
+        return buf
