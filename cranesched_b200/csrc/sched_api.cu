@@ -686,6 +686,25 @@ int crane_sched_node_select(crane_sched_t* h, int64_t now, const crane_running_t
   return crane_sched_fetch(h, out);
 }
 
+int crane_sched_sync(crane_sched_t* h, float* run_ms) {
+  if (!h) return CRANE_EINVAL;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  if (h->ran) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->timing.init_ms = ms;
+    cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->timing.priority_ms = ms;
+    cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->timing.feas_ms = ms;
+    cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]); h->timing.commit_ms = ms;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[6]); h->timing.total_ms = ms;
+    if (run_ms) *run_ms = ms;
+  } else if (run_ms) {
+    *run_ms = 0.f;
+  }
+  return CRANE_OK;
+}
+
 int crane_sched_get_timing(const crane_sched_t* h, crane_sched_timing_t* t) {
   if (!h || !t) return CRANE_EINVAL;
   *t = h->timing;

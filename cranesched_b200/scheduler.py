@@ -53,6 +53,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.crane_sched_run.argtypes = [C.c_void_p, C.c_int64]
     lib.crane_sched_fetch.restype = C.c_int
     lib.crane_sched_fetch.argtypes = [C.c_void_p, P(abi.PlacementsC)]
+    lib.crane_sched_sync.restype = C.c_int
+    lib.crane_sched_sync.argtypes = [C.c_void_p, P(C.c_float)]
     lib.crane_sched_get_timing.restype = C.c_int
     lib.crane_sched_get_timing.argtypes = [C.c_void_p, P(abi.TimingC)]
     lib.crane_sched_debug_bitmap.restype = C.c_int
@@ -63,7 +65,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 
 EXPORTS = ("crane_sched_create", "crane_sched_destroy", "crane_sched_last_error",
            "crane_sched_set_cluster", "crane_sched_node_select", "crane_sched_upload",
-           "crane_sched_run", "crane_sched_fetch", "crane_sched_get_timing",
+           "crane_sched_run", "crane_sched_fetch", "crane_sched_sync", "crane_sched_get_timing",
            "crane_sched_debug_bitmap")
 
 
@@ -116,6 +118,12 @@ class GpuScheduler:
 
     def run(self, now: int):
         self._check(self._lib.crane_sched_run(self._h, now))
+
+    def sync(self) -> float:
+        """Waits for the handle's stream; returns the device ms of the last run."""
+        ms = C.c_float(0.0)
+        self._check(self._lib.crane_sched_sync(self._h, C.byref(ms)))
+        return ms.value
 
     def fetch(self, out: abi.Placements) -> abi.Placements:
         c_out = out.as_c()

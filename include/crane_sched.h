@@ -223,6 +223,10 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* running,
 int crane_sched_run(crane_sched_t* h, int64_t now);
 int crane_sched_fetch(crane_sched_t* h, crane_placements_t* out);
 
+/* Blocks until the handle's stream is idle; *run_ms (optional) receives the
+ * device time of the last crane_sched_run (CUDA events on that stream). */
+int crane_sched_sync(crane_sched_t* h, float* run_ms);
+
 int crane_sched_get_timing(const crane_sched_t* h, crane_sched_timing_t* t);
 
 /* Capability bitmap of the last run (the jobs x nodes feasibility bitmap):

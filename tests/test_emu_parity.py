@@ -1,0 +1,24 @@
+"""CPU-side execution of the REAL kernel source under tests/cuda_emu (every
+CUDA thread a host thread) against the oracle. Small cases only: this checks
+kernel logic and barrier structure before any GPU time is spent; the parity
+tests proper are the `-m gpu` ones."""
+import pytest
+
+from cranesched_b200 import synth
+from tests.helpers import assert_same, check_invariants, run_sched
+
+CASES = {
+    "fifo_small": lambda: synth.config1(n_jobs=150, n_nodes=12),
+    "random_multifactor": lambda: synth.random_case(11, n_jobs=100, n_nodes=20, n_running=12),
+    "random_fifo_cap": lambda: synth.random_case(12, n_jobs=90, n_nodes=10, n_parts=2, n_running=6, fifo=True,
+                                                 max_jobs_per_node=12, short=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_emulated_kernels_match_oracle(oracle, emu_lib, name):
+    case = CASES[name]()
+    ref, _, _ = oracle.node_select(*case[:4], case[4])
+    got, _ = run_sched(case, emu_lib)
+    assert_same(ref, got)
+    check_invariants(case, got)

@@ -1,0 +1,138 @@
+"""Parity tests proper: the sm_100a kernels, called through the C-ABI, against
+the oracle (bit-exact: reasons, fp64 priority bits, start/end times, node sets,
+per-node core and gres slot masks) and against the committed golden fixtures;
+plus size-independent invariants at sizes the oracle cannot finish."""
+import os
+
+import numpy as np
+import pytest
+
+from cranesched_b200 import abi, synth
+from tests.helpers import assert_same, check_invariants, run_sched
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_config1_plumbing(oracle, gpu_lib):
+    case = synth.config1()
+    ref, _, _ = oracle.node_select(*case[:4], case[4])
+    got, _ = run_sched(case, gpu_lib)
+    assert_same(ref, got)
+
+
+@pytest.mark.parametrize("seed", range(20, 32))
+def test_random_feature_mix(oracle, gpu_lib, seed):
+    """running jobs, fractional cpus, typed/untyped gres over two names, node
+    lists, exclusive jobs, dead/drained nodes, unknown partitions, mandated
+    priorities; multifactor and FIFO."""
+    case = synth.random_case(seed, n_jobs=400, n_nodes=64, n_parts=1 + seed % 4, n_running=50,
+                             fifo=bool(seed % 3 == 0))
+    ref, _, _ = oracle.node_select(*case[:4], case[4])
+    got, _ = run_sched(case, gpu_lib)
+    assert_same(ref, got)
+    check_invariants(case, got)
+
+
+@pytest.mark.parametrize("seed", [40, 41, 42])
+def test_timeline_cap_and_window(oracle, gpu_lib, seed):
+    """kAlgoMaxJobNumPerNode cap (nodes drop out mid-tick) and the 7-day
+    backfill window (JobScheduler.h:263-264, 809)."""
+    case = synth.random_case(seed, n_jobs=600, n_nodes=12, n_parts=2, n_running=10, max_jobs_per_node=16)
+    ref, _, _ = oracle.node_select(*case[:4], case[4])
+    got, _ = run_sched(case, gpu_lib)
+    assert_same(ref, got)
+
+
+def test_batch_limit(oracle, gpu_lib):
+    """ScheduledBatchSize: ranks beyond the limit get "Priority"."""
+    case = synth.random_case(50, n_jobs=500, n_nodes=40, n_running=20, limit=137)
+    ref, _, _ = oracle.node_select(*case[:4], case[4])
+    got, _ = run_sched(case, gpu_lib)
+    assert_same(ref, got)
+    assert (got.reason == abi.REASON_PRIORITY).sum() >= 500 - 137
+
+
+@pytest.mark.parametrize("name", ["random_7", "random_8", "config2_small"])
+def test_golden_fixtures(gpu_lib, name):
+    from tests.golden.make_golden import CASES
+    case = CASES[name]()
+    got, _ = run_sched(case, gpu_lib)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    ref = abi.Placements(**{f: g[f] for f in abi.Placements.__dataclass_fields__})
+    assert_same(ref, got)
+
+
+def test_config2_medium_vs_oracle(oracle, gpu_lib):
+    """config-2 shape (4 partitions, cpu+mem+gres, multifactor + backfill) at a
+    size the oracle finishes in seconds."""
+    case = synth.config2(n_jobs=6000, n_nodes=600)
+    ref, _, _ = oracle.node_select(*case[:4], case[4])
+    got, _ = run_sched(case, gpu_lib)
+    assert_same(ref, got)
+    check_invariants(case, got)
+
+
+def test_config5_backfill_stress_small(oracle, gpu_lib):
+    case = synth.config5(n_jobs=3000, n_nodes=100)
+    ref, _, _ = oracle.node_select(*case[:4], case[4])
+    got, _ = run_sched(case, gpu_lib)
+    assert_same(ref, got)
+
+
+def test_config4_hetero_gres_small(oracle, gpu_lib):
+    case = synth.config4(n_jobs=4000, n_nodes=250)
+    ref, _, _ = oracle.node_select(*case[:4], case[4])
+    got, _ = run_sched(case, gpu_lib)
+    assert_same(ref, got)
+    check_invariants(case, got)
+
+
+def test_config2_full_size_invariants_and_prefix(oracle, gpu_lib):
+    """BASELINE config 2 at full size (100k x 10k): invariants over the whole
+    result, idempotence (same input -> same bits), and bit-exactness against
+    the oracle on the prefix of the priority order the oracle can afford."""
+    case = synth.config2()
+    got, timing = run_sched(case, gpu_lib)
+    check_invariants(case, got)
+    again, _ = run_sched(case, gpu_lib)
+    assert_same(got, again)
+    cfg, cl, rn, pd, now = case
+    n_pref = 3000
+    ref, _, done = oracle.node_select(cfg, cl, rn, pd, now, max_jobs=n_pref)
+    assert done == n_pref
+    order = np.argsort(-ref.priority, kind="stable")[:n_pref]
+    for f in ("reason", "start_time", "end_time", "n_alloc"):
+        assert np.array_equal(getattr(ref, f)[order], getattr(got, f)[order]), f
+    assert np.array_equal(ref.priority.view(np.uint64), got.priority.view(np.uint64))
+    rep = np.repeat(np.arange(pd.n), pd.node_num)
+    sel = np.isin(rep, order)
+    assert np.array_equal(ref.alloc_node[sel], got.alloc_node[sel])
+    assert ref.alloc_res[sel].tobytes() == got.alloc_res[sel].tobytes()
+
+
+def test_capability_bitmap_rows(oracle, gpu_lib):
+    """The jobs x nodes bitmap row of a job equals the oracle's per-(job,node)
+    GetFeasibleResourceInNode(res_total) verdict."""
+    from cranesched_b200.scheduler import GpuScheduler
+    case = synth.random_case(60, n_jobs=120, n_nodes=40, n_parts=1, n_running=0, lists=False)
+    cfg, cl, rn, pd, now = case
+    s = GpuScheduler(cfg, 0, gpu_lib)
+    s.set_cluster(cl)
+    out = s.node_select(now, rn, pd)
+    bm = s.debug_bitmap()
+    s.close()
+    usable = np.flatnonzero((cl.alive == 1) & (cl.drain == 0))
+    queued = [j for j in np.argsort(-out.priority, kind="stable") if pd.partition[j] < cl.n_partitions]
+    assert bm.shape[0] == len(queued)
+    for r, j in enumerate(queued):
+        req = np.zeros((), abi.RES_VIEW)
+        t = int(pd.ntasks_per_node_min[j])
+        for f in ("cpu_raw", "mem", "mem_sw"):
+            req[f] = int(pd.req_node[j][f]) + int(pd.req_task[j][f]) * t
+        req["gres_total"] = pd.req_node[j]["gres_total"] + pd.req_task[j]["gres_total"] * t
+        req["gres_spec"] = pd.req_node[j]["gres_spec"] + pd.req_task[j]["gres_spec"] * t
+        for q, node in enumerate(usable):
+            want = oracle.feasible(cl, req, cl.res_total[node])[0]
+            have = bool(bm[r, q // 32] >> (q % 32) & 1)
+            assert want == have, (r, j, q)
