@@ -412,12 +412,13 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
     H2D(h->d_rn_account, rn->account, R);
     H2D(h->d_rn_cpu, rn->view_cpu_raw, R);
     H2D(h->d_rn_mem, rn->view_mem, R);
-    H2D(h->d_rn_slot_off, slot_off.data(), slot_off.size());
     H2D(h->d_rn_slot_end, slot_end.data(), slot_end.size());
     H2D(h->d_rn_slot_res, slot_res.data(), slot_res.size());
-    H2D(h->d_rn_acc_off, acc_off.data(), acc_off.size());
-    H2D(h->d_rn_acc_job, acc_job.data(), acc_job.size());
   }
+  // always present: k_service / k_node_init index these even with no running job
+  H2D(h->d_rn_acc_off, acc_off.data(), acc_off.size());
+  H2D(h->d_rn_acc_job, acc_job.data(), acc_job.size());
+  H2D(h->d_rn_slot_off, slot_off.data(), slot_off.size());
   H2D(h->d_acc_present, acc_present.data(), acc_present.size());
   // staging vectors above are pageable: the copies have completed on return,
   // but make it explicit before they go out of scope

@@ -860,18 +860,19 @@ __global__ void __launch_bounds__(512, 1) k_commit(CommitArgs a) {
   CommitSmem sm;
   {
     unsigned char* ptr = smem_raw;
+    // widest element type first so every array is naturally aligned
     sm.cost = reinterpret_cast<double*>(ptr); ptr += (size_t)mp * 8;
     sm.cpu0 = reinterpret_cast<long long*>(ptr); ptr += (size_t)mp * 8;
     sm.gcnt = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)mp * 8;
+    sm.bits = reinterpret_cast<uint32_t*>(ptr); ptr += (size_t)words * 4;
     sm.order = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.pos = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.cand = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
-    sm.skip = ptr; ptr += ((size_t)mp + 7) / 8 * 8;
-    sm.bits = reinterpret_cast<uint32_t*>(ptr);
+    sm.skip = ptr;
   }
   __shared__ JobQ s_job;
   __shared__ uint32_t s_warp_cnt[32];
-  __shared__ uint32_t s_ncand, s_nsel, s_flag[32], s_fail;
+  __shared__ uint32_t s_nsel, s_flag[32];
   __shared__ int64_t s_tmax;
   __shared__ int64_t s_tnode[32];
   __shared__ uint32_t s_resource_label;
@@ -905,7 +906,7 @@ __global__ void __launch_bounds__(512, 1) k_commit(CommitArgs a) {
     if (threadIdx.x < sizeof(JobQ) / 4)
       reinterpret_cast<uint32_t*>(&s_job)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&a.jobq[r])[threadIdx.x];
     for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) sm.bits[w] = a.bitmap[(size_t)r * words + w];
-    if (threadIdx.x == 0) { s_nsel = 0; s_fail = 0; s_resource_label = 0; }
+    if (threadIdx.x == 0) { s_nsel = 0; s_resource_label = 0; }
     __syncthreads();
     const JobQ jq = s_job;
     const uint32_t K = jq.node_num;

@@ -9,6 +9,7 @@ from tests.helpers import assert_same, check_invariants, run_sched
 
 CASES = {
     "fifo_small": lambda: synth.config1(n_jobs=150, n_nodes=12),
+    "config2_tiny_no_running": lambda: synth.config2(n_jobs=160, n_nodes=20),
     "random_multifactor": lambda: synth.random_case(11, n_jobs=100, n_nodes=20, n_running=12),
     "random_fifo_cap": lambda: synth.random_case(12, n_jobs=90, n_nodes=10, n_parts=2, n_running=6, fifo=True,
                                                  max_jobs_per_node=12, short=True),
