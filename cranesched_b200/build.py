@@ -34,6 +34,15 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return SO
 
 
+def build_prof(force: bool = True) -> str:
+    """Profiling variant (-DCRANE_PROFILE: clock64 phase counters in k_commit); tools only."""
+    so = os.path.join(CSRC, "libcrane_sched_prof.so")
+    cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--fmad=false",
+           "-DCRANE_PROFILE", "-Xcompiler", "-fPIC", "-shared", "-o", so, os.path.join(CSRC, "sched_api.cu")]
+    subprocess.check_call(cmd)
+    return so
+
+
 def build_emu(force: bool = False) -> str:
     emu_h = os.path.join(ROOT, "tests", "cuda_emu", "cuda_emu.h")
     if force or _stale(EMU_SO, [emu_h]):
@@ -47,7 +56,9 @@ def build_emu(force: bool = False) -> str:
 
 if __name__ == "__main__":
     import sys
-    if "emu" in sys.argv:
+    if "prof" in sys.argv:
+        print(build_prof())
+    elif "emu" in sys.argv:
         print(build_emu(force=True))
     else:
         print(build_cuda(force=True, verbose="-v" in sys.argv))

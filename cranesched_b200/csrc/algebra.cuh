@@ -18,15 +18,35 @@
 
 namespace crane {
 
-typedef crane_res_in_node_t Row;  // ResourceInNodeV3 (PublicHeader.h:562)
-typedef crane_res_view_t View;    // ResourceView     (PublicHeader.h:671)
+// Device-side views of the ABI rows with the SAME memory layout; the eight
+// uint16 gres slot masks / counts are handled as two 64-bit words so set
+// algebra on all gres entries is two AND/ANDN instructions.
+struct __align__(8) Row {   // crane_res_in_node_t / ResourceInNodeV3 (PublicHeader.h:562)
+  int64_t cpu_raw;
+  uint64_t mem;
+  uint64_t mem_sw;
+  uint64_t core[CRANE_CORE_WORDS];
+  uint64_t g[2];            // gres[0..3], gres[4..7]
+};
+struct __align__(8) View {  // crane_res_view_t / ResourceView (PublicHeader.h:671)
+  int64_t cpu_raw;
+  uint64_t mem;
+  uint64_t mem_sw;
+  uint64_t gtot[2];         // gres_total[0..7] as 16-bit fields
+  uint64_t gspec[2];        // gres_spec[0..7]
+};
+static_assert(sizeof(Row) == sizeof(crane_res_in_node_t), "Row layout");
+static_assert(sizeof(View) == sizeof(crane_res_view_t), "View layout");
 
 struct GresDict {
   uint32_t n_entries;
+  uint32_t pad;
   uint8_t entry_name[CRANE_GRES_ENTRIES];
+  uint8_t name_first[CRANE_GRES_NAMES];   // first entry of each name (entries of a name are contiguous)
+  uint8_t name_count[CRANE_GRES_NAMES];
 };
 
-CRANE_HD int popc16(uint32_t v) {
+CRANE_HD int popc32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
   return __popc(v);
 #else
@@ -40,43 +60,42 @@ CRANE_HD int popc64(uint64_t v) {
   return __builtin_popcountll(v);
 #endif
 }
-
-// the n lowest set bits of m (n <= popcount(m)); "it = begin(); n times ++it"
-// over an ordered std::set (PublicHeader.cpp:535-537, 572-574).
-CRANE_HD uint32_t lowest_bits32(uint32_t m, int n) {
-  uint32_t r = 0;
-  for (int i = 0; i < n; ++i) {
-    uint32_t low = m & (0u - m);
-    r |= low;
-    m ^= low;
-  }
-  return r;
+// 16-bit field e (0..7) of a two-word array; selects instead of indexing so
+// the words stay in registers
+CRANE_HD uint32_t field16(const uint64_t* w, uint32_t e) {
+  const uint64_t x = (e & 4u) ? w[1] : w[0];
+  return (uint32_t)(x >> ((e & 3u) * 16u)) & 0xffffu;
 }
+CRANE_HD void set_field16(uint64_t* w, uint32_t e, uint32_t v) {
+  const uint32_t sh = (e & 3u) * 16u;
+  const uint64_t clr = ~(0xffffull << sh), val = (uint64_t)(v & 0xffffu) << sh;
+  if (e & 4u) w[1] = (w[1] & clr) | val; else w[0] = (w[0] & clr) | val;
+}
+
+// the n lowest set bits of m: "it = begin(); n times ++it" over an ordered
+// std::set (PublicHeader.cpp:535-537, 572-574).
 CRANE_HD uint64_t lowest_bits64(uint64_t m, int n) {
-  if (n >= 64) return m;
-  uint64_t r = 0;
-  for (int i = 0; i < n; ++i) {
-    uint64_t low = m & (0ull - m);
-    r |= low;
-    m ^= low;
+  if (n >= popc64(m)) return m;
+  if (n <= 0) return 0;
+  // branch-free select of the n-th set bit: halve the search window six times
+  uint32_t pos = 0;
+  int rem = n;
+#pragma unroll
+  for (uint32_t w = 32; w >= 1; w >>= 1) {
+    const int c = popc64((m >> pos) & ((1ull << w) - 1ull));
+    if (c < rem) { rem -= c; pos += w; }
   }
-  return r;
+  return m & ((2ull << pos) - 1ull);  // pos <= 62 here because n < popcount(m)
 }
 
 CRANE_HD void row_zero(Row& r) {
   r.cpu_raw = 0; r.mem = 0; r.mem_sw = 0;
   for (int w = 0; w < CRANE_CORE_WORDS; ++w) r.core[w] = 0;
-  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) r.gres[e] = 0;
+  r.g[0] = r.g[1] = 0;
 }
-CRANE_HD bool core_empty(const Row& r) {
-  uint64_t any = 0;
-  for (int w = 0; w < CRANE_CORE_WORDS; ++w) any |= r.core[w];
-  return any == 0;
-}
+CRANE_HD bool core_empty(const Row& r) { return (r.core[0] | r.core[1] | r.core[2] | r.core[3]) == 0; }
 CRANE_HD int core_count(const Row& r) {
-  int n = 0;
-  for (int w = 0; w < CRANE_CORE_WORDS; ++w) n += popc64(r.core[w]);
-  return n;
+  return popc64(r.core[0]) + popc64(r.core[1]) + popc64(r.core[2]) + popc64(r.core[3]);
 }
 
 // ResourceInNodeV3::operator-= (PublicHeader.cpp:789-796; CpuSet 758-766;
@@ -87,7 +106,8 @@ CRANE_HD void row_sub(Row& a, const Row& b) {
   a.mem -= b.mem;
   a.mem_sw -= b.mem_sw;
   for (int w = 0; w < CRANE_CORE_WORDS; ++w) a.core[w] &= ~b.core[w];
-  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) a.gres[e] &= (uint16_t)~b.gres[e];
+  a.g[0] &= ~b.g[0];
+  a.g[1] &= ~b.g[1];
 }
 // ResourceInNodeV3::operator+= (PublicHeader.cpp:781-787)
 CRANE_HD void row_add(Row& a, const Row& b) {
@@ -95,65 +115,25 @@ CRANE_HD void row_add(Row& a, const Row& b) {
   a.mem += b.mem;
   a.mem_sw += b.mem_sw;
   for (int w = 0; w < CRANE_CORE_WORDS; ++w) a.core[w] |= b.core[w];
-  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) a.gres[e] |= b.gres[e];
+  a.g[0] |= b.g[0];
+  a.g[1] |= b.g[1];
 }
 // operator<=(ResourceInNodeV3, ResourceInNodeV3) (PublicHeader.cpp:886-890,
 // 159-169, 334-343): cpu, mem, slot-set inclusion. core ids and mem_sw are NOT
 // compared.
 CRANE_HD bool row_le(const Row& a, const Row& b) {
-  if (a.cpu_raw > b.cpu_raw) return false;
-  if (a.mem > b.mem) return false;
-  uint32_t bad = 0;
-  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) bad |= (uint32_t)(a.gres[e] & (uint16_t)~b.gres[e]);
-  return bad == 0;
-}
-// ResourceInNodeV3::Ckmin (PublicHeader.cpp:815-827), literal form.
-CRANE_HD void row_ckmin(Row& a, const Row& b) {
-  if (b.cpu_raw < a.cpu_raw) a.cpu_raw = b.cpu_raw;
-  if (!core_empty(a) && !core_empty(b))
-    for (int w = 0; w < CRANE_CORE_WORDS; ++w) a.core[w] &= b.core[w];
-  if (b.mem < a.mem) a.mem = b.mem;
-  if (b.mem_sw < a.mem_sw) a.mem_sw = b.mem_sw;
-  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) a.gres[e] &= b.gres[e];
+  return a.cpu_raw <= b.cpu_raw && a.mem <= b.mem && ((a.g[0] & ~b.g[0]) | (a.g[1] & ~b.g[1])) == 0;
 }
 
-// ---- prefix form of Ckmin -------------------------------------------------
-// The window minimum of JobScheduler.cpp:5314-5319 is the left fold
-//   row = res_avail; for seg in window: row.Ckmin(seg)
-// Its core rule ("intersect only when both sides are non-empty") is not
-// associative as written, but the fold equals
-//   core = res_avail.core & AND{ seg.core : seg.core != {} }
-// (once the running set is empty it stays empty either way). So the per-node
-// prefix array `pm` stores, for the core field, the AND over the non-empty
-// segment masks with all-ones as the identity; every other field is a plain
-// min / AND. pm_identity() is the fold's neutral element.
-CRANE_HD void pm_identity(Row& r) {
-  r.cpu_raw = INT64_MAX; r.mem = UINT64_MAX; r.mem_sw = UINT64_MAX;
-  for (int w = 0; w < CRANE_CORE_WORDS; ++w) r.core[w] = ~0ull;
-  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) r.gres[e] = 0xFFFF;
-}
-// acc = acc (+) seg, seg a raw timeline segment
-CRANE_HD void pm_absorb(Row& acc, const Row& seg) {
-  if (seg.cpu_raw < acc.cpu_raw) acc.cpu_raw = seg.cpu_raw;
-  if (seg.mem < acc.mem) acc.mem = seg.mem;
-  if (seg.mem_sw < acc.mem_sw) acc.mem_sw = seg.mem_sw;
-  if (!core_empty(seg))
-    for (int w = 0; w < CRANE_CORE_WORDS; ++w) acc.core[w] &= seg.core[w];
-  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) acc.gres[e] &= seg.gres[e];
-}
-// acc = acc (+) other, both already in prefix form (associative combine)
-CRANE_HD void pm_combine(Row& acc, const Row& o) {
-  if (o.cpu_raw < acc.cpu_raw) acc.cpu_raw = o.cpu_raw;
-  if (o.mem < acc.mem) acc.mem = o.mem;
-  if (o.mem_sw < acc.mem_sw) acc.mem_sw = o.mem_sw;
-  for (int w = 0; w < CRANE_CORE_WORDS; ++w) acc.core[w] &= o.core[w];
-  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) acc.gres[e] &= o.gres[e];
-}
-// the window-min row: fold started from the (stale) tick-start res_avail
-CRANE_HD void window_row(Row& out, const Row& avail0, const Row& pm) {
-  out = avail0;
-  pm_combine(out, pm);
-}
+// ---- the window minimum ------------------------------------------------------
+// JobScheduler.cpp:5314-5319 folds  row = res_avail; for seg in window:
+// row.Ckmin(seg)  (PublicHeader.cpp:815-827). Its core rule ("intersect only
+// when both sides are non-empty") is not associative as written, but the fold
+// equals  core = res_avail.core & AND{ seg.core : seg.core != {} }  (once the
+// running set is empty it stays empty either way); cpu/mem are minima and the
+// gres sets plain intersections. The kernels therefore AND-reduce the masks
+// with all-ones standing in for an empty core set, and test cpu/mem per
+// segment.
 
 // ---- requests ---------------------------------------------------------------
 // req_node_res_view + req_task_res_view * t  (JobScheduler.cpp:5190-5192,
@@ -163,32 +143,78 @@ CRANE_HD void view_node_plus_tasks(View& out, const View& node, const View& task
   out.cpu_raw = node.cpu_raw + task.cpu_raw * (int64_t)t;
   out.mem = node.mem + task.mem * (uint64_t)t;
   out.mem_sw = node.mem_sw + task.mem_sw * (uint64_t)t;
-  for (int g = 0; g < CRANE_GRES_NAMES; ++g) {
-    uint64_t v = (uint64_t)node.gres_total[g] + (uint64_t)task.gres_total[g] * t;
-    out.gres_total[g] = (uint16_t)(v > 0xFFFF ? 0xFFFF : v);
+  out.gtot[0] = out.gtot[1] = out.gspec[0] = out.gspec[1] = 0;
+  for (uint32_t i = 0; i < 8; ++i) {
+    uint64_t v = (uint64_t)field16(node.gtot, i) + (uint64_t)field16(task.gtot, i) * t;
+    set_field16(out.gtot, i, (uint32_t)(v > 0xFFFF ? 0xFFFF : v));
+    uint64_t s = (uint64_t)field16(node.gspec, i) + (uint64_t)field16(task.gspec, i) * t;
+    set_field16(out.gspec, i, (uint32_t)(s > 0xFFFF ? 0xFFFF : s));
   }
-  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) {
-    uint64_t v = (uint64_t)node.gres_spec[e] + (uint64_t)task.gres_spec[e] * t;
-    out.gres_spec[e] = (uint16_t)(v > 0xFFFF ? 0xFFFF : v);
+}
+CRANE_HD bool view_has_gres(const View& v) { return (v.gtot[0] | v.gtot[1] | v.gspec[0] | v.gspec[1]) != 0; }
+
+// gres part of ResourceView::GetFeasibleResourceInNode (PublicHeader.cpp:545-595)
+// on the two packed mask words `ag` of the available row. kAlloc=false: verdict
+// only (a name is feasible iff every typed count fits its type and
+// max(total, sum typed) fits the name's slots); kAlloc=true also picks the
+// slots in the reference's order: typed first (dictionary order, deviation
+// D4), leftovers of a typed entry serve the untyped part, then the other
+// types in order.
+template <bool kAlloc>
+CRANE_HD bool feasible_gres(const View& req, const uint64_t* ag, const GresDict& d, uint64_t* out) {
+#pragma unroll 1
+  for (uint32_t g = 0; g < CRANE_GRES_NAMES; ++g) {
+    // a requested name without dictionary entries has name_count 0: absent from every node
+    const uint32_t e0 = d.name_first[g], e1 = e0 + d.name_count[g];
+    const uint32_t want_total = field16(req.gtot, g);
+    uint32_t typed_sum = 0, have_total = 0;
+    bool wanted = want_total != 0;
+#pragma unroll 1
+    for (uint32_t e = e0; e < e1; ++e) {
+      const uint32_t sp = field16(req.gspec, e);
+      typed_sum += sp;
+      wanted |= sp != 0;
+      have_total += popc32(field16(ag, e));
+    }
+    if (!wanted) continue;
+    if (have_total == 0) return false;  // name absent from avail (PH.cpp:551)
+    uint32_t untyped = want_total > typed_sum ? want_total - typed_sum : 0;
+#pragma unroll 1
+    for (uint32_t e = e0; e < e1; ++e) {  // typed first (PH.cpp:563-579)
+      const uint32_t sp = field16(req.gspec, e);
+      if (sp == 0) continue;
+      const uint32_t m = field16(ag, e);
+      const uint32_t c = popc32(m);
+      if (c < sp) return false;  // covers "type absent" (m == 0)
+      uint32_t extra = c - sp;
+      if (extra > untyped) extra = untyped;
+      untyped -= extra;
+      if (kAlloc) set_field16(out, e, (uint32_t)lowest_bits64(m, (int)(sp + extra)));
+    }
+    if (untyped > 0) {  // the other types (PH.cpp:581-592)
+#pragma unroll 1
+      for (uint32_t e = e0; e < e1 && untyped > 0; ++e) {
+        if (field16(req.gspec, e) != 0) continue;
+        const uint32_t m = field16(ag, e);
+        const uint32_t c = popc32(m);
+        const uint32_t take = c < untyped ? c : untyped;
+        untyped -= take;
+        if (kAlloc) set_field16(out, e, (uint32_t)lowest_bits64(m, (int)take));
+      }
+    }
+    if (untyped != 0) return false;
   }
+  return true;
 }
 
 // ResourceView::GetFeasibleResourceInNode (PublicHeader.cpp:519-599).
-// kAlloc=false evaluates only the verdict (counts suffice: a name is feasible
-// iff every typed count fits its type and max(total, sum typed) fits the
-// name's slots); kAlloc=true also picks the concrete cores/slots in the
-// reference's order: typed first (dictionary order, deviation D4), leftovers of
-// a typed entry serve the untyped part, then the other types in order.
 template <bool kAlloc>
 CRANE_HD bool feasible(const View& req, const Row& avail, const GresDict& d, Row* alloc) {
   if (req.cpu_raw > avail.cpu_raw) return false;
   if (req.mem > avail.mem) return false;
-
-  int64_t whole = req.cpu_raw / 256;  // static_cast<int64_t>(cpu_t): truncates
-  bool integer_req = (whole * 256 == req.cpu_raw) && !core_empty(avail);
-  if (integer_req) {
-    if ((int64_t)core_count(avail) < whole) return false;
-  }
+  const int64_t whole = req.cpu_raw / 256;  // static_cast<int64_t>(cpu_t): truncates
+  const bool integer_req = (whole * 256 == req.cpu_raw) && !core_empty(avail);
+  if (integer_req && (int64_t)core_count(avail) < whole) return false;
   if (kAlloc) {
     row_zero(*alloc);
     alloc->cpu_raw = req.cpu_raw;
@@ -197,48 +223,15 @@ CRANE_HD bool feasible(const View& req, const Row& avail, const GresDict& d, Row
     if (integer_req) {
       int left = (int)whole;
       for (int w = 0; w < CRANE_CORE_WORDS && left > 0; ++w) {
-        int c = popc64(avail.core[w]);
-        int take = c < left ? c : left;
+        const int c = popc64(avail.core[w]);
+        const int take = c < left ? c : left;
         alloc->core[w] = lowest_bits64(avail.core[w], take);
         left -= take;
       }
     }
   }
-  for (int g = 0; g < CRANE_GRES_NAMES; ++g) {
-    uint32_t typed_sum = 0, have_total = 0;
-    bool wanted = req.gres_total[g] != 0;
-    for (uint32_t e = 0; e < d.n_entries; ++e) {
-      if (d.entry_name[e] != g) continue;
-      typed_sum += req.gres_spec[e];
-      if (req.gres_spec[e]) wanted = true;
-      have_total += popc16(avail.gres[e]);
-    }
-    if (!wanted) continue;
-    if (have_total == 0) return false;  // name absent from avail (PH.cpp:551)
-    uint32_t untyped = req.gres_total[g] > typed_sum ? req.gres_total[g] - typed_sum : 0;
-    for (uint32_t e = 0; e < d.n_entries; ++e) {  // typed first (PH.cpp:563-579)
-      if (d.entry_name[e] != g || req.gres_spec[e] == 0) continue;
-      uint32_t m = avail.gres[e];
-      uint32_t c = popc16(m);
-      if (c < req.gres_spec[e]) return false;  // covers "type absent" (m == 0)
-      uint32_t extra = c - req.gres_spec[e];
-      if (extra > untyped) extra = untyped;
-      untyped -= extra;
-      if (kAlloc) alloc->gres[e] = (uint16_t)lowest_bits32(m, (int)(req.gres_spec[e] + extra));
-    }
-    if (untyped > 0) {  // the other types (PH.cpp:581-592)
-      for (uint32_t e = 0; e < d.n_entries && untyped > 0; ++e) {
-        if (d.entry_name[e] != g || req.gres_spec[e] != 0) continue;
-        uint32_t m = avail.gres[e];
-        uint32_t c = popc16(m);
-        uint32_t take = c < untyped ? c : untyped;
-        untyped -= take;
-        if (kAlloc) alloc->gres[e] = (uint16_t)lowest_bits32(m, (int)take);
-      }
-    }
-    if (untyped != 0) return false;
-  }
-  return true;
+  if (!view_has_gres(req)) return true;
+  return feasible_gres<kAlloc>(req, avail.g, d, kAlloc ? alloc->g : nullptr);
 }
 
 // MinCpuTimeRatioFirst::UpdateCost delta (JobScheduler.h:46-48):

@@ -62,7 +62,7 @@ struct crane_sched {
   cudaEvent_t ev[8]{};
   std::string err;
   crane_sched_timing_t timing{};
-  int commit_threads = 512;
+  int commit_threads = kCommitThreads;
 
   // cluster (host copies)
   bool have_cluster = false;
@@ -76,8 +76,9 @@ struct crane_sched {
   DBuf<Row> d_slot_total;
   // timelines
   DBuf<uint32_t> d_tl_n;
-  DBuf<int64_t> d_tl_time;
-  DBuf<Row> d_tl_seg, d_tl_pm, d_avail0, d_scratch;
+  DBuf<TlEntry> d_tl_ent;
+  DBuf<Row> d_avail0, d_class_rows;
+  DBuf<uint8_t> d_slot_class;
   DBuf<double> d_cost0;
   DBuf<uint8_t> d_skip;
 
@@ -104,6 +105,7 @@ struct crane_sched {
   DBuf<uint64_t> d_keys_a, d_keys_b;
   DBuf<uint32_t> d_vals_a, d_vals_b, d_hist, d_part_count, d_part_job_off, d_bitmap;
   DBuf<JobQ> d_jobq;
+  DBuf<unsigned long long> d_prof;
   uint32_t* d_queue = nullptr;  // points into vals_a / vals_b after the sorts
   // outputs (device)
   DBuf<uint8_t> d_reason;
@@ -190,7 +192,7 @@ int crane_sched_create(const crane_sched_config_t* cfg, int device, crane_sched_
   for (auto& e : h->ev) cudaEventCreate(&e);
   if (const char* s = getenv("CRANE_COMMIT_THREADS")) {
     int t = atoi(s);
-    if (t >= 64 && t <= 512 && t % 32 == 0) h->commit_threads = t;
+    if (t >= 64 && t <= kCommitThreads && t % 32 == 0) h->commit_threads = t;
   }
 #ifdef CRANE_EMU
   if (!getenv("CRANE_COMMIT_THREADS")) h->commit_threads = 128;
@@ -206,8 +208,8 @@ void crane_sched_destroy(crane_sched_t* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
 #define REL(b) h->b.release()
-  REL(d_part_base); REL(d_slot_node); REL(d_node_slot); REL(d_slot_total); REL(d_tl_n); REL(d_tl_time);
-  REL(d_tl_seg); REL(d_tl_pm); REL(d_avail0); REL(d_scratch); REL(d_cost0); REL(d_skip); REL(d_partition);
+  REL(d_part_base); REL(d_slot_node); REL(d_node_slot); REL(d_slot_total); REL(d_tl_n); REL(d_tl_ent);
+  REL(d_avail0); REL(d_class_rows); REL(d_slot_class); REL(d_cost0); REL(d_skip); REL(d_partition);
   REL(d_node_num); REL(d_ntpn); REL(d_part_prio); REL(d_qos_prio); REL(d_account); REL(d_alloc_off);
   REL(d_time_limit); REL(d_submit); REL(d_exclusive); REL(d_mandated); REL(d_req_node); REL(d_req_task);
   REL(d_req_total); REL(d_incl_off); REL(d_incl_nodes); REL(d_excl_off); REL(d_excl_nodes); REL(d_rn_start);
@@ -216,7 +218,7 @@ void crane_sched_destroy(crane_sched_t* h) {
   REL(d_acc_present); REL(d_bounds); REL(d_acc_service); REL(d_prio); REL(d_keys_a); REL(d_keys_b); REL(d_vals_a);
   REL(d_vals_b); REL(d_hist); REL(d_part_count); REL(d_part_job_off); REL(d_bitmap); REL(d_jobq); REL(d_reason);
   REL(d_out_prio); REL(d_out_start); REL(d_out_end); REL(d_out_nalloc); REL(d_out_node); REL(d_out_ntasks);
-  REL(d_out_res);
+  REL(d_out_res); REL(d_prof);
 #undef REL
   for (auto& e : h->ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -237,8 +239,14 @@ int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
   h->have_cluster = false;
   h->n_nodes = c->n_nodes;
   h->n_parts = c->n_partitions;
+  memset(&h->dict, 0, sizeof h->dict);
   h->dict.n_entries = c->n_gres_entries;
   for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) h->dict.entry_name[e] = c->gres_entry_name[e];
+  for (uint32_t e = 0; e < c->n_gres_entries; ++e) {
+    const uint8_t g = c->gres_entry_name[e];
+    if (h->dict.name_count[g] == 0) h->dict.name_first[g] = (uint8_t)e;
+    h->dict.name_count[g]++;
+  }
   h->h_node_slot.assign(c->n_nodes, 0xffffffffu);
   h->h_part_base.assign(c->n_partitions + 1, 0);
   h->h_slot_node.clear();
@@ -258,10 +266,10 @@ int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
       if (seen[n]) return fail(h, CRANE_ENOSYS, "cluster: node %u is in more than one partition (overlapping partitions are not built yet)", n);
       seen[n] = 1;
       if (!c->alive[n] || c->drain[n]) continue;  // JobScheduler.cpp:5629
-      const Row& t = c->res_total[n];
+      const Row& t = reinterpret_cast<const Row&>(c->res_total[n]);
       if (t.cpu_raw < 0 || t.cpu_raw > (int64_t)1 << 40) return fail(h, CRANE_EINVAL, "cluster: node %u cpu out of range", n);
       for (uint32_t e = c->n_gres_entries; e < CRANE_GRES_ENTRIES; ++e)
-        if (t.gres[e]) return fail(h, CRANE_EINVAL, "cluster: node %u has slots for an undeclared gres entry", n);
+        if (field16(t.g, e)) return fail(h, CRANE_EINVAL, "cluster: node %u has slots for an undeclared gres entry", n);
       h->h_node_slot[n] = (uint32_t)h->h_slot_node.size();
       h->h_slot_node.push_back(n);
       slot_total.push_back(t);
@@ -272,22 +280,38 @@ int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
   h->h_part_base[c->n_partitions] = (uint32_t)h->h_slot_node.size();
   h->n_slots = (uint32_t)h->h_slot_node.size();
   h->max_part_slots = max_mp;
-  h->words_per_row = std::max<uint32_t>(1, (max_mp + 31) / 32);
+  h->words_per_row = std::max<uint32_t>(4, ((max_mp + 31) / 32 + 3) / 4 * 4);  // 16-byte rows for the bulk copies
   if (max_mp > 65535 || commit_smem_bytes(max_mp, h->words_per_row) > kMaxDynSmem)
     return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
+  // res_total classes per partition (distinct rows), cached in shared memory by the commit kernel
+  std::vector<uint8_t> slot_class(std::max<size_t>(slot_total.size(), 1), 0xff);
+  std::vector<Row> class_rows((size_t)std::max<uint32_t>(c->n_partitions, 1) * kMaxClasses);
+  memset(class_rows.data(), 0, class_rows.size() * sizeof(Row));
+  for (uint32_t p = 0; p < c->n_partitions; ++p) {
+    uint32_t ncls = 0;
+    for (uint32_t g = h->h_part_base[p]; g < h->h_part_base[p + 1]; ++g) {
+      uint32_t k = 0;
+      for (; k < ncls; ++k)
+        if (memcmp(&class_rows[(size_t)p * kMaxClasses + k], &slot_total[g], sizeof(Row)) == 0) break;
+      if (k == ncls) {
+        if (ncls == (uint32_t)kMaxClasses) continue;  // no class: the kernel reads slot_total
+        class_rows[(size_t)p * kMaxClasses + ncls++] = slot_total[g];
+      }
+      slot_class[g] = (uint8_t)k;
+    }
+  }
 
   H2D(h->d_part_base, h->h_part_base.data(), h->h_part_base.size());
   H2D(h->d_slot_node, h->h_slot_node.data(), h->h_slot_node.size());
   H2D(h->d_node_slot, h->h_node_slot.data(), h->h_node_slot.size());
   H2D(h->d_slot_total, slot_total.data(), slot_total.size());
+  H2D(h->d_slot_class, slot_class.data(), slot_class.size());
+  H2D(h->d_class_rows, class_rows.data(), class_rows.size());
   CU(cudaMemcpyToSymbolAsync(c_dict, &h->dict, sizeof(GresDict), 0, cudaMemcpyHostToDevice, h->stream));
   size_t ns = std::max<uint32_t>(h->n_slots, 1);
   CU(h->d_tl_n.ensure(ns));
-  CU(h->d_tl_time.ensure(ns * h->tl_cap));
-  CU(h->d_tl_seg.ensure(ns * h->tl_cap));
-  CU(h->d_tl_pm.ensure(ns * h->tl_cap));
+  CU(h->d_tl_ent.ensure(ns * h->tl_cap));
   CU(h->d_avail0.ensure(ns));
-  CU(h->d_scratch.ensure(ns));
   CU(h->d_cost0.ensure(ns));
   CU(h->d_skip.ensure(ns));
   CU(h->d_part_count.ensure(h->n_parts + 2));
@@ -401,7 +425,7 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
         if (g == 0xffffffffu) continue;
         uint32_t dst = fill_s[g]++;
         slot_end[dst] = rn->end_time[j];
-        slot_res[dst] = rn->alloc_res[k];
+        slot_res[dst] = reinterpret_cast<const Row&>(rn->alloc_res[k]);
       }
     }
     H2D(h->d_rn_start, rn->start_time, R);
@@ -509,13 +533,13 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
   cl.slot_node = h->d_slot_node.p;
   cl.node_slot = h->d_node_slot.p;
   cl.slot_total = h->d_slot_total.p;
+  cl.slot_class = h->d_slot_class.p;
+  cl.class_rows = h->d_class_rows.p;
 
   TimelineDev tl{};
   tl.cap = h->tl_cap;
   tl.n = h->d_tl_n.p;
-  tl.time = h->d_tl_time.p;
-  tl.seg = h->d_tl_seg.p;
-  tl.pm = h->d_tl_pm.p;
+  tl.ent = h->d_tl_ent.p;
   tl.avail0 = h->d_avail0.p;
   tl.cost0 = h->d_cost0.p;
   tl.skip = h->d_skip.p;
@@ -626,10 +650,11 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
     ca.bitmap = h->d_bitmap.p;
     ca.words_per_row = h->words_per_row;
     ca.out = out;
-    ca.scratch_alloc = h->d_scratch.p;
     ca.now = now;
     ca.max_window = h->cfg.max_time_window_s;
     ca.max_jobs = h->cfg.max_jobs_per_node;
+    CU(h->d_prof.ensure((size_t)h->n_parts * 16));
+    ca.prof = h->d_prof.p;
     size_t smem = commit_smem_bytes(h->max_part_slots, h->words_per_row);
     CRANE_LAUNCH(k_commit, h->n_parts, h->commit_threads, smem, st, ca);
     h->timing.kernel_launches++;
@@ -703,6 +728,15 @@ int crane_sched_sync(crane_sched_t* h, float* run_ms) {
   } else if (run_ms) {
     *run_ms = 0.f;
   }
+  return CRANE_OK;
+}
+
+int crane_sched_debug_profile(crane_sched_t* h, unsigned long long* dst, size_t cap) {
+  if (!h || !h->ran || !dst) return CRANE_EINVAL;
+  CU(cudaSetDevice(h->device));
+  size_t n = std::min(cap, (size_t)h->n_parts * 16);
+  CU(cudaStreamSynchronize(h->stream));
+  if (n) CU(cudaMemcpy(dst, h->d_prof.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return CRANE_OK;
 }
 

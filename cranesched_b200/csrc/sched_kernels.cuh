@@ -14,8 +14,7 @@
 // Data layout in HBM (all per tick):
 //   node slot g = compact index of an alive && !drain node inside its
 //   partition's contiguous range [part_base[p], part_base[p+1]).
-//   tl_time[g][CAP] int64, tl_seg[g][CAP] Row, tl_pm[g][CAP] Row (prefix
-//   Ckmin), tl_n[g]; CAP = max_jobs_per_node + 1.
+//   tl_ent[g][CAP] = {int64 t; Row seg} (80 B), tl_n[g]; CAP = max_jobs_per_node + 1.
 #pragma once
 
 #include "algebra.cuh"
@@ -78,6 +77,8 @@ struct RunningDev {
   const uint8_t* acc_present; // account appears in pending or running
 };
 
+constexpr int kMaxClasses = 16;  // distinct res_total rows cached per partition
+
 struct ClusterDev {
   uint32_t n_slots;           // usable nodes
   uint32_t n_parts;
@@ -86,14 +87,22 @@ struct ClusterDev {
   const uint32_t* slot_node;  // slot -> global node index
   const uint32_t* node_slot;  // global node -> slot or 0xffffffff
   const Row* slot_total;      // res_total per slot
+  const uint8_t* slot_class;  // per slot: index into its partition's class rows, 0xff = none
+  const Row* class_rows;      // [n_parts][kMaxClasses]
 };
+
+// one timeline breakpoint: from time t on, `seg` is available on the node
+// (an entry of NodeState::time_avail_res_map, JobScheduler.h:239,285)
+struct __align__(16) TlEntry {
+  int64_t t;
+  Row seg;
+};
+static_assert(sizeof(TlEntry) == 80, "TlEntry layout");
 
 struct TimelineDev {
   uint32_t cap;               // entries per slot
   uint32_t* n;                // [n_slots]
-  int64_t* time;              // [n_slots][cap]
-  Row* seg;                   // [n_slots][cap]
-  Row* pm;                    // [n_slots][cap]
+  TlEntry* ent;               // [n_slots][cap]
   Row* avail0;                // [n_slots] tick-start res_avail (NodeState::res_avail)
   double* cost0;              // [n_slots] initial cost (NodeRater)
   uint8_t* skip;              // [n_slots] timeline size >= max_jobs_per_node
@@ -145,48 +154,32 @@ __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
 __device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
   return (int64_t)__shfl_sync(kFullMask, (long long)v, src);
 }
-__device__ __forceinline__ void row_shfl(Row& out, const Row& in, int src) {
-  out.cpu_raw = shfl_i64(in.cpu_raw, src);
-  out.mem = shfl_u64(in.mem, src);
-  out.mem_sw = shfl_u64(in.mem_sw, src);
-#pragma unroll
-  for (int w = 0; w < CRANE_CORE_WORDS; ++w) out.core[w] = shfl_u64(in.core[w], src);
-  uint64_t g0, g1;
-  g0 = (uint64_t)in.gres[0] | (uint64_t)in.gres[1] << 16 | (uint64_t)in.gres[2] << 32 | (uint64_t)in.gres[3] << 48;
-  g1 = (uint64_t)in.gres[4] | (uint64_t)in.gres[5] << 16 | (uint64_t)in.gres[6] << 32 | (uint64_t)in.gres[7] << 48;
-  g0 = shfl_u64(g0, src);
-  g1 = shfl_u64(g1, src);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    out.gres[e] = (uint16_t)(g0 >> (16 * e));
-    out.gres[4 + e] = (uint16_t)(g1 >> (16 * e));
-  }
-}
-
 // packed per-entry slot counts of a row (8 x u8) for the cheap pre-filter
 __device__ __forceinline__ uint64_t pack_gres_counts(const Row& r) {
   uint64_t p = 0;
 #pragma unroll
-  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) p |= (uint64_t)popc16(r.gres[e]) << (8 * e);
+  for (uint32_t e = 0; e < CRANE_GRES_ENTRIES; ++e) p |= (uint64_t)popc32(field16(r.g, e)) << (8 * e);
   return p;
 }
-// conservative count-only gres check against packed counts (same verdict as
-// feasible<false> restricted to gres)
-__device__ __forceinline__ bool gres_counts_ok(const View& req, uint64_t packed) {
-  for (int g = 0; g < CRANE_GRES_NAMES; ++g) {
+// count-only gres verdict against packed counts (same verdict as feasible_gres<false>)
+__device__ __noinline__ bool gres_counts_ok(const View& req, uint64_t packed) {
+#pragma unroll 1
+  for (uint32_t g = 0; g < CRANE_GRES_NAMES; ++g) {
+    const uint32_t e0 = c_dict.name_first[g], e1 = e0 + c_dict.name_count[g];
+    const uint32_t want_total = field16(req.gtot, g);
     uint32_t typed = 0, have = 0;
-    bool wanted = req.gres_total[g] != 0;
-    bool ok = true;
-    for (uint32_t e = 0; e < c_dict.n_entries; ++e) {
-      if (c_dict.entry_name[e] != g) continue;
-      uint32_t c = (uint32_t)(packed >> (8 * e)) & 0xff;
-      typed += req.gres_spec[e];
-      if (req.gres_spec[e]) wanted = true;
-      if (c < req.gres_spec[e]) ok = false;
+    bool wanted = want_total != 0, ok = true;
+#pragma unroll 1
+    for (uint32_t e = e0; e < e1; ++e) {
+      const uint32_t c = (uint32_t)(packed >> (8 * e)) & 0xff;
+      const uint32_t sp = field16(req.gspec, e);
+      typed += sp;
+      wanted |= sp != 0;
+      ok &= c >= sp;
       have += c;
     }
     if (!wanted) continue;
-    uint32_t need = req.gres_total[g] > typed ? req.gres_total[g] : typed;
+    const uint32_t need = want_total > typed ? want_total : typed;
     if (!ok || have == 0 || have < need) return false;
   }
   return true;
@@ -509,10 +502,7 @@ __global__ void k_build_jobq(PendingDev pd, const uint32_t* queue, const uint32_
   q.node_num = pd.node_num[j];
   q.alloc_off = pd.alloc_off[j];
   q.ntasks_per_node = t;
-  bool gres = false;
-  for (int g = 0; g < CRANE_GRES_NAMES; ++g) gres |= q.req.gres_total[g] != 0;
-  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) gres |= q.req.gres_spec[e] != 0;
-  q.flags = (pd.exclusive[j] ? 1u : 0u) | (gres ? 2u : 0u);
+  q.flags = (pd.exclusive[j] ? 1u : 0u) | (view_has_gres(q.req) ? 2u : 0u);
   for (int i = 0; i < 3; ++i) q.pad[i] = 0;
   jobq[r] = q;
 }
@@ -537,12 +527,10 @@ __global__ void k_node_init(ClusterDev cl, RunningDev rn, TimelineDev tl, int64_
   }
   tl.avail0[g] = avail;
   tl.cost0[g] = cost;
-  int64_t* T = tl.time + (size_t)g * tl.cap;
-  Row* S = tl.seg + (size_t)g * tl.cap;
-  Row* P = tl.pm + (size_t)g * tl.cap;
+  TlEntry* E = tl.ent + (size_t)g * tl.cap;
   uint32_t n = 1;
-  T[0] = now;
-  S[0] = avail;
+  E[0].t = now;
+  E[0].seg = avail;
   bool overflow = false;
   // value of the segment at time t = avail + sum of releases with end <= t
   for (uint32_t k = lo; k < hi && !overflow; ++k) {
@@ -550,25 +538,19 @@ __global__ void k_node_init(ClusterDev cl, RunningDev rn, TimelineDev tl, int64_
     if (end < now + 1) end = now + 1;
     const Row res = rn.slot_res[k];
     uint32_t idx = 1;
-    while (idx < n && T[idx] < end) ++idx;
-    if (idx == n || T[idx] != end) {
+    while (idx < n && E[idx].t < end) ++idx;
+    if (idx == n || E[idx].t != end) {
       if (n + 2 > tl.cap) { overflow = true; break; }  // + sentinel would not fit
-      for (uint32_t m = n; m > idx; --m) { T[m] = T[m - 1]; S[m] = S[m - 1]; }
-      T[idx] = end;
-      S[idx] = S[idx - 1];
+      for (uint32_t m = n; m > idx; --m) E[m] = E[m - 1];
+      E[idx].t = end;
+      E[idx].seg = E[idx - 1].seg;
       ++n;
     }
-    for (uint32_t m = idx; m < n; ++m) row_add(S[m], res);
+    for (uint32_t m = idx; m < n; ++m) row_add(E[m].seg, res);
   }
-  T[n] = kInf;  // time_avail_res_map[end].SetToZero(), JobScheduler.h:331
-  row_zero(S[n]);
+  E[n].t = kInf;  // time_avail_res_map[end].SetToZero(), JobScheduler.h:331
+  row_zero(E[n].seg);
   ++n;
-  Row acc;
-  pm_identity(acc);
-  for (uint32_t m = 0; m < n; ++m) {
-    pm_absorb(acc, S[m]);
-    P[m] = acc;
-  }
   tl.n[g] = n;
   tl.skip[g] = (overflow || n >= max_jobs) ? 1 : 0;  // JobScheduler.cpp:5230
 }
@@ -578,7 +560,8 @@ __global__ void k_node_init(ClusterDev cl, RunningDev rn, TimelineDev tl, int64_
 // bit(r, q) = node q of job r's partition passes the node-list filters
 // (JobScheduler.cpp:5238-5256) and get_max_tasks(res_total) > 0 (:5258).
 // One warp per queue rank; lane l evaluates node 32*w + l; __ballot_sync
-// packs the word.
+// packs the word. Rows are `words_per_row` (a multiple of 4) words apart so
+// the commit kernel can fetch a row with one 16-byte-aligned bulk copy.
 // ------------------------------------------------------------------------
 __global__ void k_feas_bitmap(ClusterDev cl, PendingDev pd, const JobQ* jobq, const uint32_t* n_queued_ptr,
                               uint32_t words_per_row, uint32_t* bitmap) {
@@ -614,442 +597,708 @@ __global__ void k_feas_bitmap(ClusterDev cl, PendingDev pd, const JobQ* jobq, co
 // ------------------------------------------------------------------------
 // K-commit: the sequential job loop (JobScheduler.cpp:5777-5867), one
 // persistent CTA per partition, node-parallel inside each job.
+//
+// One SM issues 128 lane-instructions per cycle, so anything done "per node per
+// job" must be a handful of instructions, and anything done by one warp must be
+// a short dependency chain. Hence:
+//  * per node the CTA keeps in shared memory: cost (NodeRater::cost), the cpu
+//    count and packed gres slot counts of the first timeline segment (a cheap,
+//    conservative pre-filter), the entry count, skip flag, res_total class and
+//    the (cost, node)-sorted order;
+//  * partition-wide upper bounds on those first-segment counts (they only
+//    shrink inside a tick) let a job that cannot start anywhere skip the scan;
+//  * the scan walks the cost order in CTA-sized chunks and stops at the first
+//    chunk that yields enough nodes; candidates are tested by exactly as many
+//    warps as nodes are still needed;
+//  * timelines live in HBM/L2 as 80-byte entries; a warp opens a node by
+//    loading up to 64 entries into registers once and runs the window test
+//    (ballot + REDUX.AND), the allocation, the earliest-start search
+//    (ballot/clz run detection) and the update (per-lane stores) on them;
+//  * job records and capability-bitmap rows arrive through a 4-deep
+//    shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier)
+//    three jobs ahead.
 // ------------------------------------------------------------------------
+// optional phase profiling (-DCRANE_PROFILE builds only; never in the product .so)
+#ifdef CRANE_PROFILE
+#define PROF_DECL long long prof_last = clock64(); unsigned long long prof_acc[16] = {0}
+#define PROF(i) do { if (threadIdx.x == 0) { long long t__ = clock64(); prof_acc[i] += (unsigned long long)(t__ - prof_last); prof_last = t__; } } while (0)
+#define PROF_CNT(i, v) do { if (threadIdx.x == 0) prof_acc[i] += (v); } while (0)
+#define PROF_FLUSH(dst) do { if (threadIdx.x == 0 && (dst)) for (int i__ = 0; i__ < 16; ++i__) (dst)[blockIdx.x * 16 + i__] = prof_acc[i__]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_CNT(i, v)
+#define PROF_FLUSH(dst)
+#endif
+
 struct CommitArgs {
   ClusterDev cl;
   TimelineDev tl;
   const JobQ* jobq;
   const uint32_t* part_job_off;  // [n_parts+1] ranges of jobq
   const uint32_t* bitmap;
-  uint32_t words_per_row;
+  uint32_t words_per_row;        // multiple of 4
   PlaceDev out;
-  Row* scratch_alloc;            // [n_slots] per-partition scratch (slot-range indexed)
   int64_t now;
   int64_t max_window;
   uint32_t max_jobs;
+  unsigned long long* prof;      // [n_parts][16] cycle counters (profiling builds)
 };
 
-// shared-memory carve-up for a partition of mp nodes
+constexpr int kRing = 4;            // prefetch ring depth (jobs)
+constexpr int kCommitThreads = 256; // CTA size of k_commit
+constexpr int kHeld = 8;            // reorder: positions per thread per round
+
 struct CommitSmem {
-  double* cost;        // [mp]  NodeRater::cost
-  long long* cpu0;     // [mp]  cpu of the first timeline segment (pre-filter)
-  unsigned long long* gcnt;  // [mp] packed gres slot counts of the first segment
-  uint16_t* order;     // [mp]  position -> local node, ascending (cost, node)
-  uint16_t* pos;       // [mp]  local node -> position
-  uint16_t* cand;      // [mp]  scratch: candidates / selection
-  uint8_t* skip;       // [mp]
-  uint32_t* bits;      // [words] capability bitmap row of the current job
+  uint32_t* bits_ring;         // [kRing][words]
+  double* cost;                // [mp]  NodeRater::cost
+  long long* cpu0;             // [mp]  cpu of the first timeline segment
+  unsigned long long* gcnt;    // [mp]  packed gres slot counts of the first segment
+  uint16_t* order;             // [mp]  position -> local node, ascending (cost, node)
+  uint16_t* pos;               // [mp]  local node -> position
+  uint16_t* sel;               // [mp]  selected nodes of the current job
+  uint16_t* nseg;              // [mp]  timeline entry counts
+  uint8_t* skip;               // [mp]
+  uint8_t* cls;                // [mp]
 };
 __host__ __device__ inline size_t commit_smem_bytes(uint32_t mp, uint32_t words) {
-  size_t b = 0;
+  size_t b = (size_t)kRing * words * 4;
   b += (size_t)mp * 8 * 3;
-  b += (size_t)mp * 2 * 3;
-  b += ((size_t)mp + 7) / 8 * 8;
-  b += (size_t)words * 4 + 16;
+  b += (size_t)mp * 2 * 4;
+  b += (size_t)mp * 2;
   return b + 64;
 }
 
-// number of timeline entries with time < bound (kStrict) or <= bound
-template <bool kStrict>
-__device__ __forceinline__ uint32_t tl_count_before(const int64_t* T, uint32_t n, int64_t bound) {
-  const int lane = lane_id();
-  uint32_t cnt = 0;
-  for (uint32_t base = 0; base < n; base += 32) {
-    uint32_t i = base + lane;
-    int64_t t = i < n ? T[i] : kInf;
-    bool in = i < n && (kStrict ? t < bound : t <= bound);
-    unsigned m = __ballot_sync(kFullMask, in);
-    cnt += __popc(m);
-    if (m != kFullMask) break;
+// ---- TMA 1-D bulk copy + mbarrier (sm_90+/sm_100a) --------------------------
+#ifdef CRANE_EMU
+__device__ __forceinline__ void mbar_init(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void fence_mbar_init() {}
+#else
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
   }
-  return cnt;
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+#endif
+
+// ResourceView::GetFeasibleResourceInNode with the concrete pick, one shared
+// out-of-line instance (keeps the per-job instruction footprint small)
+__device__ __noinline__ bool feasible_alloc(const View& req, const Row& avail, Row& alloc) {
+  return feasible<true>(req, avail, c_dict, &alloc);
 }
 
-// the exact per-node test of JobScheduler.cpp:5285-5334 for one candidate:
-// window minimum over the segments that start before now+time_limit, then
-// get_max_tasks(min) > 0. All lanes of the warp return the same verdict.
-__device__ __forceinline__ bool window_check(const TimelineDev& tl, const ClusterDev& cl, uint32_t g,
-                                             const JobQ& jq, int64_t w_end, Row* win_row) {
-  const int64_t* T = tl.time + (size_t)g * tl.cap;
-  uint32_t n = tl.n[g];
-  uint32_t cnt = tl_count_before<true>(T, n, w_end);
-  const Row pm = tl.pm[(size_t)g * tl.cap + (cnt - 1)];
-  if (jq.flags & 1u) {  // exclusive: every segment in the window must hold res_total
-    const Row total = cl.slot_total[g];
-    *win_row = total;
-    return row_le(total, pm);
-  }
-  Row a0 = tl.avail0[g];
-  // stale pre-filter on res_avail (JobScheduler.cpp:5310) is implied: the
-  // window row is <= res_avail in every compared field.
-  window_row(*win_row, a0, pm);
-  return feasible<false>(jq.req, *win_row, c_dict, nullptr);
+__device__ __forceinline__ uint64_t warp_and64(uint64_t v) {
+  const uint32_t lo = __reduce_and_sync(kFullMask, (uint32_t)v);
+  const uint32_t hi = __reduce_and_sync(kFullMask, (uint32_t)(v >> 32));
+  return (uint64_t)hi << 32 | lo;
 }
 
-// earliest t >= T0 such that `alloc` <= every segment overlapping
-// [t, t+limit) on node g; kInf if none. One warp, lanes = segments.
-// (per-node half of EarliestStartSubsetSelector, JobScheduler.h:806-849)
-__device__ __forceinline__ int64_t earliest_on_node(const TimelineDev& tl, uint32_t g, const Row& alloc,
-                                                    int64_t T0, int64_t limit) {
-  const int lane = lane_id();
-  const int64_t* T = tl.time + (size_t)g * tl.cap;
-  const Row* S = tl.seg + (size_t)g * tl.cap;
-  const uint32_t n = tl.n[g];
-  int64_t carry = -1;  // start time of the satisfied run that reaches this chunk, or -1
+// ---- a node's timeline held by one warp -------------------------------------
+// lane l holds entries l and l+32 (timelines of up to 64 entries). Longer
+// timelines take the *_big paths below, which walk the entries in memory.
+struct NodeRegs {
+  int64_t t0, t1;
+  Row s0, s1;
+  uint32_t n;
+};
+
+__device__ __forceinline__ void node_open(const TimelineDev& tl, uint32_t g, uint32_t n, NodeRegs& nr) {
+  const TlEntry* E = tl.ent + (size_t)g * tl.cap;
+  const uint32_t lane = lane_id();
+  nr.n = n;
+  nr.t0 = kInf;
+  nr.t1 = kInf;
+  row_zero(nr.s0);
+  row_zero(nr.s1);
+  if (n <= 64) {
+    if (lane < n) { const TlEntry e = E[lane]; nr.t0 = e.t; nr.s0 = e.seg; }
+    if (lane + 32 < n) { const TlEntry e = E[lane + 32]; nr.t1 = e.t; nr.s1 = e.seg; }
+  }
+}
+
+// The exact per-node test of JobScheduler.cpp:5285-5334 and the allocation of
+// :5340-5361 in one go: window minimum over the entries that start before
+// now+time_limit, get_max_tasks(min) > 0, and the concrete cores/slots taken
+// from that minimum. cpu/mem minima are tested per entry (ballot); the core
+// and gres masks are AND-reduced (see "the window minimum" in algebra.cuh).
+__device__ __forceinline__ bool window_finish(const View& req, const Row& a0, uint64_t c0, uint64_t c1, uint64_t c2,
+                                              uint64_t c3, uint64_t g0, uint64_t g1, Row& alloc) {
+  if (a0.cpu_raw < req.cpu_raw || a0.mem < req.mem) return false;  // res_avail itself (JS.cpp:5310)
+  Row wr;
+  wr.cpu_raw = req.cpu_raw;  // the minima were checked entry by entry
+  wr.mem = req.mem;
+  wr.mem_sw = 0;
+  wr.core[0] = a0.core[0] & warp_and64(c0);
+  wr.core[1] = a0.core[1] & warp_and64(c1);
+  wr.core[2] = a0.core[2] & warp_and64(c2);
+  wr.core[3] = a0.core[3] & warp_and64(c3);
+  wr.g[0] = a0.g[0] & warp_and64(g0);
+  wr.g[1] = a0.g[1] & warp_and64(g1);
+  return feasible_alloc(req, wr, alloc);
+}
+
+__device__ __forceinline__ bool node_test_now(const NodeRegs& nr, const View& req, bool exclusive, const Row& tot,
+                                              const Row& a0, int64_t w_end, Row& alloc) {
+  const bool in0 = nr.t0 < w_end, in1 = nr.t1 < w_end;
+  if (exclusive) {  // every entry in the window must still hold res_total (JS.cpp:5285-5293)
+    const bool ok = (!in0 || row_le(tot, nr.s0)) && (!in1 || row_le(tot, nr.s1));
+    alloc = tot;
+    return __all_sync(kFullMask, ok);
+  }
+  const bool ok = (!in0 || (nr.s0.cpu_raw >= req.cpu_raw && nr.s0.mem >= req.mem)) &&
+                  (!in1 || (nr.s1.cpu_raw >= req.cpu_raw && nr.s1.mem >= req.mem));
+  if (!__all_sync(kFullMask, ok)) return false;
+  const bool e0 = in0 && !core_empty(nr.s0), e1 = in1 && !core_empty(nr.s1);
+  const uint64_t ones = ~0ull;
+  return window_finish(req, a0, (e0 ? nr.s0.core[0] : ones) & (e1 ? nr.s1.core[0] : ones),
+                       (e0 ? nr.s0.core[1] : ones) & (e1 ? nr.s1.core[1] : ones),
+                       (e0 ? nr.s0.core[2] : ones) & (e1 ? nr.s1.core[2] : ones),
+                       (e0 ? nr.s0.core[3] : ones) & (e1 ? nr.s1.core[3] : ones),
+                       (in0 ? nr.s0.g[0] : ones) & (in1 ? nr.s1.g[0] : ones),
+                       (in0 ? nr.s0.g[1] : ones) & (in1 ? nr.s1.g[1] : ones), alloc);
+}
+
+__device__ __noinline__ bool node_test_now_big(const TimelineDev& tl, uint32_t g, uint32_t n, const View& req,
+                                               bool exclusive, const Row& tot, const Row& a0, int64_t w_end,
+                                               Row& alloc) {
+  const TlEntry* E = tl.ent + (size_t)g * tl.cap;
+  const uint32_t lane = lane_id();
+  const uint64_t ones = ~0ull;
+  uint64_t c0 = ones, c1 = ones, c2 = ones, c3 = ones, g0 = ones, g1 = ones;
+  bool ok = true;
   for (uint32_t base = 0; base < n; base += 32) {
-    uint32_t i = base + lane;
-    bool valid = i < n;
-    int64_t t = valid ? T[i] : kInf;
-    int64_t tend = (i + 1 < n) ? T[i + 1] : kInf;
+    const uint32_t i = base + lane;
+    bool in = false;
+    if (i < n) {
+      const TlEntry e = E[i];
+      in = e.t < w_end;
+      if (in) {
+        if (exclusive) ok = ok && row_le(tot, e.seg);
+        else {
+          ok = ok && e.seg.cpu_raw >= req.cpu_raw && e.seg.mem >= req.mem;
+          if (!core_empty(e.seg)) { c0 &= e.seg.core[0]; c1 &= e.seg.core[1]; c2 &= e.seg.core[2]; c3 &= e.seg.core[3]; }
+          g0 &= e.seg.g[0];
+          g1 &= e.seg.g[1];
+        }
+      }
+    }
+    if (!__all_sync(kFullMask, in)) break;  // entries are time-sorted
+  }
+  if (!__all_sync(kFullMask, ok)) return false;
+  if (exclusive) { alloc = tot; return true; }
+  return window_finish(req, a0, c0, c1, c2, c3, g0, g1, alloc);
+}
+
+// one 32-entry chunk of the earliest-fit scan: sat = this lane's entry holds the
+// allocation and ends after T0; carry = start of the satisfied run that reaches
+// the chunk from the left, or -1. Run starts come from the ballot of breakers.
+__device__ __forceinline__ bool earliest_chunk(int64_t t, int64_t tend, bool sat, int64_t T0, int64_t limit,
+                                               int64_t& carry, int64_t& result) {
+  const uint32_t lane = lane_id();
+  const unsigned bm = __ballot_sync(kFullMask, !sat);
+  const unsigned below = bm & ((1u << lane) - 1u);
+  const uint32_t r = below ? 32u - (uint32_t)__clz((int)below) : 0u;  // first lane of my run in this chunk
+  int64_t rs = shfl_i64(t, (int)r);
+  rs = rs > T0 ? rs : T0;
+  if (!below && carry >= 0) rs = carry;  // the run started in an earlier chunk
+  const bool ok = sat && (tend == kInf || tend - rs >= limit);
+  const unsigned okm = __ballot_sync(kFullMask, ok);
+  if (okm) {
+    result = shfl_i64(rs, __ffs((int)okm) - 1);
+    return true;
+  }
+  const int64_t last = shfl_i64(rs, 31);
+  carry = ((bm >> 31) & 1u) ? -1 : last;
+  return false;
+}
+
+// earliest t >= T0 such that `alloc` <= every entry overlapping [t, t+limit)
+// on this node, kInf if none (per-node half of EarliestStartSubsetSelector,
+// JobScheduler.h:731-784, 806-849).
+__device__ __forceinline__ int64_t node_earliest(const NodeRegs& nr, const Row& alloc, int64_t T0, int64_t limit) {
+  const uint32_t lane = lane_id();
+  int64_t carry = -1, result = kInf;
+  {
+    int64_t tend = shfl_i64(nr.t0, lane + 1 < 32 ? (int)lane + 1 : (int)lane);
+    const int64_t t32 = shfl_i64(nr.t1, 0);
+    if (lane == 31) tend = t32;
+    const bool sat = lane < nr.n && tend > T0 && row_le(alloc, nr.s0);
+    if (earliest_chunk(nr.t0, tend, sat, T0, limit, carry, result)) return result;
+  }
+  if (nr.n > 32) {
+    int64_t tend = shfl_i64(nr.t1, lane + 1 < 32 ? (int)lane + 1 : (int)lane);
+    if (lane == 31) tend = kInf;
+    const bool sat = lane + 32 < nr.n && tend > T0 && row_le(alloc, nr.s1);
+    if (earliest_chunk(nr.t1, tend, sat, T0, limit, carry, result)) return result;
+  }
+  return kInf;
+}
+
+__device__ __noinline__ int64_t node_earliest_big(const TimelineDev& tl, uint32_t g, uint32_t n, const Row& alloc,
+                                                  int64_t T0, int64_t limit) {
+  const uint32_t lane = lane_id();
+  const TlEntry* E = tl.ent + (size_t)g * tl.cap;
+  int64_t carry = -1, result = kInf;
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t i = base + lane;
+    int64_t t = kInf, tend = kInf;
     bool sat = false;
-    if (valid && tend > T0) {
-      const Row s = S[i];
-      sat = row_le(alloc, s);
+    if (i < n) {
+      const TlEntry e = E[i];
+      t = e.t;
+      tend = (i + 1 < n) ? E[i + 1].t : kInf;
+      sat = tend > T0 && row_le(alloc, e.seg);
     }
-    bool breaker = !sat;  // unsatisfied, or entirely before T0, or past the end
-    unsigned bm = __ballot_sync(kFullMask, breaker);
-    bool prev_break = lane == 0 ? (carry < 0) : ((bm >> (lane - 1)) & 1u);
-    int64_t startv = (!breaker && prev_break) ? (t > T0 ? t : T0) : -1;
-    if (lane == 0 && !breaker && !prev_break) startv = carry;
-    // inclusive max-scan: run starts are non-decreasing along the timeline
-    for (int o = 1; o < 32; o <<= 1) {
-      int64_t up = shfl_i64(startv, lane - o >= 0 ? lane - o : lane);
-      if (lane >= o && up > startv) startv = up;
-    }
-    bool ok = !breaker && (tend == kInf || tend - startv >= limit);
-    unsigned okm = __ballot_sync(kFullMask, ok);
-    if (okm) {
-      int first = __ffs((int)okm) - 1;
-      return shfl_i64(startv, first);
-    }
-    bool last_break = (bm >> 31) & 1u;
-    int64_t last_start = shfl_i64(startv, 31);
-    carry = last_break ? -1 : last_start;
+    if (earliest_chunk(t, tend, sat, T0, limit, carry, result)) return result;
   }
   return kInf;
 }
 
 // NodeState::UpdateResourceInNode (JobScheduler.h:334-453, allocation
-// direction) on the array timeline of slot g, by one warp, followed by the
-// prefix-min refresh. Returns the new entry count.
-__device__ __forceinline__ uint32_t timeline_update(const TimelineDev& tl, uint32_t g, int64_t start,
-                                                    int64_t end, const Row& alloc) {
-  const int lane = lane_id();
-  int64_t* T = tl.time + (size_t)g * tl.cap;
-  Row* S = tl.seg + (size_t)g * tl.cap;
-  Row* P = tl.pm + (size_t)g * tl.cap;
-  const uint32_t n = tl.n[g];
-  const uint32_t i_s = tl_count_before<false>(T, n, start) - 1;  // last key <= start
-  const uint32_t i_e = tl_count_before<false>(T, n, end) - 1;    // last key <= end
-  const bool ins_s = T[i_s] != start;
-  const bool ins_e = T[i_e] != end;
-  const Row seg_s = S[i_s];  // values before any modification
-  const Row seg_e = S[i_e];
-  const uint32_t add = (ins_s ? 1u : 0u) + (ins_e ? 1u : 0u);
-  __syncwarp();
-  // move old entries (i_s, n) upward, top chunk first; subtract inside [start,end)
-  if (n > i_s + 1) {
-    int64_t hi = (int64_t)n - 1;
-    const int64_t lo = (int64_t)i_s + 1;
-    while (hi >= lo) {
-      int64_t j = hi - lane;
-      bool act = j >= lo;
-      int64_t t = 0;
-      Row r;
-      if (act) { t = T[j]; r = S[j]; }
-      __syncwarp();
-      if (act) {
-        if (t >= start && t < end) row_sub(r, alloc);
-        uint32_t nj = (uint32_t)j + (ins_s ? 1u : 0u) + (((uint32_t)j > i_e && ins_e) ? 1u : 0u);
-        T[nj] = t;
-        S[nj] = r;
+// direction): breakpoints at start/end, subtract inside [start, end). Every
+// lane writes its own entries to their new places; the lanes holding the
+// covering segments also write the two inserted breakpoints. Lane 0 receives
+// the (new) first segment. Returns the new entry count.
+__device__ __forceinline__ uint32_t node_update(const TimelineDev& tl, uint32_t g, const NodeRegs& nr, int64_t start,
+                                                int64_t end, const Row& alloc, Row& seg0) {
+  const uint32_t lane = lane_id();
+  TlEntry* E = tl.ent + (size_t)g * tl.cap;
+  const uint32_t n = nr.n;
+  const uint32_t i_s = __popc(__ballot_sync(kFullMask, nr.t0 <= start)) + __popc(__ballot_sync(kFullMask, nr.t1 <= start)) - 1;
+  const uint32_t i_e = __popc(__ballot_sync(kFullMask, nr.t0 <= end)) + __popc(__ballot_sync(kFullMask, nr.t1 <= end)) - 1;
+  const uint32_t ins_s = __any_sync(kFullMask, nr.t0 == start || nr.t1 == start) ? 0u : 1u;
+  const uint32_t ins_e = __any_sync(kFullMask, nr.t0 == end || nr.t1 == end) ? 0u : 1u;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t j = lane + 32u * h;
+    if (j >= n) continue;
+    TlEntry e;
+    e.t = h ? nr.t1 : nr.t0;
+    e.seg = h ? nr.s1 : nr.s0;
+    if (j == i_e && ins_e) {  // new breakpoint at `end` keeps the un-subtracted value
+      TlEntry f;
+      f.t = end;
+      f.seg = e.seg;
+      E[i_e + ins_s + 1] = f;
+    }
+    if (j > i_s) {
+      const uint32_t nj = j + ins_s + (j > i_e ? ins_e : 0u);
+      const bool sub = e.t < end;  // e.t > start here
+      if (sub) row_sub(e.seg, alloc);
+      if (sub || nj != j) E[nj] = e;
+    } else if (j == i_s) {
+      row_sub(e.seg, alloc);
+      if (ins_s) {  // case #3: copy of the covering segment at `start`, minus the job
+        e.t = start;
+        E[i_s + 1] = e;
+      } else {      // case #4: the key `start` exists
+        E[i_s] = e;
       }
-      __syncwarp();
-      hi -= 32;
     }
   }
   if (lane == 0) {
-    if (ins_s) {  // case #3: copy of the covering segment, minus the job
-      Row r = seg_s;
-      row_sub(r, alloc);
-      T[i_s + 1] = start;
-      S[i_s + 1] = r;
-    } else {      // case #4: key == start already exists
-      Row r = seg_s;
-      row_sub(r, alloc);
-      S[i_s] = r;
-    }
-    if (ins_e) {  // new breakpoint at `end` keeps the un-subtracted value
-      uint32_t ne = i_e + (ins_s ? 1u : 0u) + 1u;
-      T[ne] = end;
-      S[ne] = seg_e;
-    }
+    seg0 = nr.s0;
+    if (i_s == 0 && !ins_s) row_sub(seg0, alloc);
+    tl.n[g] = n + ins_s + ins_e;
   }
-  __syncwarp();
-  const uint32_t nn = n + add;
-  // refresh prefix minima from the first changed entry
-  uint32_t m0 = ins_s ? i_s + 1 : i_s;
-  Row carry;
-  if (m0 > 0) carry = P[m0 - 1]; else pm_identity(carry);
-  for (uint32_t base = m0; base < nn; base += 32) {
-    uint32_t i = base + lane;
-    Row v;
-    pm_identity(v);
-    if (i < nn) { const Row s = S[i]; pm_absorb(v, s); }
-    for (int o = 1; o < 32; o <<= 1) {
-      Row up;
-      row_shfl(up, v, lane - o >= 0 ? lane - o : lane);
-      if (lane >= o) pm_combine(v, up);
-    }
-    pm_combine(v, carry);
-    if (i < nn) P[i] = v;
-    Row last;
-    row_shfl(last, v, 31);
-    carry = last;
-  }
-  __syncwarp();
-  if (lane == 0) tl.n[g] = nn;
-  return nn;
+  return n + ins_s + ins_e;
 }
 
-// move local node u (whose cost just grew to new_cost) toward the back of the
-// (cost, node) order; block-wide. NodeSelector::UpdateCost's erase+emplace in
+__device__ __noinline__ uint32_t node_update_big(const TimelineDev& tl, uint32_t g, uint32_t n, int64_t start,
+                                                 int64_t end, const Row& alloc, Row& seg0) {
+  const uint32_t lane = lane_id();
+  TlEntry* E = tl.ent + (size_t)g * tl.cap;
+  uint32_t cnt_s = 0, cnt_e = 0;
+  bool has_s = false, has_e = false;
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t i = base + lane;
+    const int64_t t = i < n ? E[i].t : kInf;
+    const unsigned ms = __ballot_sync(kFullMask, t <= start), me = __ballot_sync(kFullMask, t <= end);
+    cnt_s += __popc(ms);
+    cnt_e += __popc(me);
+    has_s = has_s || __any_sync(kFullMask, t == start);
+    has_e = has_e || __any_sync(kFullMask, t == end);
+    if (me != kFullMask) break;
+  }
+  const uint32_t i_s = cnt_s - 1, i_e = cnt_e - 1;
+  const uint32_t ins_s = has_s ? 0u : 1u, ins_e = has_e ? 0u : 1u;
+  const TlEntry es = E[i_s], ee = E[i_e];  // values before any modification
+  __syncwarp();
+  int64_t hi = (int64_t)n - 1;
+  const int64_t lo = (int64_t)i_s + 1;
+  while (hi >= lo) {  // move entries (i_s, n) upward, top chunk first
+    const int64_t j = hi - lane;
+    const bool act = j >= lo;
+    TlEntry e;
+    e.t = 0;
+    if (act) e = E[j];
+    __syncwarp();
+    if (act) {
+      if (e.t < end) row_sub(e.seg, alloc);
+      E[(uint32_t)j + ins_s + ((uint32_t)j > i_e ? ins_e : 0u)] = e;
+    }
+    __syncwarp();
+    hi -= 32;
+  }
+  if (lane == 0) {
+    TlEntry e = es;
+    row_sub(e.seg, alloc);
+    if (ins_s) { e.t = start; E[i_s + 1] = e; } else { E[i_s] = e; }
+    if (ins_e) { TlEntry f; f.t = end; f.seg = ee.seg; E[i_e + ins_s + 1] = f; }
+    tl.n[g] = n + ins_s + ins_e;
+  }
+  __syncwarp();
+  seg0 = E[0].seg;
+  return n + ins_s + ins_e;
+}
+
+__device__ __forceinline__ Row node_total(const ClusterDev& cl, const Row* class_rows, const CommitSmem& sm,
+                                          uint32_t base, uint32_t q) {
+  const uint8_t c = sm.cls[q];
+  if (c != 0xff) return class_rows[c];
+  return cl.slot_total[base + q];
+}
+
+// move local node u (cost grew to new_cost) toward the back of the (cost, node)
+// order. NodeSelector::UpdateCost's erase+emplace on
 // std::set<pair<double,NodeState*>> (JobScheduler.h:520-532), tie = node index.
-__device__ __forceinline__ void reorder_node(CommitSmem& sm, uint32_t mp, uint32_t u, double new_cost) {
-  __shared__ uint32_t s_stop;
+// Per round of kHeld*blockDim positions: all reads, barrier, all writes.
+__device__ __forceinline__ void reorder_node(CommitSmem& sm, uint32_t mp, uint32_t u, double new_cost,
+                                             uint32_t* s_ltcnt, uint32_t& flip) {
   const uint32_t p = sm.pos[u];
-  if (threadIdx.x == 0) s_stop = 0xffffffffu;
-  __syncthreads();
-  for (uint32_t base = p + 1; base < mp; base += blockDim.x) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t o = 0;
-    bool lt = false;
-    if (i < mp) {
-      o = sm.order[i];
-      double c = sm.cost[o];
-      lt = (c < new_cost) || (c == new_cost && o < u);
-      if (!lt) atomicMin(&s_stop, i);
+  uint32_t moved = 0;  // elements shifted so far
+  for (uint32_t r0 = p + 1;; r0 += kHeld * blockDim.x) {
+    uint16_t held[kHeld];
+    uint32_t nheld = 0;
+#pragma unroll
+    for (int k = 0; k < kHeld; ++k) {
+      const uint32_t i = r0 + threadIdx.x + k * blockDim.x;
+      if (nheld == (uint32_t)k && i < mp) {
+        const uint32_t o = sm.order[i];
+        const double c = sm.cost[o];
+        if ((c < new_cost) || (c == new_cost && o < u)) held[nheld++] = (uint16_t)o;  // sorted: a prefix
+      }
+    }
+    unsigned tot = nheld;
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFullMask, tot, o);
+    if (lane_id() == 0 && tot) atomicAdd(&s_ltcnt[flip], tot);
+    __syncthreads();
+    const uint32_t cnt = s_ltcnt[flip];
+    if (threadIdx.x == 0) s_ltcnt[flip ^ 1u] = 0;
+#pragma unroll
+    for (int k = 0; k < kHeld; ++k) {
+      if ((uint32_t)k < nheld) {
+        const uint32_t i = r0 + threadIdx.x + k * blockDim.x;
+        sm.order[i - 1] = held[k];
+        sm.pos[held[k]] = (uint16_t)(i - 1);
+      }
+    }
+    moved += cnt;
+    flip ^= 1u;
+    const bool more = cnt == kHeld * blockDim.x && r0 + kHeld * blockDim.x < mp;  // the whole round moved
+    if (!more) {
+      if (threadIdx.x == 0) {
+        sm.order[p + moved] = (uint16_t)u;
+        sm.pos[u] = (uint16_t)(p + moved);
+        sm.cost[u] = new_cost;
+      }
+      __syncthreads();
+      return;
     }
     __syncthreads();
-    if (i < mp && lt) {  // sorted => the lt positions form a prefix of (p, mp)
-      sm.order[i - 1] = (uint16_t)o;
-      sm.pos[o] = (uint16_t)(i - 1);
-    }
-    __syncthreads();
-    if (s_stop != 0xffffffffu) break;
   }
-  if (threadIdx.x == 0) {
-    uint32_t stop = s_stop == 0xffffffffu ? mp : s_stop;  // first position not less than u
-    sm.order[stop - 1] = (uint16_t)u;
-    sm.pos[u] = (uint16_t)(stop - 1);
-    sm.cost[u] = new_cost;
-  }
-  __syncthreads();
 }
 
-__global__ void __launch_bounds__(512, 1) k_commit(CommitArgs a) {
+__global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   CRANE_DYN_SMEM(unsigned char, smem_raw);
   const uint32_t part = blockIdx.x;
   const uint32_t base = a.cl.part_base[part];
   const uint32_t mp = a.cl.part_base[part + 1] - base;
   const uint32_t words = a.words_per_row;
-  const int lane = lane_id();
-  const int wid = warp_id();
-  const int nwarps = blockDim.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t wid = warp_id();
+  const uint32_t nw = blockDim.x >> 5;
 
   CommitSmem sm;
   {
-    unsigned char* ptr = smem_raw;
-    // widest element type first so every array is naturally aligned
+    unsigned char* ptr = smem_raw;  // 16-byte aligned; widest element types first
+    sm.bits_ring = reinterpret_cast<uint32_t*>(ptr); ptr += (size_t)kRing * words * 4;
     sm.cost = reinterpret_cast<double*>(ptr); ptr += (size_t)mp * 8;
     sm.cpu0 = reinterpret_cast<long long*>(ptr); ptr += (size_t)mp * 8;
     sm.gcnt = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)mp * 8;
-    sm.bits = reinterpret_cast<uint32_t*>(ptr); ptr += (size_t)words * 4;
     sm.order = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.pos = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
-    sm.cand = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
-    sm.skip = ptr;
+    sm.sel = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
+    sm.nseg = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
+    sm.skip = ptr; ptr += mp;
+    sm.cls = ptr;
   }
-  __shared__ JobQ s_job;
-  __shared__ uint32_t s_warp_cnt[32];
-  __shared__ uint32_t s_nsel, s_flag[32];
-  __shared__ int64_t s_tmax;
-  __shared__ int64_t s_tnode[32];
-  __shared__ uint32_t s_resource_label;
+  __shared__ JobQ s_jobs[kRing];
+  __shared__ __align__(8) uint64_t s_bar[kRing];
+  __shared__ Row s_classrow[kMaxClasses];
+  __shared__ uint16_t s_cand[kCommitThreads];
+  __shared__ uint32_t s_wcnt[32], s_pass[32], s_selw[32];
+  __shared__ int64_t s_t[32];
+  __shared__ long long s_wmax[32];
+  __shared__ unsigned long long s_wmaxg[32];
+  __shared__ long long s_ub_cpu;            // >= max over nodes of the first segment's cpu
+  __shared__ unsigned long long s_ub_g;     // >= per-entry max of the packed gres counts
+  __shared__ uint32_t s_label, s_ncap, s_ltcnt[2];
 
   // ---- load node state; initial order = ascending (cost, node) -----------
   for (uint32_t q = threadIdx.x; q < mp; q += blockDim.x) {
     const uint32_t g = base + q;
     sm.cost[q] = a.tl.cost0[g];
-    const Row s0 = a.tl.seg[(size_t)g * a.tl.cap];
+    const Row s0 = a.tl.ent[(size_t)g * a.tl.cap].seg;
     sm.cpu0[q] = s0.cpu_raw;
     sm.gcnt[q] = pack_gres_counts(s0);
     sm.skip[q] = a.tl.skip[g];
+    sm.nseg[q] = (uint16_t)a.tl.n[g];
+    sm.cls[q] = a.cl.slot_class[g];
+  }
+  if (threadIdx.x < kMaxClasses) s_classrow[threadIdx.x] = a.cl.class_rows[(size_t)part * kMaxClasses + threadIdx.x];
+  if (threadIdx.x == 0) {
+    s_ltcnt[0] = s_ltcnt[1] = 0;
+    s_ub_cpu = INT64_MAX;
+    s_ub_g = ~0ull;
+    for (int s = 0; s < kRing; ++s) mbar_init(&s_bar[s], 1);
+    fence_mbar_init();
   }
   __syncthreads();
-  // rank sort: position = number of nodes with a smaller (cost, node) key
-  for (uint32_t q = threadIdx.x; q < mp; q += blockDim.x) {
+  for (uint32_t q = threadIdx.x; q < mp; q += blockDim.x) {  // rank sort
     const double c = sm.cost[q];
     uint32_t rank = 0;
     for (uint32_t o = 0; o < mp; ++o) {
-      double co = sm.cost[o];
+      const double co = sm.cost[o];
       rank += (co < c || (co == c && o < q)) ? 1u : 0u;
     }
     sm.order[rank] = (uint16_t)q;
     sm.pos[q] = (uint16_t)rank;
   }
-  __syncthreads();
 
   const uint32_t r_begin = a.part_job_off[part], r_end = a.part_job_off[part + 1];
-  for (uint32_t r = r_begin; r < r_end; ++r) {
-    // ---- job record + capability row ------------------------------------
-    if (threadIdx.x < sizeof(JobQ) / 4)
-      reinterpret_cast<uint32_t*>(&s_job)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&a.jobq[r])[threadIdx.x];
-    for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) sm.bits[w] = a.bitmap[(size_t)r * words + w];
-    if (threadIdx.x == 0) { s_nsel = 0; s_resource_label = 0; }
-    __syncthreads();
-    const JobQ jq = s_job;
-    const uint32_t K = jq.node_num;
-    const bool exclusive = jq.flags & 1u;
-    const int64_t w_end = a.now + jq.time_limit;
-    bool start_now = false;
+  const uint32_t njobs = r_end - r_begin;
+  const uint32_t row_bytes = words * 4;
+  const uint32_t issuer = blockDim.x - 32;  // lane 0 of the last warp feeds the ring
+  auto issue = [&](uint32_t i) {
+    const uint32_t slot = i % kRing;
+    mbar_expect_tx(&s_bar[slot], (uint32_t)sizeof(JobQ) + row_bytes);
+    tma_load_1d(&s_jobs[slot], &a.jobq[r_begin + i], (uint32_t)sizeof(JobQ), &s_bar[slot]);
+    tma_load_1d(sm.bits_ring + (size_t)slot * words, a.bitmap + (size_t)(r_begin + i) * words, row_bytes, &s_bar[slot]);
+  };
+  if (threadIdx.x == issuer)
+    for (uint32_t i = 0; i < njobs && i < (uint32_t)kRing - 1; ++i) issue(i);
+  __syncthreads();
 
-    // ---- phase 1: nodes that can run the job now, in cost order ----------
-    // (JobScheduler.cpp:5224-5336); sm.cand[0..K) collects the selection
-    if (K <= mp) {
-      for (uint32_t cbase = 0; cbase < mp && !start_now; cbase += blockDim.x) {
+  uint32_t flip = 0;
+  PROF_DECL;
+  for (uint32_t ji = 0; ji < njobs; ++ji) {
+    PROF(15);
+    const uint32_t slot = ji % kRing;
+    if (threadIdx.x == issuer && ji + kRing - 1 < njobs) issue(ji + kRing - 1);  // its slot was last read in job ji-1
+    mbar_wait(&s_bar[slot], (ji / kRing) & 1u);
+    const JobQ& jq = s_jobs[slot];
+    const uint32_t* bits = sm.bits_ring + (size_t)slot * words;
+    const uint32_t K = jq.node_num;
+    const uint32_t jflags = jq.flags;
+    const bool exclusive = jflags & 1u;
+    const int64_t limit = jq.time_limit;
+    const int64_t w_end = a.now + limit;
+    const View req = jq.req;
+    if (threadIdx.x == 0) s_label = 0;
+    PROF(0);
+
+    NodeRegs nr;
+    Row my_alloc;
+    uint32_t held_q = 0xffffffffu;  // node whose timeline `nr` holds
+    int64_t start_time = 0;
+    bool placed = false, start_now = false;
+    uint32_t nsel = 0;
+
+    // ---- nodes that can run the job now, in cost order --------------------
+    // (JobScheduler.cpp:5224-5336). Skipped when the partition-wide bounds say
+    // no node passes the pre-filter (then the reference's loop finds none).
+    const bool may_fit = exclusive || (req.cpu_raw <= s_ub_cpu && (!(jflags & 2u) || gres_counts_ok(req, s_ub_g)));
+    if (K <= mp && may_fit) {
+      bool scanned_all = true;
+      long long mx_cpu = INT64_MIN;
+      unsigned long long mx_g = 0;
+      for (uint32_t cbase = 0; cbase < mp; cbase += blockDim.x) {
         const uint32_t i = cbase + threadIdx.x;
         bool cand = false;
         uint32_t q = 0;
         if (i < mp) {
           q = sm.order[i];
-          cand = ((sm.bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
-          if (cand && !exclusive)
-            cand = sm.cpu0[q] >= jq.req.cpu_raw && (!(jq.flags & 2u) || gres_counts_ok(jq.req, sm.gcnt[q]));
+          const long long c0 = sm.cpu0[q];
+          const unsigned long long gc = sm.gcnt[q];
+          mx_cpu = c0 > mx_cpu ? c0 : mx_cpu;
+          mx_g = (unsigned long long)__vmaxu4((unsigned)mx_g, (unsigned)gc) |
+                 (unsigned long long)__vmaxu4((unsigned)(mx_g >> 32), (unsigned)(gc >> 32)) << 32;
+          cand = ((bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
+          if (cand && !exclusive) cand = c0 >= req.cpu_raw && (!(jflags & 2u) || gres_counts_ok(req, gc));
         }
-        // ordered compaction of the candidates of this chunk
-        unsigned bm = __ballot_sync(kFullMask, cand);
-        if (lane == 0) s_warp_cnt[wid] = __popc(bm);
+        const unsigned bm = __ballot_sync(kFullMask, cand);
+        if (lane == 0) s_wcnt[wid] = __popc(bm);
         __syncthreads();
         uint32_t before = 0, total = 0;
-        for (int w = 0; w < nwarps; ++w) {
-          uint32_t c = s_warp_cnt[w];
-          if (w < wid) before += c;
+        for (uint32_t w = 0; w < nw; ++w) {
+          const uint32_t c = s_wcnt[w];
+          before += w < wid ? c : 0u;
           total += c;
         }
-        // candidates are staged behind the (< K) nodes already selected
-        const uint32_t nsel0 = s_nsel;
-        if (cand) sm.cand[nsel0 + before + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)q;
+        if (cand) s_cand[before + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)q;
         __syncthreads();
-        // exact window test, one warp per candidate, batches in order
-        for (uint32_t b0 = 0; b0 < total && !start_now; b0 += nwarps) {
-          const uint32_t ci = b0 + wid;
-          bool ok = false;
-          if (ci < total) {
-            Row wr;
-            ok = window_check(a.tl, a.cl, base + sm.cand[nsel0 + ci], jq, w_end, &wr);
+        PROF(1);
+        PROF_CNT(8, total);
+        // exact test, exactly as many warps as nodes still needed, in order
+        uint32_t b0 = 0;
+        while (b0 < total && !start_now) {
+          PROF_CNT(9, 1);
+          uint32_t W = K - nsel;
+          W = W < nw ? W : nw;
+          W = W < total - b0 ? W : total - b0;
+          bool pass = false;
+          if (wid < W) {
+            const uint32_t q2 = s_cand[b0 + wid];
+            const uint32_t g = base + q2;
+            const uint32_t n = sm.nseg[q2];
+            const Row a0 = a.tl.avail0[g];
+            Row tot;
+            if (exclusive) tot = node_total(a.cl, s_classrow, sm, base, q2);
+            node_open(a.tl, g, n, nr);
+            held_q = q2;
+            pass = n <= 64 ? node_test_now(nr, req, exclusive, tot, a0, w_end, my_alloc)
+                           : node_test_now_big(a.tl, g, n, req, exclusive, tot, a0, w_end, my_alloc);
+            if (lane == 0) s_pass[wid] = pass ? 1u : 0u;
           }
-          if (lane == 0) s_flag[wid] = ok ? 1u : 0u;
           __syncthreads();
-          if (threadIdx.x == 0) {
-            uint32_t ns = s_nsel;
-            for (int w = 0; w < nwarps && ns < K; ++w) {
-              if (b0 + w < total && s_flag[w]) {
-                sm.cand[ns] = sm.cand[nsel0 + b0 + w];  // ns <= nsel0 + b0 + w: in-place compaction
-                ++ns;
-              }
+          for (uint32_t w = 0; w < W; ++w) {
+            if (s_pass[w]) {
+              if (threadIdx.x == 0) { sm.sel[nsel] = s_cand[b0 + w]; if (nsel < 32) s_selw[nsel] = w; }
+              ++nsel;
             }
-            s_nsel = ns;
           }
-          __syncthreads();
-          if (s_nsel >= K) start_now = true;
+          b0 += W;
+          if (nsel >= K) start_now = true;
+          else __syncthreads();  // s_pass / s_cand are rewritten
         }
-        // keep the passing candidates compacted at the front for the next chunk:
-        // (already done in place: sm.cand[0..s_nsel) holds the selection)
+        PROF(2);
+        if (start_now) { scanned_all = false; break; }
+      }
+      if (!start_now && scanned_all) {
+        // every node was looked at: tighten the partition-wide bounds
+        for (int o = 16; o > 0; o >>= 1) {
+          const long long oc = __shfl_xor_sync(kFullMask, mx_cpu, o);
+          const unsigned long long og = __shfl_xor_sync(kFullMask, mx_g, o);
+          mx_cpu = oc > mx_cpu ? oc : mx_cpu;
+          mx_g = (unsigned long long)__vmaxu4((unsigned)mx_g, (unsigned)og) |
+                 (unsigned long long)__vmaxu4((unsigned)(mx_g >> 32), (unsigned)(og >> 32)) << 32;
+        }
+        if (lane == 0) { s_wmax[wid] = mx_cpu; s_wmaxg[wid] = mx_g; }
         __syncthreads();
+        if (threadIdx.x == 0) {
+          long long m = INT64_MIN;
+          unsigned long long mg = 0;
+          for (uint32_t w = 0; w < nw; ++w) {
+            m = s_wmax[w] > m ? s_wmax[w] : m;
+            mg = (unsigned long long)__vmaxu4((unsigned)mg, (unsigned)s_wmaxg[w]) |
+                 (unsigned long long)__vmaxu4((unsigned)(mg >> 32), (unsigned)(s_wmaxg[w] >> 32)) << 32;
+          }
+          s_ub_cpu = m;
+          s_ub_g = mg;
+        }
       }
     }
 
-    int64_t start_time = 0;
-    bool placed = false;
     if (start_now) {
       start_time = a.now;
       placed = true;
-      // allocation against the window minimum (JobScheduler.cpp:5338-5362)
-      for (uint32_t k = wid; k < K; k += nwarps) {
-        const uint32_t g = base + sm.cand[k];
-        Row wr, alloc;
-        window_check(a.tl, a.cl, g, jq, w_end, &wr);
-        if (exclusive) alloc = wr; else feasible<true>(jq.req, wr, c_dict, &alloc);
-        if (lane == 0) a.scratch_alloc[base + k] = alloc;
-      }
+      PROF_CNT(10, 1);
     } else {
-      // ---- phase 3: first K capable nodes, then backfill -----------------
-      // (JobScheduler.cpp:5269-5278, 5371-5404, 5407-5412)
+      // ---- backfill: the first K capable nodes in cost order, allocation
+      // against res_total, earliest common start (JobScheduler.cpp:5269-5278,
+      // 5371-5404; JobScheduler.h:806-849)
       __syncthreads();
-      if (threadIdx.x == 0) s_nsel = 0;
-      __syncthreads();
-      for (uint32_t cbase = 0; cbase < mp; cbase += blockDim.x) {
-        const uint32_t i = cbase + threadIdx.x;
-        bool cap = false;
-        uint32_t q = 0;
-        if (i < mp) {
-          q = sm.order[i];
-          cap = ((sm.bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
+      if (wid == 0) {
+        uint32_t cum = 0;
+        for (uint32_t i0 = 0; i0 < mp && cum < K; i0 += 32) {
+          const uint32_t i = i0 + lane;
+          bool cap = false;
+          uint32_t q = 0;
+          if (i < mp) {
+            q = sm.order[i];
+            cap = ((bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
+          }
+          const unsigned m = __ballot_sync(kFullMask, cap);
+          const uint32_t rank = cum + __popc(m & ((1u << lane) - 1u));
+          if (cap && rank < K) sm.sel[rank] = (uint16_t)q;
+          cum += __popc(m);
         }
-        unsigned bm = __ballot_sync(kFullMask, cap);
-        if (lane == 0) s_warp_cnt[wid] = __popc(bm);
-        __syncthreads();
-        uint32_t before = s_nsel, total = 0;
-        for (int w = 0; w < nwarps; ++w) {
-          uint32_t c = s_warp_cnt[w];
-          if (w < wid) before += c;
-          total += c;
-        }
-        uint32_t slot = before + __popc(bm & ((1u << lane) - 1u));
-        if (cap && slot < K) sm.cand[slot] = (uint16_t)q;
-        __syncthreads();
-        if (threadIdx.x == 0) s_nsel = s_nsel + total;
-        __syncthreads();
-        if (s_nsel >= K) break;
+        if (lane == 0) s_ncap = cum;
       }
-      if (K <= mp && s_nsel >= K) {
-        // allocation against res_total (JobScheduler.cpp:5381-5403)
-        for (uint32_t k = wid; k < K; k += nwarps) {
-          const uint32_t g = base + sm.cand[k];
-          const Row total = a.cl.slot_total[g];
-          Row alloc;
-          if (exclusive) alloc = total; else feasible<true>(jq.req, total, c_dict, &alloc);
-          if (lane == 0) a.scratch_alloc[base + k] = alloc;
-        }
-        __syncthreads();
-        // earliest common start: fixed point of the per-node earliest fits
+      __syncthreads();
+      PROF(4);
+      if (K <= mp && s_ncap >= K) {
+        PROF_CNT(12, 1);
         int64_t Tcur = a.now;
-        bool found = false, failed = false;
+        bool found = false, failed = false, first = true;
+        const bool resident = K <= nw;  // every node stays in its warp's registers
         while (!found && !failed) {
-          if (threadIdx.x == 0) s_tmax = Tcur;
-          __syncthreads();
-          for (uint32_t k0 = 0; k0 < K; k0 += nwarps) {
+          PROF_CNT(11, 1);
+          int64_t tmax = Tcur;
+          for (uint32_t k0 = 0; k0 < K; k0 += nw) {
             const uint32_t k = k0 + wid;
             int64_t t = Tcur;
             if (k < K) {
-              const Row alloc = a.scratch_alloc[base + k];
-              t = earliest_on_node(a.tl, base + sm.cand[k], alloc, Tcur, jq.time_limit);
+              const uint32_t q = sm.sel[k];
+              const uint32_t g = base + q;
+              const uint32_t n = sm.nseg[q];
+              if (!resident || first) {
+                const Row tot = node_total(a.cl, s_classrow, sm, base, q);
+                node_open(a.tl, g, n, nr);
+                held_q = q;
+                if (exclusive) my_alloc = tot; else feasible_alloc(req, tot, my_alloc);
+              }
+              t = n <= 64 ? node_earliest(nr, my_alloc, Tcur, limit) : node_earliest_big(a.tl, g, n, my_alloc, Tcur, limit);
             }
-            if (lane == 0) s_tnode[wid] = t;
+            if (lane == 0) s_t[wid] = t;
             __syncthreads();
-            if (threadIdx.x == 0) {
-              int64_t m = s_tmax;
-              for (int w = 0; w < nwarps; ++w) m = s_tnode[w] > m ? s_tnode[w] : m;
-              s_tmax = m;
-            }
-            __syncthreads();
+            for (uint32_t w = 0; w < nw; ++w) tmax = s_t[w] > tmax ? s_t[w] : tmax;
+            if (k0 + nw < K) __syncthreads();
           }
-          const int64_t Tn = s_tmax;
-          __syncthreads();
-          if (Tn == kInf) failed = true;
-          else if (Tn == Tcur) found = true;
-          else Tcur = Tn;
+          first = false;
+          if (tmax == kInf) failed = true;
+          else if (tmax == Tcur || K == 1) { found = true; Tcur = tmax; }
+          else { Tcur = tmax; __syncthreads(); }
         }
         // `current_time - now > kAlgoMaxTimeWindow` (JobScheduler.h:809)
         if (found && Tcur - a.now <= a.max_window) {
@@ -1057,60 +1306,87 @@ __global__ void __launch_bounds__(512, 1) k_commit(CommitArgs a) {
           start_time = Tcur;
         }
       }
+      PROF(5);
     }
 
-    __syncthreads();
-    // ---- commit: timeline update, cost, order, outputs -------------------
+    // ---- commit: timeline update, outputs, cost and order ------------------
     if (placed) {
-      const int64_t end_time = start_time + jq.time_limit;
-      for (uint32_t k = wid; k < K; k += nwarps) {
-        const uint32_t q = sm.cand[k];
+      const int64_t end_time = start_time + limit;
+      __syncthreads();  // sm.sel / s_selw complete
+      // updates one selected node with the warp's registers (reopening it if a
+      // later batch reused them) and writes its allocation, node-index ascending
+      // (deviation D3).
+      auto commit_node = [&](uint32_t k) {
+        const uint32_t q = sm.sel[k];
         const uint32_t g = base + q;
-        const Row alloc = a.scratch_alloc[base + k];
-        uint32_t nn = timeline_update(a.tl, g, start_time, end_time, alloc);
-        if (lane == 0) {
-          if (nn >= a.max_jobs) sm.skip[q] = 1;
-          if (start_time == a.now) {
-            const Row s0 = a.tl.seg[(size_t)g * a.tl.cap];
-            sm.cpu0[q] = s0.cpu_raw;
-            sm.gcnt[q] = pack_gres_counts(s0);
+        const uint32_t n = sm.nseg[q];
+        Row seg0;
+        uint32_t nn;
+        if (held_q == q && n <= 64) {
+          nn = node_update(a.tl, g, nr, start_time, end_time, my_alloc, seg0);
+        } else {
+          // registers hold another node (a later batch reused them, or K > warps)
+          // or the timeline is long: recompute the allocation and update in memory
+          if (held_q != q) {
+            const Row tot = node_total(a.cl, s_classrow, sm, base, q);
+            if (start_now) node_test_now_big(a.tl, g, n, req, exclusive, tot, a.tl.avail0[g], w_end, my_alloc);
+            else if (exclusive) my_alloc = tot;
+            else feasible_alloc(req, tot, my_alloc);
           }
-          // pending-reason label for future starts (JobScheduler.cpp:5842-5848)
-          if (start_time != a.now && !row_le(alloc, a.tl.avail0[g])) atomicOr(&s_resource_label, 1u);
+          nn = node_update_big(a.tl, g, n, start_time, end_time, my_alloc, seg0);
         }
+        held_q = 0xffffffffu;
+        uint32_t rank = 0;
+        for (uint32_t m = lane; m < K; m += 32) rank += sm.sel[m] < q ? 1u : 0u;
+        for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(kFullMask, rank, o);
+        if (lane == 0) {
+          sm.nseg[q] = (uint16_t)nn;
+          if (nn >= a.max_jobs) sm.skip[q] = 1;
+          sm.cpu0[q] = seg0.cpu_raw;
+          sm.gcnt[q] = pack_gres_counts(seg0);
+          const uint32_t dst = jq.alloc_off + rank;
+          a.out.alloc_node[dst] = a.cl.slot_node[g];
+          a.out.alloc_ntasks[dst] = jq.ntasks_per_node;
+          a.out.alloc_res[dst] = my_alloc;
+          // pending-reason label for future starts (JobScheduler.cpp:5842-5848)
+          if (start_time != a.now && !row_le(my_alloc, a.tl.avail0[g])) atomicOr(&s_label, 1u);
+        }
+      };
+      // start-now with K <= warps: the warp that tested a node owns it (possibly
+      // one per batch); otherwise nodes are dealt round-robin
+      const bool owner_mode = start_now && K <= nw;
+#pragma unroll 1
+      for (uint32_t k = 0; k < K; ++k) {
+        const bool mine = owner_mode ? (s_selw[k] == wid) : (k % nw == wid);
+        if (mine) commit_node(k);
       }
       __syncthreads();
-      // outputs, node-index ascending (deviation D3)
-      for (uint32_t k = threadIdx.x; k < K; k += blockDim.x) {
-        const uint32_t q = sm.cand[k];
-        uint32_t rank = 0;
-        for (uint32_t m = 0; m < K; ++m) rank += sm.cand[m] < q ? 1u : 0u;
-        const uint32_t dst = jq.alloc_off + rank;
-        a.out.alloc_node[dst] = a.cl.slot_node[base + q];
-        a.out.alloc_ntasks[dst] = jq.ntasks_per_node;
-        a.out.alloc_res[dst] = a.scratch_alloc[base + k];
-      }
+      PROF(6);
       if (threadIdx.x == 0) {
         a.out.start_time[jq.job] = start_time;
         a.out.end_time[jq.job] = end_time;
         a.out.n_alloc[jq.job] = K;
         uint8_t reason = CRANE_REASON_NONE;
-        if (start_time != a.now) reason = s_resource_label ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY;
+        if (start_time != a.now) reason = s_label ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY;
         a.out.reason[jq.job] = reason;
       }
-      // cost += (end-start) * cpu ratio, then re-key (JobScheduler.h:46-52,520-532)
+      // cost += (end-start) * cpu ratio, then re-key (JobScheduler.h:46-52,520-532).
+      // The allocation's cpu is the job's per-node request, or the node total
+      // for exclusive jobs.
       for (uint32_t k = 0; k < K; ++k) {
-        const uint32_t q = sm.cand[k];
-        const uint32_t g = base + q;
-        const double delta = cost_delta(jq.time_limit, a.scratch_alloc[base + k].cpu_raw, a.cl.slot_total[g].cpu_raw);
+        const uint32_t q = sm.sel[k];
+        const int64_t tot_cpu = node_total(a.cl, s_classrow, sm, base, q).cpu_raw;
+        const double delta = cost_delta(limit, exclusive ? tot_cpu : req.cpu_raw, tot_cpu);
         const double nc = __dadd_rn(sm.cost[q], delta);
-        reorder_node(sm, mp, q, nc);
+        reorder_node(sm, mp, q, nc, s_ltcnt, flip);
       }
+      PROF(7);
     } else {
       if (threadIdx.x == 0) a.out.reason[jq.job] = CRANE_REASON_RESOURCE;  // JobScheduler.cpp:5802
+      __syncthreads();
     }
-    __syncthreads();
   }
+  PROF_FLUSH(a.prof);
 }
 
 }  // namespace crane

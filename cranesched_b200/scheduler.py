@@ -59,6 +59,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.crane_sched_get_timing.argtypes = [C.c_void_p, P(abi.TimingC)]
     lib.crane_sched_debug_bitmap.restype = C.c_int
     lib.crane_sched_debug_bitmap.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_uint32), P(C.c_uint32)]
+    lib.crane_sched_debug_profile.restype = C.c_int
+    lib.crane_sched_debug_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     _libs[path] = lib
     return lib
 
@@ -66,7 +68,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 EXPORTS = ("crane_sched_create", "crane_sched_destroy", "crane_sched_last_error",
            "crane_sched_set_cluster", "crane_sched_node_select", "crane_sched_upload",
            "crane_sched_run", "crane_sched_fetch", "crane_sched_sync", "crane_sched_get_timing",
-           "crane_sched_debug_bitmap")
+           "crane_sched_debug_bitmap", "crane_sched_debug_profile")
 
 
 class GpuScheduler:
@@ -134,6 +136,12 @@ class GpuScheduler:
         t = abi.TimingC()
         self._check(self._lib.crane_sched_get_timing(self._h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in abi.TimingC._fields_}
+
+    def debug_profile(self):
+        import numpy as np
+        buf = np.zeros((self.cluster.n_partitions, 16), np.uint64)
+        self._check(self._lib.crane_sched_debug_profile(self._h, buf.ctypes.data, buf.size))
+        return buf
 
     def debug_bitmap(self):
         import numpy as np

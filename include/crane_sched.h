@@ -237,6 +237,11 @@ int crane_sched_get_timing(const crane_sched_t* h, crane_sched_timing_t* t);
 int crane_sched_debug_bitmap(crane_sched_t* h, uint32_t* dst, size_t cap_words,
                              uint32_t* rows, uint32_t* words_per_row);
 
+/* Per-partition phase cycle counters of the commit kernel, [n_partitions][16];
+ * all zero unless the library was built with -DCRANE_PROFILE (a profiling
+ * build, never the shipped one). For tools/. */
+int crane_sched_debug_profile(crane_sched_t* h, unsigned long long* dst, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

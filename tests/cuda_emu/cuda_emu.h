@@ -172,6 +172,33 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   w->bar.arrive_and_wait();
   return m;
 }
+inline unsigned __reduce_and_sync(unsigned, unsigned v) {
+  emu::WarpCtx* w = emu::tctx.warp;
+  w->slot[emu::tctx.lane] = v;
+  w->bar.arrive_and_wait();
+  unsigned r = 0xffffffffu;
+  for (int i = 0; i < 32; ++i) r &= (unsigned)w->slot[i];
+  w->bar.arrive_and_wait();
+  return r;
+}
+inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+  emu::WarpCtx* w = emu::tctx.warp;
+  w->slot[emu::tctx.lane] = v;
+  w->bar.arrive_and_wait();
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r = (unsigned)w->slot[i] > r ? (unsigned)w->slot[i] : r;
+  w->bar.arrive_and_wait();
+  return r;
+}
+inline unsigned __vmaxu4(unsigned a, unsigned b) {
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) {
+    unsigned x = (a >> (8 * i)) & 0xff, y = (b >> (8 * i)) & 0xff;
+    r |= (x > y ? x : y) << (8 * i);
+  }
+  return r;
+}
+inline long long clock64() { return (long long)std::chrono::steady_clock::now().time_since_epoch().count(); }
 inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
 inline int __all_sync(unsigned m, int p) { return __ballot_sync(m, p) == 0xffffffffu; }
 inline int __syncthreads_or(int p) {

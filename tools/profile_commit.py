@@ -1,0 +1,34 @@
+"""Phase breakdown of k_commit (needs the -DCRANE_PROFILE build)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from cranesched_b200 import synth, abi
+from cranesched_b200.scheduler import GpuScheduler
+from cranesched_b200.build import CSRC
+
+NAMES = ["0 job load", "1 scan+compact", "2 exact batches", "3 alloc(now)", "4 total-list scan", "5 alloc+earliest",
+         "6 timeline update", "7 outputs+reorder", "8 #cand", "9 #batches", "10 #start-now", "11 #fixpoint iters",
+         "12 #backfill", "13", "14", "15 loop tail"]
+cfg_id = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+kw = {}
+if len(sys.argv) > 3:
+    kw = dict(n_jobs=int(sys.argv[2]), n_nodes=int(sys.argv[3]))
+cfg, cl, rn, pd, now = synth.CONFIGS[cfg_id](**kw)
+s = GpuScheduler(cfg, 0, os.path.join(CSRC, "libcrane_sched_prof.so"))
+s.set_cluster(cl)
+for _ in range(2):
+    out = s.node_select(now, rn, pd)
+t = s.timing()
+prof = s.debug_profile()
+jobs = np.bincount(pd.partition[pd.partition < cl.n_partitions], minlength=cl.n_partitions)
+print(json.dumps({k: round(v, 3) for k, v in t.items()}))
+for p in range(cl.n_partitions):
+    tot = prof[p, :8].sum() + prof[p, 15]
+    print("partition %d: %d jobs, %.0f cycles/job, total %.1f Mcycles" % (p, jobs[p], tot / max(jobs[p], 1), tot / 1e6))
+    for i, n in enumerate(NAMES):
+        v = int(prof[p, i])
+        if i < 8 or i == 15:
+            print("   %-20s %8.0f cyc/job  %5.1f%%" % (n, v / max(jobs[p], 1), 100.0 * v / max(tot, 1)))
+        elif v:
+            print("   %-20s %10.2f per job" % (n, v / max(jobs[p], 1)))
+s.close()
