@@ -44,6 +44,7 @@ struct GresDict {
   uint8_t entry_name[CRANE_GRES_ENTRIES];
   uint8_t name_first[CRANE_GRES_NAMES];   // first entry of each name (entries of a name are contiguous)
   uint8_t name_count[CRANE_GRES_NAMES];
+  uint64_t name_mask8[CRANE_GRES_NAMES];  // 0xFF in byte e for every entry e of the name
 };
 
 CRANE_HD int popc32(uint32_t v) {
@@ -222,7 +223,9 @@ CRANE_HD bool feasible(const View& req, const Row& avail, const GresDict& d, Row
     alloc->mem_sw = req.mem_sw;
     if (integer_req) {
       int left = (int)whole;
-      for (int w = 0; w < CRANE_CORE_WORDS && left > 0; ++w) {
+#pragma unroll
+      for (int w = 0; w < CRANE_CORE_WORDS; ++w) {
+        if (left <= 0) break;
         const int c = popc64(avail.core[w]);
         const int take = c < left ? c : left;
         alloc->core[w] = lowest_bits64(avail.core[w], take);

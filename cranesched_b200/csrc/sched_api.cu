@@ -246,6 +246,7 @@ int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
     const uint8_t g = c->gres_entry_name[e];
     if (h->dict.name_count[g] == 0) h->dict.name_first[g] = (uint8_t)e;
     h->dict.name_count[g]++;
+    h->dict.name_mask8[g] |= 0xFFull << (8 * e);
   }
   h->h_node_slot.assign(c->n_nodes, 0xffffffffu);
   h->h_part_base.assign(c->n_partitions + 1, 0);
@@ -281,7 +282,7 @@ int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
   h->n_slots = (uint32_t)h->h_slot_node.size();
   h->max_part_slots = max_mp;
   h->words_per_row = std::max<uint32_t>(4, ((max_mp + 31) / 32 + 3) / 4 * 4);  // 16-byte rows for the bulk copies
-  if (max_mp > 65535 || commit_smem_bytes(max_mp, h->words_per_row) > kMaxDynSmem)
+  if (max_mp > 65535 || commit_smem_bytes(max_mp, h->words_per_row) > kMaxDynSmem || max_mp > 32u * (uint32_t)h->commit_threads)
     return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
   // res_total classes per partition (distinct rows), cached in shared memory by the commit kernel
   std::vector<uint8_t> slot_class(std::max<size_t>(slot_total.size(), 1), 0xff);

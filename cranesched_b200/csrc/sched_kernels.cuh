@@ -116,10 +116,13 @@ struct __align__(16) JobQ {
   uint32_t node_num;
   uint32_t alloc_off;
   uint32_t ntasks_per_node;
-  uint32_t flags;      // bit0 exclusive, bit1 has gres request
-  uint32_t pad[3];
+  uint32_t flags;      // bit0 exclusive, bit1 has gres request, bits 8-15 requested gres names
+  uint32_t pad0;
+  uint64_t spec8;      // per-entry typed counts, one byte each (clamped to 127)
+  uint8_t name_need[CRANE_GRES_NAMES];  // per name max(total, sum typed), clamped to 255
+  uint64_t pad1;
 };
-static_assert(sizeof(JobQ) == 96, "JobQ layout");
+static_assert(sizeof(JobQ) == 112, "JobQ layout");
 
 struct PlaceDev {
   uint8_t* reason;
@@ -161,26 +164,18 @@ __device__ __forceinline__ uint64_t pack_gres_counts(const Row& r) {
   for (uint32_t e = 0; e < CRANE_GRES_ENTRIES; ++e) p |= (uint64_t)popc32(field16(r.g, e)) << (8 * e);
   return p;
 }
-// count-only gres verdict against packed counts (same verdict as feasible_gres<false>)
-__device__ __noinline__ bool gres_counts_ok(const View& req, uint64_t packed) {
-#pragma unroll 1
-  for (uint32_t g = 0; g < CRANE_GRES_NAMES; ++g) {
-    const uint32_t e0 = c_dict.name_first[g], e1 = e0 + c_dict.name_count[g];
-    const uint32_t want_total = field16(req.gtot, g);
-    uint32_t typed = 0, have = 0;
-    bool wanted = want_total != 0, ok = true;
-#pragma unroll 1
-    for (uint32_t e = e0; e < e1; ++e) {
-      const uint32_t c = (uint32_t)(packed >> (8 * e)) & 0xff;
-      const uint32_t sp = field16(req.gspec, e);
-      typed += sp;
-      wanted |= sp != 0;
-      ok &= c >= sp;
-      have += c;
-    }
-    if (!wanted) continue;
-    const uint32_t need = want_total > typed ? want_total : typed;
-    if (!ok || have == 0 || have < need) return false;
+// count-only gres verdict against packed per-entry slot counts (all < 128):
+// every typed count fits its entry (byte-wise >= without borrows) and each
+// requested name has max(total, sum typed) slots over its entries (byte sum by
+// multiply). Same verdict as feasible_gres<false> on a row with these counts.
+__device__ __forceinline__ bool gres_counts_ok(uint64_t packed, uint64_t spec8, uint32_t names, const uint8_t* name_need) {
+  const uint64_t H = 0x8080808080808080ull;
+  if ((((packed | H) - spec8) & H) != H) return false;
+  while (names) {
+    const uint32_t g = (uint32_t)__ffs((int)names) - 1u;
+    names &= names - 1u;
+    const uint32_t have = (uint32_t)(((packed & c_dict.name_mask8[g]) * 0x0101010101010101ull) >> 56);
+    if (have < name_need[g]) return false;
   }
   return true;
 }
@@ -503,7 +498,21 @@ __global__ void k_build_jobq(PendingDev pd, const uint32_t* queue, const uint32_
   q.alloc_off = pd.alloc_off[j];
   q.ntasks_per_node = t;
   q.flags = (pd.exclusive[j] ? 1u : 0u) | (view_has_gres(q.req) ? 2u : 0u);
-  for (int i = 0; i < 3; ++i) q.pad[i] = 0;
+  q.pad0 = 0;
+  q.pad1 = 0;
+  q.spec8 = 0;
+  for (uint32_t g = 0; g < CRANE_GRES_NAMES; ++g) {
+    uint32_t typed = 0;
+    for (uint32_t e = c_dict.name_first[g]; e < (uint32_t)c_dict.name_first[g] + c_dict.name_count[g]; ++e) {
+      const uint32_t sp = field16(q.req.gspec, e);
+      typed += sp;
+      q.spec8 |= (uint64_t)(sp > 127 ? 127 : sp) << (8 * e);
+    }
+    const uint32_t tot = field16(q.req.gtot, g);
+    const uint32_t need = tot > typed ? tot : typed;
+    q.name_need[g] = (uint8_t)(need > 255 ? 255 : need);
+    if (need) q.flags |= 1u << (8 + g);
+  }
   jobq[r] = q;
 }
 
@@ -647,7 +656,7 @@ struct CommitArgs {
 
 constexpr int kRing = 4;            // prefetch ring depth (jobs)
 constexpr int kCommitThreads = 256; // CTA size of k_commit
-constexpr int kHeld = 8;            // reorder: positions per thread per round
+constexpr int kHeld = 8;            // reorder: positions per thread per chunk
 
 struct CommitSmem {
   uint32_t* bits_ring;         // [kRing][words]
@@ -655,7 +664,6 @@ struct CommitSmem {
   long long* cpu0;             // [mp]  cpu of the first timeline segment
   unsigned long long* gcnt;    // [mp]  packed gres slot counts of the first segment
   uint16_t* order;             // [mp]  position -> local node, ascending (cost, node)
-  uint16_t* pos;               // [mp]  local node -> position
   uint16_t* sel;               // [mp]  selected nodes of the current job
   uint16_t* nseg;              // [mp]  timeline entry counts
   uint8_t* skip;               // [mp]
@@ -664,7 +672,7 @@ struct CommitSmem {
 __host__ __device__ inline size_t commit_smem_bytes(uint32_t mp, uint32_t words) {
   size_t b = (size_t)kRing * words * 4;
   b += (size_t)mp * 8 * 3;
-  b += (size_t)mp * 2 * 4;
+  b += (size_t)mp * 2 * 3;
   b += (size_t)mp * 2;
   return b + 64;
 }
@@ -714,6 +722,14 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 // out-of-line instance (keeps the per-job instruction footprint small)
 __device__ __noinline__ bool feasible_alloc(const View& req, const Row& avail, Row& alloc) {
   return feasible<true>(req, avail, c_dict, &alloc);
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+#ifndef CRANE_EMU
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
 }
 
 __device__ __forceinline__ uint64_t warp_and64(uint64_t v) {
@@ -988,54 +1004,76 @@ __device__ __forceinline__ Row node_total(const ClusterDev& cl, const Row* class
   return cl.slot_total[base + q];
 }
 
-// move local node u (cost grew to new_cost) toward the back of the (cost, node)
-// order. NodeSelector::UpdateCost's erase+emplace on
+// move local node u (cost grew from old_cost to new_cost) toward the back of
+// the (cost, node) order: NodeSelector::UpdateCost's erase+emplace on
 // std::set<pair<double,NodeState*>> (JobScheduler.h:520-532), tie = node index.
-// Per round of kHeld*blockDim positions: all reads, barrier, all writes.
-__device__ __forceinline__ void reorder_node(CommitSmem& sm, uint32_t mp, uint32_t u, double new_cost,
-                                             uint32_t* s_ltcnt, uint32_t& flip) {
-  const uint32_t p = sm.pos[u];
-  uint32_t moved = 0;  // elements shifted so far
-  for (uint32_t r0 = p + 1;; r0 += kHeld * blockDim.x) {
-    uint16_t held[kHeld];
-    uint32_t nheld = 0;
-#pragma unroll
-    for (int k = 0; k < kHeld; ++k) {
-      const uint32_t i = r0 + threadIdx.x + k * blockDim.x;
-      if (nheld == (uint32_t)k && i < mp) {
-        const uint32_t o = sm.order[i];
-        const double c = sm.cost[o];
-        if ((c < new_cost) || (c == new_cost && o < u)) held[nheld++] = (uint16_t)o;  // sorted: a prefix
-      }
+// Two-level block search for u's position p and for the number b of keys below
+// the new key, then a one-element left shift of order(p, b).
+__device__ __forceinline__ bool key_lt(double c, uint32_t o, double kc, uint32_t ko) {
+  return (c < kc) || (c == kc && o < ko);
+}
+__device__ __forceinline__ void reorder_node(CommitSmem& sm, uint32_t mp, uint32_t u, double old_cost,
+                                             double new_cost, uint32_t* s_red, uint32_t* s_pb) {
+  const uint32_t T = blockDim.x, nw = T >> 5, lane = lane_id(), wid = warp_id();
+  const uint32_t S = (mp + T - 1) / T;  // sample stride (<= 32)
+  {
+    const uint32_t i = threadIdx.x * S;
+    bool lo = false, ln = false;
+    if (i < mp) {
+      const uint32_t o = sm.order[i];
+      const double c = sm.cost[o];
+      lo = key_lt(c, o, old_cost, u);
+      ln = key_lt(c, o, new_cost, u);
     }
-    unsigned tot = nheld;
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFullMask, tot, o);
-    if (lane_id() == 0 && tot) atomicAdd(&s_ltcnt[flip], tot);
-    __syncthreads();
-    const uint32_t cnt = s_ltcnt[flip];
-    if (threadIdx.x == 0) s_ltcnt[flip ^ 1u] = 0;
-#pragma unroll
-    for (int k = 0; k < kHeld; ++k) {
-      if ((uint32_t)k < nheld) {
-        const uint32_t i = r0 + threadIdx.x + k * blockDim.x;
-        sm.order[i - 1] = held[k];
-        sm.pos[held[k]] = (uint16_t)(i - 1);
-      }
-    }
-    moved += cnt;
-    flip ^= 1u;
-    const bool more = cnt == kHeld * blockDim.x && r0 + kHeld * blockDim.x < mp;  // the whole round moved
-    if (!more) {
-      if (threadIdx.x == 0) {
-        sm.order[p + moved] = (uint16_t)u;
-        sm.pos[u] = (uint16_t)(p + moved);
-        sm.cost[u] = new_cost;
-      }
-      __syncthreads();
-      return;
-    }
-    __syncthreads();
+    const unsigned bo = __ballot_sync(kFullMask, lo), bn = __ballot_sync(kFullMask, ln);
+    if (lane == 0) s_red[wid] = (uint32_t)__popc(bo) | (uint32_t)__popc(bn) << 16;
   }
+  __syncthreads();
+  uint32_t c_old = 0, c_new = 0;
+  for (uint32_t w = 0; w < nw; ++w) {
+    const uint32_t v = s_red[w];
+    c_old += v & 0xffffu;
+    c_new += v >> 16;
+  }
+  // keys below a sample point are below the key; refine between two samples
+  if (wid < 2) {
+    const uint32_t c = wid == 0 ? c_old : c_new;
+    const double kc = wid == 0 ? old_cost : new_cost;
+    uint32_t cnt = 0;
+    if (c > 0) {
+      const uint32_t i = (c - 1) * S + 1 + lane;
+      bool lt = false;
+      if (lane + 1 < S && i < mp) {
+        const uint32_t o = sm.order[i];
+        lt = key_lt(sm.cost[o], o, kc, u);
+      }
+      cnt = (c - 1) * S + 1 + (uint32_t)__popc(__ballot_sync(kFullMask, lt));
+    }
+    if (lane == 0) s_pb[wid] = cnt;  // [0] = p (position of u), [1] = b (#keys below the new key, u included)
+  }
+  __syncthreads();
+  const uint32_t p = s_pb[0], last = s_pb[1] - 1;  // u moves to `last`
+  // left shift of order(p, last] in chunks of kHeld*T: read, barrier, write. A
+  // chunk's writes end below the next chunk's reads, so one barrier per chunk.
+  for (uint32_t cb = p + 1; cb <= last; cb += kHeld * T) {
+    uint16_t held[kHeld];
+#pragma unroll
+    for (int k = 0; k < kHeld; ++k) {
+      const uint32_t i = cb + threadIdx.x + k * T;
+      held[k] = i <= last ? sm.order[i] : (uint16_t)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kHeld; ++k) {
+      const uint32_t i = cb + threadIdx.x + k * T;
+      if (i <= last) sm.order[i - 1] = held[k];
+    }
+  }
+  if (threadIdx.x == 0) {
+    sm.order[last] = (uint16_t)u;
+    sm.cost[u] = new_cost;
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
@@ -1056,7 +1094,6 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     sm.cpu0 = reinterpret_cast<long long*>(ptr); ptr += (size_t)mp * 8;
     sm.gcnt = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)mp * 8;
     sm.order = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
-    sm.pos = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.sel = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.nseg = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.skip = ptr; ptr += mp;
@@ -1065,14 +1102,14 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   __shared__ JobQ s_jobs[kRing];
   __shared__ __align__(8) uint64_t s_bar[kRing];
   __shared__ Row s_classrow[kMaxClasses];
-  __shared__ uint16_t s_cand[kCommitThreads];
-  __shared__ uint32_t s_wcnt[32], s_pass[32], s_selw[32];
+  __shared__ uint16_t s_cand2[2][kCommitThreads];
+  __shared__ uint32_t s_wcnt2[2][32], s_pass[32], s_passq[32], s_selw[32];
   __shared__ int64_t s_t[32];
   __shared__ long long s_wmax[32];
   __shared__ unsigned long long s_wmaxg[32];
   __shared__ long long s_ub_cpu;            // >= max over nodes of the first segment's cpu
   __shared__ unsigned long long s_ub_g;     // >= per-entry max of the packed gres counts
-  __shared__ uint32_t s_label, s_ncap, s_ltcnt[2];
+  __shared__ uint32_t s_label, s_ncap, s_red[32], s_pb[2];
 
   // ---- load node state; initial order = ascending (cost, node) -----------
   for (uint32_t q = threadIdx.x; q < mp; q += blockDim.x) {
@@ -1087,9 +1124,8 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   }
   if (threadIdx.x < kMaxClasses) s_classrow[threadIdx.x] = a.cl.class_rows[(size_t)part * kMaxClasses + threadIdx.x];
   if (threadIdx.x == 0) {
-    s_ltcnt[0] = s_ltcnt[1] = 0;
     s_ub_cpu = INT64_MAX;
-    s_ub_g = ~0ull;
+    s_ub_g = 0x1010101010101010ull;  // CRANE_MAX_SLOTS per entry
     for (int s = 0; s < kRing; ++s) mbar_init(&s_bar[s], 1);
     fence_mbar_init();
   }
@@ -1102,7 +1138,6 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       rank += (co < c || (co == c && o < q)) ? 1u : 0u;
     }
     sm.order[rank] = (uint16_t)q;
-    sm.pos[q] = (uint16_t)rank;
   }
 
   const uint32_t r_begin = a.part_job_off[part], r_end = a.part_job_off[part + 1];
@@ -1119,7 +1154,6 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     for (uint32_t i = 0; i < njobs && i < (uint32_t)kRing - 1; ++i) issue(i);
   __syncthreads();
 
-  uint32_t flip = 0;
   PROF_DECL;
   for (uint32_t ji = 0; ji < njobs; ++ji) {
     PROF(15);
@@ -1130,11 +1164,29 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     const uint32_t* bits = sm.bits_ring + (size_t)slot * words;
     const uint32_t K = jq.node_num;
     const uint32_t jflags = jq.flags;
+    // copies: the ring slot is refilled as soon as the last barrier of this job is passed
+    const uint32_t job_idx = jq.job, job_alloc_off = jq.alloc_off, job_ntpn = jq.ntasks_per_node;
     const bool exclusive = jflags & 1u;
     const int64_t limit = jq.time_limit;
     const int64_t w_end = a.now + limit;
     const View req = jq.req;
+    const uint64_t spec8 = jq.spec8;
+    const uint32_t gnames = (jflags >> 8) & 0xffu;
     if (threadIdx.x == 0) s_label = 0;
+    // pull the timeline head of the cheapest nodes toward L1 while the scan runs:
+    // they are the usual pick both for an immediate start and for a backfill
+    if (wid == nw - 1) {
+      const uint32_t npf = K < 2u ? K : 2u;
+      for (uint32_t k = 0; k < npf && k < mp; ++k) {
+        const uint32_t q = sm.order[k];
+        const uint32_t g = base + q;
+        const uint32_t nlines = ((uint32_t)sm.nseg[q] * (uint32_t)sizeof(TlEntry) + 127u) / 128u;
+        const char* ptr = reinterpret_cast<const char*>(a.tl.ent + (size_t)g * a.tl.cap);
+        if (lane < nlines && lane < 30) prefetch_l1(ptr + 128u * lane);
+        if (lane == 30) prefetch_l1(&a.tl.avail0[g]);
+        if (lane == 31) prefetch_l1(&a.cl.slot_node[g]);
+      }
+    }
     PROF(0);
 
     NodeRegs nr;
@@ -1147,12 +1199,18 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     // ---- nodes that can run the job now, in cost order --------------------
     // (JobScheduler.cpp:5224-5336). Skipped when the partition-wide bounds say
     // no node passes the pre-filter (then the reference's loop finds none).
-    const bool may_fit = exclusive || (req.cpu_raw <= s_ub_cpu && (!(jflags & 2u) || gres_counts_ok(req, s_ub_g)));
+    const bool may_fit = exclusive || (req.cpu_raw <= s_ub_cpu &&
+                                       (!(jflags & 2u) || gres_counts_ok(s_ub_g, spec8, gnames, jq.name_need)));
     if (K <= mp && may_fit) {
       bool scanned_all = true;
       long long mx_cpu = INT64_MIN;
       unsigned long long mx_g = 0;
       for (uint32_t cbase = 0; cbase < mp; cbase += blockDim.x) {
+        // warp w looks at positions [cbase + 32w, +32) and lists its candidates,
+        // in order, in s_cand[32w ...); the lists of warps 0,1,.. concatenate to
+        // the cost order.
+        uint16_t* s_cand = s_cand2[(cbase / blockDim.x) & 1u];  // double-buffered: one barrier per chunk
+        uint32_t* s_wcnt = s_wcnt2[(cbase / blockDim.x) & 1u];
         const uint32_t i = cbase + threadIdx.x;
         bool cand = false;
         uint32_t q = 0;
@@ -1164,19 +1222,15 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
           mx_g = (unsigned long long)__vmaxu4((unsigned)mx_g, (unsigned)gc) |
                  (unsigned long long)__vmaxu4((unsigned)(mx_g >> 32), (unsigned)(gc >> 32)) << 32;
           cand = ((bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
-          if (cand && !exclusive) cand = c0 >= req.cpu_raw && (!(jflags & 2u) || gres_counts_ok(req, gc));
+          if (cand && !exclusive)
+            cand = c0 >= req.cpu_raw && (!(jflags & 2u) || gres_counts_ok(gc, spec8, gnames, jq.name_need));
         }
         const unsigned bm = __ballot_sync(kFullMask, cand);
+        if (cand) s_cand[wid * 32 + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)q;
         if (lane == 0) s_wcnt[wid] = __popc(bm);
         __syncthreads();
-        uint32_t before = 0, total = 0;
-        for (uint32_t w = 0; w < nw; ++w) {
-          const uint32_t c = s_wcnt[w];
-          before += w < wid ? c : 0u;
-          total += c;
-        }
-        if (cand) s_cand[before + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)q;
-        __syncthreads();
+        uint32_t total = 0;
+        for (uint32_t w = 0; w < nw; ++w) total += s_wcnt[w];
         PROF(1);
         PROF_CNT(8, total);
         // exact test, exactly as many warps as nodes still needed, in order
@@ -1186,9 +1240,10 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
           uint32_t W = K - nsel;
           W = W < nw ? W : nw;
           W = W < total - b0 ? W : total - b0;
-          bool pass = false;
           if (wid < W) {
-            const uint32_t q2 = s_cand[b0 + wid];
+            uint32_t ww = 0, rem = b0 + wid;  // candidate b0+wid of the concatenated lists
+            while (rem >= s_wcnt[ww]) { rem -= s_wcnt[ww]; ++ww; }
+            const uint32_t q2 = s_cand[ww * 32 + rem];
             const uint32_t g = base + q2;
             const uint32_t n = sm.nseg[q2];
             const Row a0 = a.tl.avail0[g];
@@ -1196,20 +1251,20 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
             if (exclusive) tot = node_total(a.cl, s_classrow, sm, base, q2);
             node_open(a.tl, g, n, nr);
             held_q = q2;
-            pass = n <= 64 ? node_test_now(nr, req, exclusive, tot, a0, w_end, my_alloc)
-                           : node_test_now_big(a.tl, g, n, req, exclusive, tot, a0, w_end, my_alloc);
-            if (lane == 0) s_pass[wid] = pass ? 1u : 0u;
+            const bool pass = n <= 64 ? node_test_now(nr, req, exclusive, tot, a0, w_end, my_alloc)
+                                      : node_test_now_big(a.tl, g, n, req, exclusive, tot, a0, w_end, my_alloc);
+            if (lane == 0) { s_pass[wid] = pass ? 1u : 0u; s_passq[wid] = q2; }
           }
           __syncthreads();
           for (uint32_t w = 0; w < W; ++w) {
             if (s_pass[w]) {
-              if (threadIdx.x == 0) { sm.sel[nsel] = s_cand[b0 + w]; if (nsel < 32) s_selw[nsel] = w; }
+              if (threadIdx.x == 0) { sm.sel[nsel] = (uint16_t)s_passq[w]; if (nsel < 32) s_selw[nsel] = w; }
               ++nsel;
             }
           }
           b0 += W;
           if (nsel >= K) start_now = true;
-          else __syncthreads();  // s_pass / s_cand are rewritten
+          else if (b0 < total) __syncthreads();  // s_pass is rewritten by the next batch
         }
         PROF(2);
         if (start_now) { scanned_all = false; break; }
@@ -1344,9 +1399,9 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
           if (nn >= a.max_jobs) sm.skip[q] = 1;
           sm.cpu0[q] = seg0.cpu_raw;
           sm.gcnt[q] = pack_gres_counts(seg0);
-          const uint32_t dst = jq.alloc_off + rank;
+          const uint32_t dst = job_alloc_off + rank;
           a.out.alloc_node[dst] = a.cl.slot_node[g];
-          a.out.alloc_ntasks[dst] = jq.ntasks_per_node;
+          a.out.alloc_ntasks[dst] = job_ntpn;
           a.out.alloc_res[dst] = my_alloc;
           // pending-reason label for future starts (JobScheduler.cpp:5842-5848)
           if (start_time != a.now && !row_le(my_alloc, a.tl.avail0[g])) atomicOr(&s_label, 1u);
@@ -1360,29 +1415,33 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         const bool mine = owner_mode ? (s_selw[k] == wid) : (k % nw == wid);
         if (mine) commit_node(k);
       }
-      __syncthreads();
       PROF(6);
-      if (threadIdx.x == 0) {
-        a.out.start_time[jq.job] = start_time;
-        a.out.end_time[jq.job] = end_time;
-        a.out.n_alloc[jq.job] = K;
-        uint8_t reason = CRANE_REASON_NONE;
-        if (start_time != a.now) reason = s_label ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY;
-        a.out.reason[jq.job] = reason;
-      }
       // cost += (end-start) * cpu ratio, then re-key (JobScheduler.h:46-52,520-532).
       // The allocation's cpu is the job's per-node request, or the node total
       // for exclusive jobs.
+      bool synced = false;
       for (uint32_t k = 0; k < K; ++k) {
         const uint32_t q = sm.sel[k];
         const int64_t tot_cpu = node_total(a.cl, s_classrow, sm, base, q).cpu_raw;
         const double delta = cost_delta(limit, exclusive ? tot_cpu : req.cpu_raw, tot_cpu);
-        const double nc = __dadd_rn(sm.cost[q], delta);
-        reorder_node(sm, mp, q, nc, s_ltcnt, flip);
+        const double oc = sm.cost[q];
+        const double nc = __dadd_rn(oc, delta);
+        if (nc > oc) { reorder_node(sm, mp, q, oc, nc, s_red, s_pb); synced = true; }  // barriers inside
+      }
+      if (!synced) __syncthreads();
+      // job-level outputs; s_label is complete: every path above passed a barrier
+      // after the node updates
+      if (threadIdx.x == 0) {
+        a.out.start_time[job_idx] = start_time;
+        a.out.end_time[job_idx] = end_time;
+        a.out.n_alloc[job_idx] = K;
+        uint8_t reason = CRANE_REASON_NONE;
+        if (start_time != a.now) reason = s_label ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY;
+        a.out.reason[job_idx] = reason;
       }
       PROF(7);
     } else {
-      if (threadIdx.x == 0) a.out.reason[jq.job] = CRANE_REASON_RESOURCE;  // JobScheduler.cpp:5802
+      if (threadIdx.x == 0) a.out.reason[job_idx] = CRANE_REASON_RESOURCE;  // JobScheduler.cpp:5802
       __syncthreads();
     }
   }
