@@ -605,20 +605,21 @@ __global__ void k_feas_bitmap(ClusterDev cl, PendingDev pd, const JobQ* jobq, co
 
 // ------------------------------------------------------------------------
 // K-commit: the sequential job loop (JobScheduler.cpp:5777-5867), one
-// persistent CTA per partition, node-parallel inside each job.
+// persistent CTA per partition (the reference's LocalScheduler).
 //
-// One SM issues 128 lane-instructions per cycle, so anything done "per node per
-// job" must be a handful of instructions, and anything done by one warp must be
-// a short dependency chain. Hence:
-//  * per node the CTA keeps in shared memory: cost (NodeRater::cost), the cpu
-//    count and packed gres slot counts of the first timeline segment (a cheap,
-//    conservative pre-filter), the entry count, skip flag, res_total class and
-//    the (cost, node)-sorted order;
-//  * partition-wide upper bounds on those first-segment counts (they only
-//    shrink inside a tick) let a job that cannot start anywhere skip the scan;
-//  * the scan walks the cost order in CTA-sized chunks and stops at the first
-//    chunk that yields enough nodes; candidates are tested by exactly as many
-//    warps as nodes are still needed;
+// The loop is a dependency chain (job j+1 sees job j's allocation and cost
+// update), so the design minimises the latency of one job, not throughput:
+//  * a DRIVER warp (warp 0) runs a one-node job entirely by itself — scan,
+//    exact test, allocation, timeline update, re-keying — with no block
+//    barrier; the other warps are HELPERS parked on a barrier that the driver
+//    only touches for multi-node jobs (one node per helper);
+//  * the (cost, node) order of NodeSelector (JobScheduler.h:588) is a bucketed
+//    sorted list in shared memory (<= 64 nodes per bucket), so re-keying a node
+//    shifts tens of entries, not half the partition; every bucket carries an
+//    upper bound of its nodes' first-segment cpu / gres counts so the scan for
+//    an immediate start jumps over buckets that cannot match (availability
+//    only shrinks inside a tick, so the bounds stay valid and are tightened
+//    lazily);
 //  * timelines live in HBM/L2 as 80-byte entries; a warp opens a node by
 //    loading up to 64 entries into registers once and runs the window test
 //    (ballot + REDUX.AND), the allocation, the earliest-start search
@@ -654,27 +655,37 @@ struct CommitArgs {
   unsigned long long* prof;      // [n_parts][16] cycle counters (profiling builds)
 };
 
-constexpr int kRing = 4;            // prefetch ring depth (jobs)
-constexpr int kCommitThreads = 256; // CTA size of k_commit
-constexpr int kHeld = 8;            // reorder: positions per thread per chunk
+constexpr int kRing = 4;             // prefetch ring depth (jobs)
+constexpr int kCommitThreads = 256;  // CTA size of k_commit: driver warp + 7 helpers
+constexpr int kBucket = 64;          // bucket capacity of the cost order
+constexpr int kBucketFill = 32;      // entries per bucket after a (re)build
 
 struct CommitSmem {
   uint32_t* bits_ring;         // [kRing][words]
   double* cost;                // [mp]  NodeRater::cost
   long long* cpu0;             // [mp]  cpu of the first timeline segment
   unsigned long long* gcnt;    // [mp]  packed gres slot counts of the first segment
-  uint16_t* order;             // [mp]  position -> local node, ascending (cost, node)
-  uint16_t* sel;               // [mp]  selected nodes of the current job
+  long long* bmax_cpu;         // [nb]  >= cpu0 of every node in the bucket
+  unsigned long long* bmax_g;  // [nb]  >= gcnt (per byte) of every node in the bucket
+  uint16_t* bk;                // [nb][kBucket] node ids, ascending (cost, node); buckets ascending
+  uint16_t* bcnt;              // [nb]
+  uint16_t* bkt;               // [mp]  bucket of a node
+  uint16_t* list;              // [mp]  nodes handed to the workers / selected nodes of the job
+  uint16_t* tmp;               // [mp]  scratch of (re)builds
   uint16_t* nseg;              // [mp]  timeline entry counts
   uint8_t* skip;               // [mp]
   uint8_t* cls;                // [mp]
+  uint32_t nb;
 };
+__host__ __device__ inline uint32_t commit_nbuckets(uint32_t mp) { return (mp + kBucketFill - 1) / kBucketFill + 1; }
 __host__ __device__ inline size_t commit_smem_bytes(uint32_t mp, uint32_t words) {
+  const size_t nb = commit_nbuckets(mp);
   size_t b = (size_t)kRing * words * 4;
-  b += (size_t)mp * 8 * 3;
-  b += (size_t)mp * 2 * 3;
+  b += (size_t)mp * 8 * 3 + nb * 8 * 2;
+  b += nb * kBucket * 2 + nb * 2;
+  b += (size_t)mp * 2 * 4;
   b += (size_t)mp * 2;
-  return b + 64;
+  return b + 96;
 }
 
 // ---- TMA 1-D bulk copy + mbarrier (sm_90+/sm_100a) --------------------------
@@ -1004,76 +1015,232 @@ __device__ __forceinline__ Row node_total(const ClusterDev& cl, const Row* class
   return cl.slot_total[base + q];
 }
 
-// move local node u (cost grew from old_cost to new_cost) toward the back of
-// the (cost, node) order: NodeSelector::UpdateCost's erase+emplace on
-// std::set<pair<double,NodeState*>> (JobScheduler.h:520-532), tie = node index.
-// Two-level block search for u's position p and for the number b of keys below
-// the new key, then a one-element left shift of order(p, b).
 __device__ __forceinline__ bool key_lt(double c, uint32_t o, double kc, uint32_t ko) {
   return (c < kc) || (c == kc && o < ko);
 }
-__device__ __forceinline__ void reorder_node(CommitSmem& sm, uint32_t mp, uint32_t u, double old_cost,
-                                             double new_cost, uint32_t* s_red, uint32_t* s_pb) {
-  const uint32_t T = blockDim.x, nw = T >> 5, lane = lane_id(), wid = warp_id();
-  const uint32_t S = (mp + T - 1) / T;  // sample stride (<= 32)
-  {
-    const uint32_t i = threadIdx.x * S;
-    bool lo = false, ln = false;
-    if (i < mp) {
-      const uint32_t o = sm.order[i];
-      const double c = sm.cost[o];
-      lo = key_lt(c, o, old_cost, u);
-      ln = key_lt(c, o, new_cost, u);
-    }
-    const unsigned bo = __ballot_sync(kFullMask, lo), bn = __ballot_sync(kFullMask, ln);
-    if (lane == 0) s_red[wid] = (uint32_t)__popc(bo) | (uint32_t)__popc(bn) << 16;
-  }
-  __syncthreads();
-  uint32_t c_old = 0, c_new = 0;
-  for (uint32_t w = 0; w < nw; ++w) {
-    const uint32_t v = s_red[w];
-    c_old += v & 0xffffu;
-    c_new += v >> 16;
-  }
-  // keys below a sample point are below the key; refine between two samples
-  if (wid < 2) {
-    const uint32_t c = wid == 0 ? c_old : c_new;
-    const double kc = wid == 0 ? old_cost : new_cost;
-    uint32_t cnt = 0;
-    if (c > 0) {
-      const uint32_t i = (c - 1) * S + 1 + lane;
-      bool lt = false;
-      if (lane + 1 < S && i < mp) {
-        const uint32_t o = sm.order[i];
-        lt = key_lt(sm.cost[o], o, kc, u);
+__device__ __forceinline__ unsigned long long vmax8(unsigned long long a, unsigned long long b) {
+  return (unsigned long long)__vmaxu4((unsigned)a, (unsigned)b) |
+         (unsigned long long)__vmaxu4((unsigned)(a >> 32), (unsigned)(b >> 32)) << 32;
+}
+
+// ---- bucketed (cost, node) order: driver-warp operations -------------------
+// NodeSelector::UpdateCost erases and re-inserts the node in a
+// std::set<pair<double,NodeState*>> (JobScheduler.h:520-532). Here: remove u from
+// its bucket, find the first bucket whose largest key is not below the new key,
+// insert in place. Costs only grow inside a tick, so the search starts at u's
+// old bucket. Returns false when the target bucket is full (caller rebuilds).
+__device__ __forceinline__ void bucket_remove(CommitSmem& sm, uint32_t u) {
+  const uint32_t lane = lane_id();
+  const uint32_t b = sm.bkt[u];
+  uint16_t* B = sm.bk + (size_t)b * kBucket;
+  const uint32_t n = sm.bcnt[b];
+  const uint16_t e0 = lane < n ? B[lane] : (uint16_t)0xffff;
+  const uint16_t e1 = lane + 32 < n ? B[lane + 32] : (uint16_t)0xffff;
+  const unsigned m0 = __ballot_sync(kFullMask, e0 == u), m1 = __ballot_sync(kFullMask, e1 == u);
+  const uint32_t idx = m0 ? (uint32_t)__ffs((int)m0) - 1u : 32u + (uint32_t)__ffs((int)m1) - 1u;
+  // entries after idx move one slot down (values are already in registers)
+  if (lane > idx && lane < n) B[lane - 1] = e0;
+  if (lane + 32 > idx && lane + 32 < n) B[lane + 31] = e1;
+  if (lane == 0) sm.bcnt[b] = (uint16_t)(n - 1);
+  __syncwarp();
+}
+
+__device__ __forceinline__ bool bucket_insert(CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
+  const uint32_t lane = lane_id();
+  // first non-empty bucket >= from_bucket whose last key is >= the new key;
+  // if there is none, the last non-empty bucket
+  uint32_t tb = 0xffffffffu, last_nonempty = 0xffffffffu;
+  for (uint32_t b0 = from_bucket; b0 < sm.nb && tb == 0xffffffffu; b0 += 32) {
+    const uint32_t b = b0 + lane;
+    bool nonempty = false, ge = false;
+    if (b < sm.nb) {
+      const uint32_t n = sm.bcnt[b];
+      if (n) {
+        nonempty = true;
+        const uint32_t o = sm.bk[(size_t)b * kBucket + n - 1];
+        ge = !key_lt(sm.cost[o], o, new_cost, u);
       }
-      cnt = (c - 1) * S + 1 + (uint32_t)__popc(__ballot_sync(kFullMask, lt));
     }
-    if (lane == 0) s_pb[wid] = cnt;  // [0] = p (position of u), [1] = b (#keys below the new key, u included)
+    const unsigned mg = __ballot_sync(kFullMask, ge), mn = __ballot_sync(kFullMask, nonempty);
+    if (mg) tb = b0 + (uint32_t)__ffs((int)mg) - 1u;
+    if (mn) last_nonempty = b0 + 31u - (uint32_t)__clz((int)mn);
   }
-  __syncthreads();
-  const uint32_t p = s_pb[0], last = s_pb[1] - 1;  // u moves to `last`
-  // left shift of order(p, last] in chunks of kHeld*T: read, barrier, write. A
-  // chunk's writes end below the next chunk's reads, so one barrier per chunk.
-  for (uint32_t cb = p + 1; cb <= last; cb += kHeld * T) {
-    uint16_t held[kHeld];
-#pragma unroll
-    for (int k = 0; k < kHeld; ++k) {
-      const uint32_t i = cb + threadIdx.x + k * T;
-      held[k] = i <= last ? sm.order[i] : (uint16_t)0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kHeld; ++k) {
-      const uint32_t i = cb + threadIdx.x + k * T;
-      if (i <= last) sm.order[i - 1] = held[k];
-    }
-  }
-  if (threadIdx.x == 0) {
-    sm.order[last] = (uint16_t)u;
+  if (tb == 0xffffffffu) tb = last_nonempty != 0xffffffffu ? last_nonempty : from_bucket;
+  uint16_t* B = sm.bk + (size_t)tb * kBucket;
+  const uint32_t n = sm.bcnt[tb];
+  if (n >= (uint32_t)kBucket) return false;
+  const uint16_t e0 = lane < n ? B[lane] : (uint16_t)0xffff;
+  const uint16_t e1 = lane + 32 < n ? B[lane + 32] : (uint16_t)0xffff;
+  const bool l0 = lane < n && key_lt(sm.cost[e0], e0, new_cost, u);
+  const bool l1 = lane + 32 < n && key_lt(sm.cost[e1], e1, new_cost, u);
+  const uint32_t pos = (uint32_t)__popc(__ballot_sync(kFullMask, l0)) + (uint32_t)__popc(__ballot_sync(kFullMask, l1));
+  if (lane >= pos && lane < n) B[lane + 1] = e0;
+  if (lane + 32 >= pos && lane + 32 < n) B[lane + 33] = e1;
+  if (lane == 0) {
+    B[pos] = (uint16_t)u;
+    sm.bcnt[tb] = (uint16_t)(n + 1);
+    sm.bkt[u] = (uint16_t)tb;
     sm.cost[u] = new_cost;
+    const long long c = sm.cpu0[u];
+    if (c > sm.bmax_cpu[tb]) sm.bmax_cpu[tb] = c;
+    sm.bmax_g[tb] = vmax8(sm.bmax_g[tb], sm.gcnt[u]);
   }
-  __syncthreads();
+  __syncwarp();
+  return true;
+}
+
+// Deal sm.tmp[0..total) (already in (cost, node) order) out to the buckets,
+// kBucketFill per bucket, and refresh bkt[] and the per-bucket bounds.
+__device__ __noinline__ void bucket_deal(CommitSmem& sm, uint32_t total) {
+  const uint32_t lane = lane_id();
+  for (uint32_t b = 0; b < sm.nb; ++b) {
+    const uint32_t lo = b * kBucketFill;
+    const uint32_t n = lo < total ? (total - lo < (uint32_t)kBucketFill ? total - lo : (uint32_t)kBucketFill) : 0u;
+    long long mc = INT64_MIN;
+    unsigned long long mg = 0;
+    if (lane < n) {
+      const uint32_t q = sm.tmp[lo + lane];
+      sm.bk[(size_t)b * kBucket + lane] = (uint16_t)q;
+      sm.bkt[q] = (uint16_t)b;
+      mc = sm.cpu0[q];
+      mg = sm.gcnt[q];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long oc = __shfl_xor_sync(kFullMask, mc, o);
+      mc = oc > mc ? oc : mc;
+      mg = vmax8(mg, __shfl_xor_sync(kFullMask, mg, o));
+    }
+    if (lane == 0) { sm.bcnt[b] = (uint16_t)n; sm.bmax_cpu[b] = mc; sm.bmax_g[b] = mg; }
+  }
+  __syncwarp();
+}
+// Re-spread all bucketed nodes evenly, keeping the order. Driver warp only;
+// runs when a bucket overflows (rare: a bucket must gain 32 nodes net).
+__device__ __noinline__ void bucket_rebuild(CommitSmem& sm) {
+  const uint32_t lane = lane_id();
+  uint32_t rank = 0;
+  for (uint32_t b = 0; b < sm.nb; ++b) {
+    const uint32_t n = sm.bcnt[b];
+    for (uint32_t i = lane; i < n; i += 32) sm.tmp[rank + i] = sm.bk[(size_t)b * kBucket + i];
+    rank += n;
+  }
+  __syncwarp();
+  bucket_deal(sm, rank);
+}
+
+// worker commands (driver -> helpers, through shared memory + the CTA barrier)
+enum : uint32_t {
+  OP_NOW_K1 = 0,     // one-node job: test the node now; on success update it
+  OP_BF_K1 = 1,      // one-node job: earliest start on the node; on success update it
+  OP_TEST = 2,       // worker w tests list[w] for an immediate start
+  OP_EARLY = 3,      // workers: earliest fit >= t0 over their share of list[0..n)
+  OP_UPDATE_NOW = 4, // workers: allocate against the window minimum and update their share
+  OP_UPDATE_BF = 5,  // workers: allocate against res_total and update their share
+  OP_EXIT = 6,
+};
+struct CommitCmd {
+  uint32_t kind, n, slot, first;  // OP_TEST: worker w handles list[first + w]; others: list[w], list[w+nw], ...
+  int64_t t0;                     // OP_EARLY: T0; OP_UPDATE_*: start time
+};
+struct WorkerCtx {  // lives in shared memory; read-only after set-up
+  ClusterDev cl;
+  TimelineDev tl;
+  PlaceDev out;
+  CommitSmem sm;
+  const JobQ* jobs;
+  const Row* classrow;
+  uint32_t* label;
+  int64_t now, max_window;
+  uint32_t base, max_jobs;
+};
+
+// The per-node work of one command on this warp's share of sm.list[first, n)
+// with the given stride: open the node's timeline once, then — depending on the
+// command — the immediate-start test and allocation against the window minimum
+// (JobScheduler.cpp:5285-5361), or the allocation against res_total and the
+// earliest fit (JobScheduler.cpp:5381-5403, JobScheduler.h:806-849), and the
+// timeline update with its outputs (JobScheduler.h:334-453, JobScheduler.cpp:5827).
+// One out-of-line instance shared by the driver and the helpers.
+// Returns: OP_NOW_K1/OP_TEST pass flag; OP_BF_K1 start time or kInf; OP_EARLY
+// the max earliest fit over the share.
+__device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kind, uint32_t n, uint32_t slot,
+                                              int64_t t0, uint32_t first, uint32_t stride) {
+  const WorkerCtx& cx = *cxp;
+  const CommitSmem& sm = cx.sm;
+  const uint32_t lane = lane_id();
+  const JobQ& jq = cx.jobs[slot];
+  const View req = jq.req;
+  const bool exclusive = jq.flags & 1u;
+  const int64_t limit = jq.time_limit;
+  const int64_t now = cx.now;
+  const int64_t w_end = now + limit;
+  const uint32_t K = jq.node_num;
+  long long result = (kind == OP_EARLY) ? (long long)t0 : 0;
+#pragma unroll 1
+  for (uint32_t k = first; k < n; k += stride) {
+    const uint32_t q = sm.list[k];
+#ifdef CRANE_EMU_DEBUG
+    if (q > 60000) { fprintf(stderr, "worker_step: kind=%u n=%u first=%u stride=%u k=%u q=%u tid=%u\n", kind, n, first, stride, k, q, threadIdx.x); abort(); }
+#endif
+    const uint32_t g = cx.base + q;
+    const uint32_t ns = sm.nseg[q];
+    const bool from_window = kind == OP_NOW_K1 || kind == OP_TEST || kind == OP_UPDATE_NOW;
+    const Row a0 = cx.tl.avail0[g];
+    Row tot;
+    row_zero(tot);
+    if (exclusive || !from_window) tot = node_total(cx.cl, cx.classrow, sm, cx.base, q);
+    NodeRegs nr;
+    node_open(cx.tl, g, ns, nr);
+    Row alloc;
+    bool ok = true;
+    if (from_window) {
+      ok = ns <= 64 ? node_test_now(nr, req, exclusive, tot, a0, w_end, alloc)
+                    : node_test_now_big(cx.tl, g, ns, req, exclusive, tot, a0, w_end, alloc);
+    } else if (exclusive) {
+      alloc = tot;
+    } else {
+      feasible_alloc(req, tot, alloc);
+    }
+    int64_t start = t0;
+    if (kind == OP_NOW_K1 || kind == OP_TEST) result = ok ? 1 : 0;
+    if (kind == OP_NOW_K1) start = now;
+    if (kind == OP_BF_K1 || kind == OP_EARLY) {
+      const int64_t t = ns <= 64 ? node_earliest(nr, alloc, t0, limit) : node_earliest_big(cx.tl, g, ns, alloc, t0, limit);
+      if (kind == OP_EARLY) {
+        result = t > result ? t : result;
+      } else {
+        ok = t != kInf && t - now <= cx.max_window;  // `current_time - now > kAlgoMaxTimeWindow` (JobScheduler.h:809)
+        start = t;
+        result = ok ? t : kInf;
+      }
+    }
+    const bool do_update = ((kind == OP_NOW_K1 || kind == OP_BF_K1) && ok) || kind == OP_UPDATE_NOW || kind == OP_UPDATE_BF;
+    if (do_update) {
+      const int64_t end = start + limit;
+      Row seg0;
+      const uint32_t nn = ns <= 64 ? node_update(cx.tl, g, nr, start, end, alloc, seg0)
+                                   : node_update_big(cx.tl, g, ns, start, end, alloc, seg0);
+      uint32_t rank = 0;  // node-index ascending output slot (deviation D3)
+      if (n > 1) {
+        for (uint32_t m = lane; m < K; m += 32) rank += sm.list[m] < q ? 1u : 0u;
+        for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(kFullMask, rank, o);
+      }
+      if (lane == 0) {
+        sm.nseg[q] = (uint16_t)nn;
+        if (nn >= cx.max_jobs) sm.skip[q] = 1;
+        sm.cpu0[q] = seg0.cpu_raw;
+        sm.gcnt[q] = (seg0.g[0] | seg0.g[1]) ? pack_gres_counts(seg0) : 0ull;
+        const uint32_t dst = jq.alloc_off + rank;
+        cx.out.alloc_node[dst] = cx.cl.slot_node[g];
+        cx.out.alloc_ntasks[dst] = jq.ntasks_per_node;
+        cx.out.alloc_res[dst] = alloc;
+        // pending-reason label for future starts (JobScheduler.cpp:5842-5848)
+        if (start != now && !row_le(alloc, a0)) atomicOr(cx.label, 1u);
+      }
+      __syncwarp();  // lane 0's shared-memory writes are visible to the whole warp
+    }
+  }
+  return result;
 }
 
 __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
@@ -1087,14 +1254,20 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   const uint32_t nw = blockDim.x >> 5;
 
   CommitSmem sm;
+  sm.nb = commit_nbuckets(mp);
   {
     unsigned char* ptr = smem_raw;  // 16-byte aligned; widest element types first
     sm.bits_ring = reinterpret_cast<uint32_t*>(ptr); ptr += (size_t)kRing * words * 4;
     sm.cost = reinterpret_cast<double*>(ptr); ptr += (size_t)mp * 8;
     sm.cpu0 = reinterpret_cast<long long*>(ptr); ptr += (size_t)mp * 8;
     sm.gcnt = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)mp * 8;
-    sm.order = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
-    sm.sel = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
+    sm.bmax_cpu = reinterpret_cast<long long*>(ptr); ptr += (size_t)sm.nb * 8;
+    sm.bmax_g = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)sm.nb * 8;
+    sm.bk = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)sm.nb * kBucket * 2;
+    sm.bcnt = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)sm.nb * 2;
+    sm.bkt = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
+    sm.list = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
+    sm.tmp = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.nseg = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.skip = ptr; ptr += mp;
     sm.cls = ptr;
@@ -1102,16 +1275,12 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   __shared__ JobQ s_jobs[kRing];
   __shared__ __align__(8) uint64_t s_bar[kRing];
   __shared__ Row s_classrow[kMaxClasses];
-  __shared__ uint16_t s_cand2[2][kCommitThreads];
-  __shared__ uint32_t s_wcnt2[2][32], s_pass[32], s_passq[32], s_selw[32];
-  __shared__ int64_t s_t[32];
-  __shared__ long long s_wmax[32];
-  __shared__ unsigned long long s_wmaxg[32];
-  __shared__ long long s_ub_cpu;            // >= max over nodes of the first segment's cpu
-  __shared__ unsigned long long s_ub_g;     // >= per-entry max of the packed gres counts
-  __shared__ uint32_t s_label, s_ncap, s_red[32], s_pb[2];
+  __shared__ CommitCmd s_cmd;
+  __shared__ WorkerCtx s_cx;
+  __shared__ long long s_res[32];   // per-worker result of a multi-warp step
+  __shared__ uint32_t s_label;
 
-  // ---- load node state; initial order = ascending (cost, node) -----------
+  // ---- load node state (all warps) --------------------------------------
   for (uint32_t q = threadIdx.x; q < mp; q += blockDim.x) {
     const uint32_t g = base + q;
     sm.cost[q] = a.tl.cost0[g];
@@ -1123,328 +1292,291 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     sm.cls[q] = a.cl.slot_class[g];
   }
   if (threadIdx.x < kMaxClasses) s_classrow[threadIdx.x] = a.cl.class_rows[(size_t)part * kMaxClasses + threadIdx.x];
+  for (uint32_t b = threadIdx.x; b < sm.nb; b += blockDim.x) sm.bcnt[b] = 0;
   if (threadIdx.x == 0) {
-    s_ub_cpu = INT64_MAX;
-    s_ub_g = 0x1010101010101010ull;  // CRANE_MAX_SLOTS per entry
+    s_label = 0;
+    s_cx.cl = a.cl; s_cx.tl = a.tl; s_cx.out = a.out; s_cx.sm = sm; s_cx.jobs = s_jobs; s_cx.classrow = s_classrow;
+    s_cx.label = &s_label; s_cx.now = a.now; s_cx.max_window = a.max_window; s_cx.base = base; s_cx.max_jobs = a.max_jobs;
     for (int s = 0; s < kRing; ++s) mbar_init(&s_bar[s], 1);
     fence_mbar_init();
   }
   __syncthreads();
-  for (uint32_t q = threadIdx.x; q < mp; q += blockDim.x) {  // rank sort
+  // initial order = ascending (cost, node): rank sort into sm.list, dealt out by the driver
+  for (uint32_t q = threadIdx.x; q < mp; q += blockDim.x) {
     const double c = sm.cost[q];
     uint32_t rank = 0;
     for (uint32_t o = 0; o < mp; ++o) {
       const double co = sm.cost[o];
       rank += (co < c || (co == c && o < q)) ? 1u : 0u;
     }
-    sm.order[rank] = (uint16_t)q;
+    sm.tmp[rank] = (uint16_t)q;
   }
+  __syncthreads();
+  if (wid == 0) bucket_deal(sm, mp);
+  __syncthreads();
 
   const uint32_t r_begin = a.part_job_off[part], r_end = a.part_job_off[part + 1];
   const uint32_t njobs = r_end - r_begin;
   const uint32_t row_bytes = words * 4;
-  const uint32_t issuer = blockDim.x - 32;  // lane 0 of the last warp feeds the ring
-  auto issue = [&](uint32_t i) {
+  auto issue = [&](uint32_t i) {  // driver lane 0
     const uint32_t slot = i % kRing;
     mbar_expect_tx(&s_bar[slot], (uint32_t)sizeof(JobQ) + row_bytes);
     tma_load_1d(&s_jobs[slot], &a.jobq[r_begin + i], (uint32_t)sizeof(JobQ), &s_bar[slot]);
     tma_load_1d(sm.bits_ring + (size_t)slot * words, a.bitmap + (size_t)(r_begin + i) * words, row_bytes, &s_bar[slot]);
   };
-  if (threadIdx.x == issuer)
-    for (uint32_t i = 0; i < njobs && i < (uint32_t)kRing - 1; ++i) issue(i);
-  __syncthreads();
 
+  if (wid != 0) {
+    // ======================= helpers: parked on the barrier ================
+    for (;;) {
+      __syncthreads();  // a command is ready
+      const CommitCmd c = s_cmd;
+      if (c.kind == OP_EXIT) break;
+      const long long r = c.kind == OP_TEST ? worker_step(&s_cx, c.kind, c.n, c.slot, c.t0, c.first + wid, 0x7fffffffu)
+                                            : worker_step(&s_cx, c.kind, c.n, c.slot, c.t0, wid, nw);
+      if (lane == 0) s_res[wid] = r;
+      __syncthreads();  // results are in
+    }
+    return;
+  }
+
+  // ========================= driver warp ====================================
+  if (lane == 0)
+    for (uint32_t i = 0; i < njobs && i < (uint32_t)kRing - 1; ++i) issue(i);
+  __syncwarp();
+  // runs one multi-warp step: publish the command, join the helpers, reduce
+  auto multi_step = [&](uint32_t kind, uint32_t n, uint32_t slot, int64_t t0, uint32_t first) -> long long {
+    if (lane == 0) { s_cmd.kind = kind; s_cmd.n = n; s_cmd.slot = slot; s_cmd.first = first; s_cmd.t0 = t0; }
+    __syncthreads();
+    const long long r0 = kind == OP_TEST ? worker_step(&s_cx, kind, n, slot, t0, first, 0x7fffffffu)
+                                         : worker_step(&s_cx, kind, n, slot, t0, 0, nw);
+    if (lane == 0) s_res[0] = r0;
+    __syncthreads();
+    long long acc = r0;
+    if (kind == OP_EARLY)
+      for (uint32_t w = 1; w < nw; ++w) acc = s_res[w] > acc ? s_res[w] : acc;
+    return acc;
+  };
+
+  uint32_t first_bucket = 0;  // buckets before it are empty
   PROF_DECL;
   for (uint32_t ji = 0; ji < njobs; ++ji) {
     PROF(15);
     const uint32_t slot = ji % kRing;
-    if (threadIdx.x == issuer && ji + kRing - 1 < njobs) issue(ji + kRing - 1);  // its slot was last read in job ji-1
+    if (lane == 0 && ji + kRing - 1 < njobs) issue(ji + kRing - 1);  // its slot was last used by job ji-1
     mbar_wait(&s_bar[slot], (ji / kRing) & 1u);
     const JobQ& jq = s_jobs[slot];
     const uint32_t* bits = sm.bits_ring + (size_t)slot * words;
     const uint32_t K = jq.node_num;
     const uint32_t jflags = jq.flags;
-    // copies: the ring slot is refilled as soon as the last barrier of this job is passed
-    const uint32_t job_idx = jq.job, job_alloc_off = jq.alloc_off, job_ntpn = jq.ntasks_per_node;
     const bool exclusive = jflags & 1u;
     const int64_t limit = jq.time_limit;
-    const int64_t w_end = a.now + limit;
-    const View req = jq.req;
+    const int64_t req_cpu = jq.req.cpu_raw;
     const uint64_t spec8 = jq.spec8;
     const uint32_t gnames = (jflags >> 8) & 0xffu;
-    if (threadIdx.x == 0) s_label = 0;
-    // pull the timeline head of the cheapest nodes toward L1 while the scan runs:
-    // they are the usual pick both for an immediate start and for a backfill
-    if (wid == nw - 1) {
-      const uint32_t npf = K < 2u ? K : 2u;
-      for (uint32_t k = 0; k < npf && k < mp; ++k) {
-        const uint32_t q = sm.order[k];
-        const uint32_t g = base + q;
-        const uint32_t nlines = ((uint32_t)sm.nseg[q] * (uint32_t)sizeof(TlEntry) + 127u) / 128u;
-        const char* ptr = reinterpret_cast<const char*>(a.tl.ent + (size_t)g * a.tl.cap);
-        if (lane < nlines && lane < 30) prefetch_l1(ptr + 128u * lane);
-        if (lane == 30) prefetch_l1(&a.tl.avail0[g]);
-        if (lane == 31) prefetch_l1(&a.cl.slot_node[g]);
-      }
-    }
+    while (first_bucket + 1 < sm.nb && sm.bcnt[first_bucket] == 0) ++first_bucket;
+    if (lane == 0) s_label = 0;
+    __syncwarp();
     PROF(0);
 
-    NodeRegs nr;
-    Row my_alloc;
-    uint32_t held_q = 0xffffffffu;  // node whose timeline `nr` holds
     int64_t start_time = 0;
-    bool placed = false, start_now = false;
-    uint32_t nsel = 0;
+    bool placed = false;
+    uint32_t nsel = 0;  // nodes selected for an immediate start (in sm.list[0..nsel))
 
-    // ---- nodes that can run the job now, in cost order --------------------
-    // (JobScheduler.cpp:5224-5336). Skipped when the partition-wide bounds say
-    // no node passes the pre-filter (then the reference's loop finds none).
-    const bool may_fit = exclusive || (req.cpu_raw <= s_ub_cpu &&
-                                       (!(jflags & 2u) || gres_counts_ok(s_ub_g, spec8, gnames, jq.name_need)));
-    if (K <= mp && may_fit) {
-      bool scanned_all = true;
-      long long mx_cpu = INT64_MIN;
-      unsigned long long mx_g = 0;
-      for (uint32_t cbase = 0; cbase < mp; cbase += blockDim.x) {
-        // warp w looks at positions [cbase + 32w, +32) and lists its candidates,
-        // in order, in s_cand[32w ...); the lists of warps 0,1,.. concatenate to
-        // the cost order.
-        uint16_t* s_cand = s_cand2[(cbase / blockDim.x) & 1u];  // double-buffered: one barrier per chunk
-        uint32_t* s_wcnt = s_wcnt2[(cbase / blockDim.x) & 1u];
-        const uint32_t i = cbase + threadIdx.x;
-        bool cand = false;
-        uint32_t q = 0;
-        if (i < mp) {
-          q = sm.order[i];
-          const long long c0 = sm.cpu0[q];
-          const unsigned long long gc = sm.gcnt[q];
-          mx_cpu = c0 > mx_cpu ? c0 : mx_cpu;
-          mx_g = (unsigned long long)__vmaxu4((unsigned)mx_g, (unsigned)gc) |
-                 (unsigned long long)__vmaxu4((unsigned)(mx_g >> 32), (unsigned)(gc >> 32)) << 32;
-          cand = ((bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
-          if (cand && !exclusive)
-            cand = c0 >= req.cpu_raw && (!(jflags & 2u) || gres_counts_ok(gc, spec8, gnames, jq.name_need));
+    // ---- immediate start: walk the buckets in cost order -------------------
+    // (JobScheduler.cpp:5224-5336). A bucket whose bounds cannot satisfy the
+    // pre-filter holds no candidate and is skipped.
+    if (K <= mp) {
+      uint32_t b = first_bucket;
+      while (nsel < K) {
+        // next bucket that may hold a candidate
+        uint32_t nbk = 0xffffffffu;
+        for (uint32_t b0 = b; b0 < sm.nb && nbk == 0xffffffffu; b0 += 32) {
+          const uint32_t bb = b0 + lane;
+          bool prom = false;
+          if (bb < sm.nb && sm.bcnt[bb])
+            prom = exclusive || (sm.bmax_cpu[bb] >= req_cpu && (!(jflags & 2u) || gres_counts_ok(sm.bmax_g[bb], spec8, gnames, jq.name_need)));
+          const unsigned pm = __ballot_sync(kFullMask, prom);
+          if (pm) nbk = b0 + (uint32_t)__ffs((int)pm) - 1u;
         }
-        const unsigned bm = __ballot_sync(kFullMask, cand);
-        if (cand) s_cand[wid * 32 + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)q;
-        if (lane == 0) s_wcnt[wid] = __popc(bm);
-        __syncthreads();
-        uint32_t total = 0;
-        for (uint32_t w = 0; w < nw; ++w) total += s_wcnt[w];
-        PROF(1);
-        PROF_CNT(8, total);
-        // exact test, exactly as many warps as nodes still needed, in order
-        uint32_t b0 = 0;
-        while (b0 < total && !start_now) {
-          PROF_CNT(9, 1);
-          uint32_t W = K - nsel;
-          W = W < nw ? W : nw;
-          W = W < total - b0 ? W : total - b0;
-          if (wid < W) {
-            uint32_t ww = 0, rem = b0 + wid;  // candidate b0+wid of the concatenated lists
-            while (rem >= s_wcnt[ww]) { rem -= s_wcnt[ww]; ++ww; }
-            const uint32_t q2 = s_cand[ww * 32 + rem];
-            const uint32_t g = base + q2;
-            const uint32_t n = sm.nseg[q2];
-            const Row a0 = a.tl.avail0[g];
-            Row tot;
-            if (exclusive) tot = node_total(a.cl, s_classrow, sm, base, q2);
-            node_open(a.tl, g, n, nr);
-            held_q = q2;
-            const bool pass = n <= 64 ? node_test_now(nr, req, exclusive, tot, a0, w_end, my_alloc)
-                                      : node_test_now_big(a.tl, g, n, req, exclusive, tot, a0, w_end, my_alloc);
-            if (lane == 0) { s_pass[wid] = pass ? 1u : 0u; s_passq[wid] = q2; }
+        if (nbk == 0xffffffffu) break;
+        b = nbk;
+        const uint16_t* B = sm.bk + (size_t)b * kBucket;
+        const uint32_t n = sm.bcnt[b];
+        long long mc = INT64_MIN;
+        unsigned long long mg = 0;
+        bool any_cand = false;
+        for (uint32_t h = 0; h < 2 && nsel < K; ++h) {
+          const uint32_t idx = lane + 32 * h;
+          bool cand = false;
+          uint32_t q = 0;
+          if (idx < n) {
+            q = B[idx];
+            const long long c0 = sm.cpu0[q];
+            const unsigned long long gc = sm.gcnt[q];
+            mc = c0 > mc ? c0 : mc;
+            mg = vmax8(mg, gc);
+            cand = ((bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
+            if (cand && !exclusive) cand = c0 >= req_cpu && (!(jflags & 2u) || gres_counts_ok(gc, spec8, gnames, jq.name_need));
           }
-          __syncthreads();
-          for (uint32_t w = 0; w < W; ++w) {
-            if (s_pass[w]) {
-              if (threadIdx.x == 0) { sm.sel[nsel] = (uint16_t)s_passq[w]; if (nsel < 32) s_selw[nsel] = w; }
-              ++nsel;
+          unsigned cm = __ballot_sync(kFullMask, cand);
+          any_cand = any_cand || cm != 0;
+          PROF_CNT(8, __popc(cm));
+          while (cm && nsel < K) {
+            if (K == 1) {
+              // one-node job: the driver tests (and on success updates) the node itself
+              const uint32_t l = (uint32_t)__ffs((int)cm) - 1u;
+              cm &= cm - 1u;
+              const uint32_t qc = __shfl_sync(kFullMask, q, (int)l);
+#ifdef CRANE_EMU_DEBUG
+              if (qc > 60000 && lane == 0) fprintf(stderr, "K1 cand: b=%u n=%u h=%u cm=%08x l=%u qc=%u ji=%u nb=%u mp=%u first=%u part=%u\n", b, n, h, cm, l, qc, ji, sm.nb, mp, first_bucket, part);
+#endif
+              if (lane == 0) sm.list[0] = (uint16_t)qc;
+              __syncwarp();
+              PROF_CNT(9, 1);
+              if (worker_step(&s_cx, OP_NOW_K1, 1, slot, a.now, 0, 1)) nsel = 1;
+            } else {
+              // hand the next candidates to the workers, one each, in order
+              uint32_t W = K - nsel;
+              W = W < nw ? W : nw;
+              uint32_t cnt = 0;
+              unsigned taken = 0;
+              while (cm && cnt < W) {
+                const uint32_t l = (uint32_t)__ffs((int)cm) - 1u;
+                cm &= cm - 1u;
+                taken |= 1u << l;
+                ++cnt;
+              }
+              // stage them after the already selected nodes: list[nsel .. nsel+cnt)
+              if ((taken >> lane) & 1u) sm.list[nsel + __popc(taken & ((1u << lane) - 1u))] = (uint16_t)q;
+              __syncwarp();
+              PROF_CNT(9, 1);
+              // worker w tests list[nsel + w]
+              multi_step(OP_TEST, nsel + cnt, slot, a.now, nsel);
+              // keep the passing ones, in order, compacted at list[nsel..)
+              uint32_t keep = nsel;
+              for (uint32_t w = 0; w < cnt; ++w) {
+                if (s_res[w]) {
+                  const uint16_t v = sm.list[nsel + w];
+                  __syncwarp();
+                  if (lane == 0) sm.list[keep] = v;
+                  ++keep;
+                }
+              }
+              __syncwarp();
+              nsel = keep;
             }
           }
-          b0 += W;
-          if (nsel >= K) start_now = true;
-          else if (b0 < total) __syncthreads();  // s_pass is rewritten by the next batch
         }
-        PROF(2);
-        if (start_now) { scanned_all = false; break; }
-      }
-      if (!start_now && scanned_all) {
-        // every node was looked at: tighten the partition-wide bounds
-        for (int o = 16; o > 0; o >>= 1) {
-          const long long oc = __shfl_xor_sync(kFullMask, mx_cpu, o);
-          const unsigned long long og = __shfl_xor_sync(kFullMask, mx_g, o);
-          mx_cpu = oc > mx_cpu ? oc : mx_cpu;
-          mx_g = (unsigned long long)__vmaxu4((unsigned)mx_g, (unsigned)og) |
-                 (unsigned long long)__vmaxu4((unsigned)(mx_g >> 32), (unsigned)(og >> 32)) << 32;
-        }
-        if (lane == 0) { s_wmax[wid] = mx_cpu; s_wmaxg[wid] = mx_g; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          long long m = INT64_MIN;
-          unsigned long long mg = 0;
-          for (uint32_t w = 0; w < nw; ++w) {
-            m = s_wmax[w] > m ? s_wmax[w] : m;
-            mg = (unsigned long long)__vmaxu4((unsigned)mg, (unsigned)s_wmaxg[w]) |
-                 (unsigned long long)__vmaxu4((unsigned)(mg >> 32), (unsigned)(s_wmaxg[w] >> 32)) << 32;
+        if (!any_cand) {
+          // nothing in this bucket passes the pre-filter: tighten its bounds
+          for (int o = 16; o > 0; o >>= 1) {
+            const long long oc = __shfl_xor_sync(kFullMask, mc, o);
+            mc = oc > mc ? oc : mc;
+            mg = vmax8(mg, __shfl_xor_sync(kFullMask, mg, o));
           }
-          s_ub_cpu = m;
-          s_ub_g = mg;
+          if (lane == 0) { sm.bmax_cpu[b] = mc; sm.bmax_g[b] = mg; }
+          __syncwarp();
         }
+        ++b;
       }
     }
+    PROF(2);
 
-    if (start_now) {
-      start_time = a.now;
+    if (nsel >= K && K <= mp) {
       placed = true;
+      start_time = a.now;
       PROF_CNT(10, 1);
+      if (K > 1) multi_step(OP_UPDATE_NOW, K, slot, a.now, 0);
     } else {
       // ---- backfill: the first K capable nodes in cost order, allocation
       // against res_total, earliest common start (JobScheduler.cpp:5269-5278,
       // 5371-5404; JobScheduler.h:806-849)
-      __syncthreads();
-      if (wid == 0) {
-        uint32_t cum = 0;
-        for (uint32_t i0 = 0; i0 < mp && cum < K; i0 += 32) {
-          const uint32_t i = i0 + lane;
+      uint32_t cum = 0;
+      for (uint32_t b = first_bucket; b < sm.nb && cum < K; ++b) {
+        const uint16_t* B = sm.bk + (size_t)b * kBucket;
+        const uint32_t n = sm.bcnt[b];
+        for (uint32_t h = 0; h < 2 && cum < K; ++h) {
+          const uint32_t idx = lane + 32 * h;
           bool cap = false;
           uint32_t q = 0;
-          if (i < mp) {
-            q = sm.order[i];
+          if (idx < n) {
+            q = B[idx];
             cap = ((bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
           }
           const unsigned m = __ballot_sync(kFullMask, cap);
-          const uint32_t rank = cum + __popc(m & ((1u << lane) - 1u));
-          if (cap && rank < K) sm.sel[rank] = (uint16_t)q;
-          cum += __popc(m);
+          const uint32_t rank = cum + (uint32_t)__popc(m & ((1u << lane) - 1u));
+          if (cap && rank < K) sm.list[rank] = (uint16_t)q;
+          cum += (uint32_t)__popc(m);
         }
-        if (lane == 0) s_ncap = cum;
       }
-      __syncthreads();
+      __syncwarp();
       PROF(4);
-      if (K <= mp && s_ncap >= K) {
+      if (K <= mp && cum >= K) {
         PROF_CNT(12, 1);
-        int64_t Tcur = a.now;
-        bool found = false, failed = false, first = true;
-        const bool resident = K <= nw;  // every node stays in its warp's registers
-        while (!found && !failed) {
+        if (K == 1) {
+          const long long t = worker_step(&s_cx, OP_BF_K1, 1, slot, a.now, 0, 1);
           PROF_CNT(11, 1);
-          int64_t tmax = Tcur;
-          for (uint32_t k0 = 0; k0 < K; k0 += nw) {
-            const uint32_t k = k0 + wid;
-            int64_t t = Tcur;
-            if (k < K) {
-              const uint32_t q = sm.sel[k];
-              const uint32_t g = base + q;
-              const uint32_t n = sm.nseg[q];
-              if (!resident || first) {
-                const Row tot = node_total(a.cl, s_classrow, sm, base, q);
-                node_open(a.tl, g, n, nr);
-                held_q = q;
-                if (exclusive) my_alloc = tot; else feasible_alloc(req, tot, my_alloc);
-              }
-              t = n <= 64 ? node_earliest(nr, my_alloc, Tcur, limit) : node_earliest_big(a.tl, g, n, my_alloc, Tcur, limit);
-            }
-            if (lane == 0) s_t[wid] = t;
-            __syncthreads();
-            for (uint32_t w = 0; w < nw; ++w) tmax = s_t[w] > tmax ? s_t[w] : tmax;
-            if (k0 + nw < K) __syncthreads();
+          if (t != kInf) { placed = true; start_time = t; }
+        } else {
+          int64_t Tcur = a.now;
+          bool found = false, failed = false;
+          while (!found && !failed) {
+            PROF_CNT(11, 1);
+            const int64_t tmax = multi_step(OP_EARLY, K, slot, Tcur, 0);
+            if (tmax == kInf) failed = true;
+            else if (tmax == Tcur) found = true;
+            else Tcur = tmax;
           }
-          first = false;
-          if (tmax == kInf) failed = true;
-          else if (tmax == Tcur || K == 1) { found = true; Tcur = tmax; }
-          else { Tcur = tmax; __syncthreads(); }
-        }
-        // `current_time - now > kAlgoMaxTimeWindow` (JobScheduler.h:809)
-        if (found && Tcur - a.now <= a.max_window) {
-          placed = true;
-          start_time = Tcur;
+          if (found && Tcur - a.now <= a.max_window) {
+            placed = true;
+            start_time = Tcur;
+            multi_step(OP_UPDATE_BF, K, slot, Tcur, 0);
+          }
         }
       }
       PROF(5);
     }
 
-    // ---- commit: timeline update, outputs, cost and order ------------------
+    // ---- job-level outputs and re-keying of the chosen nodes ---------------
     if (placed) {
-      const int64_t end_time = start_time + limit;
-      __syncthreads();  // sm.sel / s_selw complete
-      // updates one selected node with the warp's registers (reopening it if a
-      // later batch reused them) and writes its allocation, node-index ascending
-      // (deviation D3).
-      auto commit_node = [&](uint32_t k) {
-        const uint32_t q = sm.sel[k];
-        const uint32_t g = base + q;
-        const uint32_t n = sm.nseg[q];
-        Row seg0;
-        uint32_t nn;
-        if (held_q == q && n <= 64) {
-          nn = node_update(a.tl, g, nr, start_time, end_time, my_alloc, seg0);
-        } else {
-          // registers hold another node (a later batch reused them, or K > warps)
-          // or the timeline is long: recompute the allocation and update in memory
-          if (held_q != q) {
-            const Row tot = node_total(a.cl, s_classrow, sm, base, q);
-            if (start_now) node_test_now_big(a.tl, g, n, req, exclusive, tot, a.tl.avail0[g], w_end, my_alloc);
-            else if (exclusive) my_alloc = tot;
-            else feasible_alloc(req, tot, my_alloc);
-          }
-          nn = node_update_big(a.tl, g, n, start_time, end_time, my_alloc, seg0);
-        }
-        held_q = 0xffffffffu;
-        uint32_t rank = 0;
-        for (uint32_t m = lane; m < K; m += 32) rank += sm.sel[m] < q ? 1u : 0u;
-        for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(kFullMask, rank, o);
-        if (lane == 0) {
-          sm.nseg[q] = (uint16_t)nn;
-          if (nn >= a.max_jobs) sm.skip[q] = 1;
-          sm.cpu0[q] = seg0.cpu_raw;
-          sm.gcnt[q] = pack_gres_counts(seg0);
-          const uint32_t dst = job_alloc_off + rank;
-          a.out.alloc_node[dst] = a.cl.slot_node[g];
-          a.out.alloc_ntasks[dst] = job_ntpn;
-          a.out.alloc_res[dst] = my_alloc;
-          // pending-reason label for future starts (JobScheduler.cpp:5842-5848)
-          if (start_time != a.now && !row_le(my_alloc, a.tl.avail0[g])) atomicOr(&s_label, 1u);
-        }
-      };
-      // start-now with K <= warps: the warp that tested a node owns it (possibly
-      // one per batch); otherwise nodes are dealt round-robin
-      const bool owner_mode = start_now && K <= nw;
-#pragma unroll 1
-      for (uint32_t k = 0; k < K; ++k) {
-        const bool mine = owner_mode ? (s_selw[k] == wid) : (k % nw == wid);
-        if (mine) commit_node(k);
-      }
       PROF(6);
-      // cost += (end-start) * cpu ratio, then re-key (JobScheduler.h:46-52,520-532).
-      // The allocation's cpu is the job's per-node request, or the node total
-      // for exclusive jobs.
-      bool synced = false;
-      for (uint32_t k = 0; k < K; ++k) {
-        const uint32_t q = sm.sel[k];
-        const int64_t tot_cpu = node_total(a.cl, s_classrow, sm, base, q).cpu_raw;
-        const double delta = cost_delta(limit, exclusive ? tot_cpu : req.cpu_raw, tot_cpu);
-        const double oc = sm.cost[q];
-        const double nc = __dadd_rn(oc, delta);
-        if (nc > oc) { reorder_node(sm, mp, q, oc, nc, s_red, s_pb); synced = true; }  // barriers inside
-      }
-      if (!synced) __syncthreads();
-      // job-level outputs; s_label is complete: every path above passed a barrier
-      // after the node updates
-      if (threadIdx.x == 0) {
-        a.out.start_time[job_idx] = start_time;
-        a.out.end_time[job_idx] = end_time;
-        a.out.n_alloc[job_idx] = K;
+      if (lane == 0) {
+        a.out.start_time[jq.job] = start_time;
+        a.out.end_time[jq.job] = start_time + limit;
+        a.out.n_alloc[jq.job] = K;
         uint8_t reason = CRANE_REASON_NONE;
         if (start_time != a.now) reason = s_label ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY;
-        a.out.reason[job_idx] = reason;
+        a.out.reason[jq.job] = reason;
+      }
+      // cost += (end-start) * cpu ratio (JobScheduler.h:46-52); the allocation's
+      // cpu is the job's per-node request, or the node total for exclusive jobs
+#pragma unroll 1
+      for (uint32_t k = 0; k < K; ++k) {
+        const uint32_t q = sm.list[k];
+        const int64_t tot_cpu = sm.cls[q] != 0xff ? s_classrow[sm.cls[q]].cpu_raw : a.cl.slot_total[base + q].cpu_raw;
+        const double delta = cost_delta(limit, exclusive ? tot_cpu : req_cpu, tot_cpu);
+        const double oc = sm.cost[q];
+        const double nc = __dadd_rn(oc, delta);
+        if (nc > oc) {
+          const uint32_t from = sm.bkt[q];
+          bucket_remove(sm, q);
+          if (!bucket_insert(sm, q, nc, from)) {
+            // the target bucket is full: spread the other nodes evenly again
+            // (q is in no bucket right now), then insert into a bucket with room
+            bucket_rebuild(sm);
+            first_bucket = 0;
+            bucket_insert(sm, q, nc, 0);
+          }
+        }
       }
       PROF(7);
     } else {
-      if (threadIdx.x == 0) a.out.reason[job_idx] = CRANE_REASON_RESOURCE;  // JobScheduler.cpp:5802
-      __syncthreads();
+      if (lane == 0) a.out.reason[jq.job] = CRANE_REASON_RESOURCE;  // JobScheduler.cpp:5802
     }
   }
+  // release the helpers
+  if (lane == 0) s_cmd.kind = OP_EXIT;
+  __syncthreads();
   PROF_FLUSH(a.prof);
 }
 
