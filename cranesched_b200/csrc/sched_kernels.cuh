@@ -655,7 +655,8 @@ struct CommitArgs {
   unsigned long long* prof;      // [n_parts][16] cycle counters (profiling builds)
 };
 
-constexpr int kRing = 4;             // prefetch ring depth (jobs)
+constexpr int kRing = 16;            // prefetch ring depth (jobs)
+constexpr int kBatch = 8;            // one-node jobs dispatched together (<= warps per CTA)
 constexpr int kCommitThreads = 256;  // CTA size of k_commit: driver warp + 7 helpers
 constexpr int kBucket = 64;          // bucket capacity of the cost order
 constexpr int kBucketFill = 32;      // entries per bucket after a (re)build
@@ -666,6 +667,7 @@ struct CommitSmem {
   long long* cpu0;             // [mp]  cpu of the first timeline segment
   unsigned long long* gcnt;    // [mp]  packed gres slot counts of the first segment
   long long* bmax_cpu;         // [nb]  >= cpu0 of every node in the bucket
+  long long* bmax_cpug;        // [nb]  >= cpu0 of every node in the bucket that still has a free gres slot
   unsigned long long* bmax_g;  // [nb]  >= gcnt (per byte) of every node in the bucket
   uint16_t* bk;                // [nb][kBucket] node ids, ascending (cost, node); buckets ascending
   uint16_t* bcnt;              // [nb]
@@ -675,17 +677,18 @@ struct CommitSmem {
   uint16_t* nseg;              // [mp]  timeline entry counts
   uint8_t* skip;               // [mp]
   uint8_t* cls;                // [mp]
+  uint8_t* bexact;             // [nb]  bounds are the exact maxima (nothing inserted since the last tightening)
   uint32_t nb;
 };
 __host__ __device__ inline uint32_t commit_nbuckets(uint32_t mp) { return (mp + kBucketFill - 1) / kBucketFill + 1; }
 __host__ __device__ inline size_t commit_smem_bytes(uint32_t mp, uint32_t words) {
   const size_t nb = commit_nbuckets(mp);
   size_t b = (size_t)kRing * words * 4;
-  b += (size_t)mp * 8 * 3 + nb * 8 * 2;
+  b += (size_t)mp * 8 * 3 + nb * 8 * 3 + nb;
   b += nb * kBucket * 2 + nb * 2;
   b += (size_t)mp * 2 * 4;
   b += (size_t)mp * 2;
-  return b + 96;
+  return b + 128;
 }
 
 // ---- TMA 1-D bulk copy + mbarrier (sm_90+/sm_100a) --------------------------
@@ -1082,8 +1085,11 @@ __device__ __forceinline__ bool bucket_insert(CommitSmem& sm, uint32_t u, double
     sm.bkt[u] = (uint16_t)tb;
     sm.cost[u] = new_cost;
     const long long c = sm.cpu0[u];
+    const unsigned long long gc = sm.gcnt[u];
     if (c > sm.bmax_cpu[tb]) sm.bmax_cpu[tb] = c;
-    sm.bmax_g[tb] = vmax8(sm.bmax_g[tb], sm.gcnt[u]);
+    if (gc && c > sm.bmax_cpug[tb]) sm.bmax_cpug[tb] = c;
+    sm.bmax_g[tb] = vmax8(sm.bmax_g[tb], gc);
+    sm.bexact[tb] = 0;
   }
   __syncwarp();
   return true;
@@ -1096,7 +1102,7 @@ __device__ __noinline__ void bucket_deal(CommitSmem& sm, uint32_t total) {
   for (uint32_t b = 0; b < sm.nb; ++b) {
     const uint32_t lo = b * kBucketFill;
     const uint32_t n = lo < total ? (total - lo < (uint32_t)kBucketFill ? total - lo : (uint32_t)kBucketFill) : 0u;
-    long long mc = INT64_MIN;
+    long long mc = INT64_MIN, mcg = INT64_MIN;
     unsigned long long mg = 0;
     if (lane < n) {
       const uint32_t q = sm.tmp[lo + lane];
@@ -1104,13 +1110,15 @@ __device__ __noinline__ void bucket_deal(CommitSmem& sm, uint32_t total) {
       sm.bkt[q] = (uint16_t)b;
       mc = sm.cpu0[q];
       mg = sm.gcnt[q];
+      if (mg) mcg = mc;
     }
     for (int o = 16; o > 0; o >>= 1) {
-      const long long oc = __shfl_xor_sync(kFullMask, mc, o);
+      const long long oc = __shfl_xor_sync(kFullMask, mc, o), ocg = __shfl_xor_sync(kFullMask, mcg, o);
       mc = oc > mc ? oc : mc;
+      mcg = ocg > mcg ? ocg : mcg;
       mg = vmax8(mg, __shfl_xor_sync(kFullMask, mg, o));
     }
-    if (lane == 0) { sm.bcnt[b] = (uint16_t)n; sm.bmax_cpu[b] = mc; sm.bmax_g[b] = mg; }
+    if (lane == 0) { sm.bcnt[b] = (uint16_t)n; sm.bmax_cpu[b] = mc; sm.bmax_cpug[b] = mcg; sm.bmax_g[b] = mg; sm.bexact[b] = 1; }
   }
   __syncwarp();
 }
@@ -1136,7 +1144,13 @@ enum : uint32_t {
   OP_EARLY = 3,      // workers: earliest fit >= t0 over their share of list[0..n)
   OP_UPDATE_NOW = 4, // workers: allocate against the window minimum and update their share
   OP_UPDATE_BF = 5,  // workers: allocate against res_total and update their share
-  OP_EXIT = 6,
+  OP_BATCH_P = 6,    // batch of one-node jobs: worker w evaluates task w (no state change)
+  OP_BATCH_C = 7,    // ... worker w < n commits task w
+  OP_EXIT = 8,
+};
+struct BatchTask {
+  uint32_t slot;   // ring slot of the job
+  uint32_t mode;   // 0 = immediate start on list[w], 1 = backfill on list[w]
 };
 struct CommitCmd {
   uint32_t kind, n, slot, first;  // OP_TEST: worker w handles list[first + w]; others: list[w], list[w+nw], ...
@@ -1164,7 +1178,7 @@ struct WorkerCtx {  // lives in shared memory; read-only after set-up
 // Returns: OP_NOW_K1/OP_TEST pass flag; OP_BF_K1 start time or kInf; OP_EARLY
 // the max earliest fit over the share.
 __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kind, uint32_t n, uint32_t slot,
-                                              int64_t t0, uint32_t first, uint32_t stride) {
+                                              int64_t t0, uint32_t first, uint32_t stride, uint32_t batch) {
   const WorkerCtx& cx = *cxp;
   const CommitSmem& sm = cx.sm;
   const uint32_t lane = lane_id();
@@ -1221,7 +1235,7 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
       const uint32_t nn = ns <= 64 ? node_update(cx.tl, g, nr, start, end, alloc, seg0)
                                    : node_update_big(cx.tl, g, ns, start, end, alloc, seg0);
       uint32_t rank = 0;  // node-index ascending output slot (deviation D3)
-      if (n > 1) {
+      if (n > 1 && !batch) {
         for (uint32_t m = lane; m < K; m += 32) rank += sm.list[m] < q ? 1u : 0u;
         for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(kFullMask, rank, o);
       }
@@ -1235,7 +1249,15 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
         cx.out.alloc_ntasks[dst] = jq.ntasks_per_node;
         cx.out.alloc_res[dst] = alloc;
         // pending-reason label for future starts (JobScheduler.cpp:5842-5848)
-        if (start != now && !row_le(alloc, a0)) atomicOr(cx.label, 1u);
+        const bool short_now = start != now && !row_le(alloc, a0);
+        if (batch) {  // one-node job of a batch: its job-level outputs are written here
+          cx.out.start_time[jq.job] = start;
+          cx.out.end_time[jq.job] = end;
+          cx.out.n_alloc[jq.job] = 1;
+          cx.out.reason[jq.job] = start == now ? CRANE_REASON_NONE : (short_now ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY);
+        } else if (short_now) {
+          atomicOr(cx.label, 1u);
+        }
       }
       __syncwarp();  // lane 0's shared-memory writes are visible to the whole warp
     }
@@ -1262,6 +1284,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     sm.cpu0 = reinterpret_cast<long long*>(ptr); ptr += (size_t)mp * 8;
     sm.gcnt = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)mp * 8;
     sm.bmax_cpu = reinterpret_cast<long long*>(ptr); ptr += (size_t)sm.nb * 8;
+    sm.bmax_cpug = reinterpret_cast<long long*>(ptr); ptr += (size_t)sm.nb * 8;
     sm.bmax_g = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)sm.nb * 8;
     sm.bk = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)sm.nb * kBucket * 2;
     sm.bcnt = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)sm.nb * 2;
@@ -1270,12 +1293,16 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     sm.tmp = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.nseg = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.skip = ptr; ptr += mp;
-    sm.cls = ptr;
+    sm.cls = ptr; ptr += mp;
+    sm.bexact = ptr;
   }
   __shared__ JobQ s_jobs[kRing];
   __shared__ __align__(8) uint64_t s_bar[kRing];
   __shared__ Row s_classrow[kMaxClasses];
   __shared__ CommitCmd s_cmd;
+  __shared__ BatchTask s_task[kBatch];
+  __shared__ int64_t s_tstart[kBatch];
+  __shared__ double s_undo[kBatch];
   __shared__ WorkerCtx s_cx;
   __shared__ long long s_res[32];   // per-worker result of a multi-warp step
   __shared__ uint32_t s_label;
@@ -1331,8 +1358,18 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       __syncthreads();  // a command is ready
       const CommitCmd c = s_cmd;
       if (c.kind == OP_EXIT) break;
-      const long long r = c.kind == OP_TEST ? worker_step(&s_cx, c.kind, c.n, c.slot, c.t0, c.first + wid, 0x7fffffffu)
-                                            : worker_step(&s_cx, c.kind, c.n, c.slot, c.t0, wid, nw);
+      long long r = 0;
+      if (c.kind == OP_BATCH_P || c.kind == OP_BATCH_C) {
+        if (wid < c.n) {  // task wid of the batch: node sm.list[wid], job in ring slot s_task[wid].slot
+          const BatchTask t = s_task[wid];
+          const uint32_t k = c.kind == OP_BATCH_P ? (t.mode ? OP_EARLY : OP_TEST) : (t.mode ? OP_UPDATE_BF : OP_UPDATE_NOW);
+          r = worker_step(&s_cx, k, wid + 1, t.slot, c.kind == OP_BATCH_P ? s_cx.now : s_tstart[wid], wid, 0x7fffffffu, 1);
+        }
+      } else if (c.kind == OP_TEST) {
+        r = worker_step(&s_cx, c.kind, c.n, c.slot, c.t0, c.first + wid, 0x7fffffffu, 0);
+      } else {
+        r = worker_step(&s_cx, c.kind, c.n, c.slot, c.t0, wid, nw, 0);
+      }
       if (lane == 0) s_res[wid] = r;
       __syncthreads();  // results are in
     }
@@ -1340,15 +1377,12 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   }
 
   // ========================= driver warp ====================================
-  if (lane == 0)
-    for (uint32_t i = 0; i < njobs && i < (uint32_t)kRing - 1; ++i) issue(i);
-  __syncwarp();
   // runs one multi-warp step: publish the command, join the helpers, reduce
   auto multi_step = [&](uint32_t kind, uint32_t n, uint32_t slot, int64_t t0, uint32_t first) -> long long {
     if (lane == 0) { s_cmd.kind = kind; s_cmd.n = n; s_cmd.slot = slot; s_cmd.first = first; s_cmd.t0 = t0; }
     __syncthreads();
-    const long long r0 = kind == OP_TEST ? worker_step(&s_cx, kind, n, slot, t0, first, 0x7fffffffu)
-                                         : worker_step(&s_cx, kind, n, slot, t0, 0, nw);
+    const long long r0 = kind == OP_TEST ? worker_step(&s_cx, kind, n, slot, t0, first, 0x7fffffffu, 0)
+                                         : worker_step(&s_cx, kind, n, slot, t0, 0, nw, 0);
     if (lane == 0) s_res[0] = r0;
     __syncthreads();
     long long acc = r0;
@@ -1358,11 +1392,33 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   };
 
   uint32_t first_bucket = 0;  // buckets before it are empty
+  uint32_t issued = 0;        // jobs whose records were requested from the ring
   PROF_DECL;
-  for (uint32_t ji = 0; ji < njobs; ++ji) {
+
+  // ring slot of job i is free once job i-kRing is finished
+  auto ensure_issued = [&](uint32_t finished) {
+    while (issued < njobs && issued < finished + (uint32_t)kRing) {
+      if (lane == 0) issue(issued);
+      ++issued;
+    }
+    __syncwarp();
+  };
+  // re-key node q to cost nc in the bucketed order (JobScheduler.h:520-532)
+  auto rekey = [&](uint32_t q, double nc, uint32_t from) {
+    bucket_remove(sm, q);
+    if (!bucket_insert(sm, q, nc, from)) {
+      // the target bucket is full: spread the other nodes evenly again (q is in
+      // no bucket right now), then insert into a bucket with room
+      bucket_rebuild(sm);
+      first_bucket = 0;
+      bucket_insert(sm, q, nc, 0);
+    }
+  };
+
+  // ---- one job, start to finish (any node_num) ------------------------------
+  auto process_single = [&](uint32_t ji) {
     PROF(15);
     const uint32_t slot = ji % kRing;
-    if (lane == 0 && ji + kRing - 1 < njobs) issue(ji + kRing - 1);  // its slot was last used by job ji-1
     mbar_wait(&s_bar[slot], (ji / kRing) & 1u);
     const JobQ& jq = s_jobs[slot];
     const uint32_t* bits = sm.bits_ring + (size_t)slot * words;
@@ -1394,7 +1450,8 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
           const uint32_t bb = b0 + lane;
           bool prom = false;
           if (bb < sm.nb && sm.bcnt[bb])
-            prom = exclusive || (sm.bmax_cpu[bb] >= req_cpu && (!(jflags & 2u) || gres_counts_ok(sm.bmax_g[bb], spec8, gnames, jq.name_need)));
+            prom = exclusive || ((jflags & 2u) ? (sm.bmax_cpug[bb] >= req_cpu && gres_counts_ok(sm.bmax_g[bb], spec8, gnames, jq.name_need))
+                                               : sm.bmax_cpu[bb] >= req_cpu);
           const unsigned pm = __ballot_sync(kFullMask, prom);
           if (pm) nbk = b0 + (uint32_t)__ffs((int)pm) - 1u;
         }
@@ -1402,8 +1459,6 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         b = nbk;
         const uint16_t* B = sm.bk + (size_t)b * kBucket;
         const uint32_t n = sm.bcnt[b];
-        long long mc = INT64_MIN;
-        unsigned long long mg = 0;
         bool any_cand = false;
         for (uint32_t h = 0; h < 2 && nsel < K; ++h) {
           const uint32_t idx = lane + 32 * h;
@@ -1411,12 +1466,9 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
           uint32_t q = 0;
           if (idx < n) {
             q = B[idx];
-            const long long c0 = sm.cpu0[q];
-            const unsigned long long gc = sm.gcnt[q];
-            mc = c0 > mc ? c0 : mc;
-            mg = vmax8(mg, gc);
             cand = ((bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
-            if (cand && !exclusive) cand = c0 >= req_cpu && (!(jflags & 2u) || gres_counts_ok(gc, spec8, gnames, jq.name_need));
+            if (cand && !exclusive)
+              cand = sm.cpu0[q] >= req_cpu && (!(jflags & 2u) || gres_counts_ok(sm.gcnt[q], spec8, gnames, jq.name_need));
           }
           unsigned cm = __ballot_sync(kFullMask, cand);
           any_cand = any_cand || cm != 0;
@@ -1427,13 +1479,10 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
               const uint32_t l = (uint32_t)__ffs((int)cm) - 1u;
               cm &= cm - 1u;
               const uint32_t qc = __shfl_sync(kFullMask, q, (int)l);
-#ifdef CRANE_EMU_DEBUG
-              if (qc > 60000 && lane == 0) fprintf(stderr, "K1 cand: b=%u n=%u h=%u cm=%08x l=%u qc=%u ji=%u nb=%u mp=%u first=%u part=%u\n", b, n, h, cm, l, qc, ji, sm.nb, mp, first_bucket, part);
-#endif
               if (lane == 0) sm.list[0] = (uint16_t)qc;
               __syncwarp();
               PROF_CNT(9, 1);
-              if (worker_step(&s_cx, OP_NOW_K1, 1, slot, a.now, 0, 1)) nsel = 1;
+              if (worker_step(&s_cx, OP_NOW_K1, 1, slot, a.now, 0, 1, 0)) nsel = 1;
             } else {
               // hand the next candidates to the workers, one each, in order
               uint32_t W = K - nsel;
@@ -1467,14 +1516,29 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
             }
           }
         }
-        if (!any_cand) {
-          // nothing in this bucket passes the pre-filter: tighten its bounds
+        if (!any_cand && !sm.bexact[b]) {
+          // nothing in this bucket passes the pre-filter: tighten its bounds to
+          // the exact maxima (once; an insert makes them inexact again)
+          long long mc = INT64_MIN, mcg = INT64_MIN;
+          unsigned long long mg = 0;
+          for (uint32_t h = 0; h < 2; ++h) {
+            const uint32_t idx = lane + 32 * h;
+            if (idx < n) {
+              const uint32_t q = B[idx];
+              const long long c0 = sm.cpu0[q];
+              const unsigned long long gc = sm.gcnt[q];
+              mc = c0 > mc ? c0 : mc;
+              if (gc && c0 > mcg) mcg = c0;
+              mg = vmax8(mg, gc);
+            }
+          }
           for (int o = 16; o > 0; o >>= 1) {
-            const long long oc = __shfl_xor_sync(kFullMask, mc, o);
+            const long long oc = __shfl_xor_sync(kFullMask, mc, o), ocg = __shfl_xor_sync(kFullMask, mcg, o);
             mc = oc > mc ? oc : mc;
+            mcg = ocg > mcg ? ocg : mcg;
             mg = vmax8(mg, __shfl_xor_sync(kFullMask, mg, o));
           }
-          if (lane == 0) { sm.bmax_cpu[b] = mc; sm.bmax_g[b] = mg; }
+          if (lane == 0) { sm.bmax_cpu[b] = mc; sm.bmax_cpug[b] = mcg; sm.bmax_g[b] = mg; sm.bexact[b] = 1; }
           __syncwarp();
         }
         ++b;
@@ -1514,7 +1578,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       if (K <= mp && cum >= K) {
         PROF_CNT(12, 1);
         if (K == 1) {
-          const long long t = worker_step(&s_cx, OP_BF_K1, 1, slot, a.now, 0, 1);
+          const long long t = worker_step(&s_cx, OP_BF_K1, 1, slot, a.now, 0, 1, 0);
           PROF_CNT(11, 1);
           if (t != kInf) { placed = true; start_time = t; }
         } else {
@@ -1557,21 +1621,191 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         const double delta = cost_delta(limit, exclusive ? tot_cpu : req_cpu, tot_cpu);
         const double oc = sm.cost[q];
         const double nc = __dadd_rn(oc, delta);
-        if (nc > oc) {
-          const uint32_t from = sm.bkt[q];
-          bucket_remove(sm, q);
-          if (!bucket_insert(sm, q, nc, from)) {
-            // the target bucket is full: spread the other nodes evenly again
-            // (q is in no bucket right now), then insert into a bucket with room
-            bucket_rebuild(sm);
-            first_bucket = 0;
-            bucket_insert(sm, q, nc, 0);
-          }
-        }
+        if (nc > oc) rekey(q, nc, sm.bkt[q]);
       }
       PROF(7);
     } else {
       if (lane == 0) a.out.reason[jq.job] = CRANE_REASON_RESOURCE;  // JobScheduler.cpp:5802
+    }
+    };
+
+  // ---- dispatcher: runs of one-node jobs go out as batches --------------------
+  // For up to kBatch consecutive one-node jobs the driver picks each job's node
+  // as the reference would (first pre-filter candidate in cost order for an
+  // immediate start, else the first capable node for a backfill), assuming the
+  // jobs before it in the batch get placed, and re-keys that node at once.
+  // The workers then evaluate all picks in parallel without touching state;
+  // picks up to the first failure are committed in parallel, the rest is rolled
+  // back (re-key undone) and the failing job takes the one-job path. A job
+  // whose pick is already in the batch ends the batch (it needs that node's
+  // updated timeline).
+  uint32_t ji = 0;
+  while (ji < njobs) {
+    ensure_issued(ji);
+    uint32_t nt = 0;
+    PROF(1);
+    while (nt < (uint32_t)kBatch && nt < nw && ji + nt < njobs) {
+      const uint32_t j = ji + nt;
+      const uint32_t slot = j % kRing;
+      mbar_wait(&s_bar[slot], (j / kRing) & 1u);
+      const JobQ& jq = s_jobs[slot];
+      if (jq.node_num != 1 || mp == 0) break;
+      const uint32_t* bits = sm.bits_ring + (size_t)slot * words;
+      const uint32_t jflags = jq.flags;
+      const bool exclusive = jflags & 1u;
+      const int64_t req_cpu = jq.req.cpu_raw;
+      const uint64_t spec8 = jq.spec8;
+      const uint32_t gnames = (jflags >> 8) & 0xffu;
+      while (first_bucket + 1 < sm.nb && sm.bcnt[first_bucket] == 0) ++first_bucket;
+      // (1) first node in cost order that passes capability + pre-filter
+      uint32_t q = 0xffffffffu, mode = 0;
+      for (uint32_t b = first_bucket; q == 0xffffffffu;) {
+        uint32_t nbk = 0xffffffffu;
+        for (uint32_t b0 = b; b0 < sm.nb && nbk == 0xffffffffu; b0 += 32) {
+          const uint32_t bb = b0 + lane;
+          bool prom = false;
+          if (bb < sm.nb && sm.bcnt[bb])
+            prom = exclusive || ((jflags & 2u) ? (sm.bmax_cpug[bb] >= req_cpu && gres_counts_ok(sm.bmax_g[bb], spec8, gnames, jq.name_need))
+                                               : sm.bmax_cpu[bb] >= req_cpu);
+          const unsigned pm = __ballot_sync(kFullMask, prom);
+          if (pm) nbk = b0 + (uint32_t)__ffs((int)pm) - 1u;
+        }
+        if (nbk == 0xffffffffu) break;
+        b = nbk;
+        const uint16_t* B = sm.bk + (size_t)b * kBucket;
+        const uint32_t n = sm.bcnt[b];
+        for (uint32_t h = 0; h < 2 && q == 0xffffffffu; ++h) {
+          const uint32_t idx = lane + 32 * h;
+          bool cand = false;
+          uint32_t qq = 0;
+          if (idx < n) {
+            qq = B[idx];
+            cand = ((bits[qq >> 5] >> (qq & 31)) & 1u) && !sm.skip[qq];
+            if (cand && !exclusive)
+              cand = sm.cpu0[qq] >= req_cpu && (!(jflags & 2u) || gres_counts_ok(sm.gcnt[qq], spec8, gnames, jq.name_need));
+          }
+          const unsigned cm = __ballot_sync(kFullMask, cand);
+          if (cm) q = __shfl_sync(kFullMask, qq, __ffs((int)cm) - 1);
+        }
+        if (q == 0xffffffffu && !sm.bexact[b]) {
+          long long mc = INT64_MIN, mcg = INT64_MIN;
+          unsigned long long mg = 0;
+          for (uint32_t h = 0; h < 2; ++h) {
+            const uint32_t idx = lane + 32 * h;
+            if (idx < n) {
+              const uint32_t qq = B[idx];
+              const long long c0 = sm.cpu0[qq];
+              const unsigned long long gc = sm.gcnt[qq];
+              mc = c0 > mc ? c0 : mc;
+              if (gc && c0 > mcg) mcg = c0;
+              mg = vmax8(mg, gc);
+            }
+          }
+          for (int o = 16; o > 0; o >>= 1) {
+            const long long oc = __shfl_xor_sync(kFullMask, mc, o), ocg = __shfl_xor_sync(kFullMask, mcg, o);
+            mc = oc > mc ? oc : mc;
+            mcg = ocg > mcg ? ocg : mcg;
+            mg = vmax8(mg, __shfl_xor_sync(kFullMask, mg, o));
+          }
+          if (lane == 0) { sm.bmax_cpu[b] = mc; sm.bmax_cpug[b] = mcg; sm.bmax_g[b] = mg; sm.bexact[b] = 1; }
+          __syncwarp();
+        }
+        ++b;
+      }
+      // (2) else the first capable node (backfill)
+      if (q == 0xffffffffu) {
+        mode = 1;
+        for (uint32_t b = first_bucket; b < sm.nb && q == 0xffffffffu; ++b) {
+          const uint16_t* B = sm.bk + (size_t)b * kBucket;
+          const uint32_t n = sm.bcnt[b];
+          for (uint32_t h = 0; h < 2 && q == 0xffffffffu; ++h) {
+            const uint32_t idx = lane + 32 * h;
+            bool cap = false;
+            uint32_t qq = 0;
+            if (idx < n) {
+              qq = B[idx];
+              cap = ((bits[qq >> 5] >> (qq & 31)) & 1u) && !sm.skip[qq];
+            }
+            const unsigned cm = __ballot_sync(kFullMask, cap);
+            if (cm) q = __shfl_sync(kFullMask, qq, __ffs((int)cm) - 1);
+          }
+        }
+      }
+      PROF(3);
+      if (q == 0xffffffffu) break;  // no capable node at all: the one-job path reports "Resource"
+      bool clash = false;
+      for (uint32_t t = 0; t < nt; ++t) clash = clash || sm.list[t] == q;
+      if (clash) break;
+      // speculative re-key (cost += (end-start) * cpu ratio, JobScheduler.h:46-52)
+      const int64_t tot_cpu = sm.cls[q] != 0xff ? s_classrow[sm.cls[q]].cpu_raw : a.cl.slot_total[base + q].cpu_raw;
+      const double oc = sm.cost[q];
+      const double nc = __dadd_rn(oc, cost_delta(jq.time_limit, exclusive ? tot_cpu : req_cpu, tot_cpu));
+      if (lane == 0) {
+        s_task[nt].slot = slot;
+        s_task[nt].mode = mode;
+        sm.list[nt] = (uint16_t)q;
+        s_undo[nt] = oc;
+      }
+      __syncwarp();
+      if (nc > oc) rekey(q, nc, sm.bkt[q]);
+      ++nt;
+      PROF(6);
+    }
+
+    bool single = nt == 0;
+    if (nt) {
+      // evaluate all picks in parallel (no state change) ...
+      if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = nt; }
+      __syncthreads();
+      {
+        const BatchTask t = s_task[0];
+        const long long r0 = worker_step(&s_cx, t.mode ? OP_EARLY : OP_TEST, 1, t.slot, a.now, 0, 0x7fffffffu, 1);
+        if (lane == 0) s_res[0] = r0;
+      }
+      __syncthreads();
+      PROF(9);
+      uint32_t f = nt;  // first pick that did not work out
+      for (uint32_t t = 0; t < nt; ++t) {
+        const long long r = s_res[t];
+        int64_t start = a.now;
+        bool ok;
+        if (s_task[t].mode == 0) ok = r != 0;
+        else { ok = r != kInf && r - a.now <= a.max_window; start = r; }  // JobScheduler.h:809
+        if (!ok) { f = t; break; }
+        if (lane == 0) s_tstart[t] = start;
+      }
+      // ... commit the good prefix in parallel
+      if (lane == 0) { s_cmd.kind = OP_BATCH_C; s_cmd.n = f; }
+      __syncthreads();
+      if (f > 0) {
+        const BatchTask t = s_task[0];
+        worker_step(&s_cx, t.mode ? OP_UPDATE_BF : OP_UPDATE_NOW, 1, t.slot, s_tstart[0], 0, 0x7fffffffu, 1);
+      }
+      __syncthreads();
+      PROF(10);
+      PROF_CNT(13, f);
+      PROF_CNT(14, 1);
+      // roll back the re-keys of the picks that were not committed, last first
+      for (uint32_t t = nt; t > f; --t) {
+        const uint32_t q = sm.list[t - 1];
+        const double oc = s_undo[t - 1];
+        if (sm.cost[q] != oc) {
+          bucket_remove(sm, q);
+          if (!bucket_insert(sm, q, oc, 0)) {
+            bucket_rebuild(sm);
+            bucket_insert(sm, q, oc, 0);
+          }
+          first_bucket = 0;
+        }
+      }
+      PROF(11);
+      ji += f;
+      single = f < nt;
+    }
+    if (single) {
+      ensure_issued(ji);
+      process_single(ji);
+      ++ji;
     }
   }
   // release the helpers

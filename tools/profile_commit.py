@@ -6,9 +6,10 @@ from cranesched_b200 import synth, abi
 from cranesched_b200.scheduler import GpuScheduler
 from cranesched_b200.build import CSRC
 
-NAMES = ["0 job load", "1 scan+compact", "2 exact batches", "3 alloc(now)", "4 total-list scan", "5 alloc+earliest",
-         "6 timeline update", "7 outputs+reorder", "8 #cand", "9 #batches", "10 #start-now", "11 #fixpoint iters",
-         "12 #backfill", "13", "14", "15 loop tail"]
+NAMES = ["0 single: job load", "1 batch: loop top", "2 single: scan+test(+update)", "3 batch: select node", "4 single: bf select",
+         "5 single: bf work", "6 batch: bookkeeping+rekey", "7 single: outputs+rekey", "8 #cand", "9 batch: P phase (eval)", "10 batch: C phase (commit)",
+         "11 batch: rollback", "12 #backfill(single)", "13 #committed in batches", "14 #batches", "15 single: entry"]
+TIMED = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 15}
 cfg_id = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 kw = {}
 if len(sys.argv) > 3:
@@ -23,11 +24,11 @@ prof = s.debug_profile()
 jobs = np.bincount(pd.partition[pd.partition < cl.n_partitions], minlength=cl.n_partitions)
 print(json.dumps({k: round(v, 3) for k, v in t.items()}))
 for p in range(cl.n_partitions):
-    tot = prof[p, :8].sum() + prof[p, 15]
+    tot = sum(int(prof[p, i]) for i in TIMED)
     print("partition %d: %d jobs, %.0f cycles/job, total %.1f Mcycles" % (p, jobs[p], tot / max(jobs[p], 1), tot / 1e6))
     for i, n in enumerate(NAMES):
         v = int(prof[p, i])
-        if i < 8 or i == 15:
+        if i in TIMED:
             print("   %-20s %8.0f cyc/job  %5.1f%%" % (n, v / max(jobs[p], 1), 100.0 * v / max(tot, 1)))
         elif v:
             print("   %-20s %10.2f per job" % (n, v / max(jobs[p], 1)))
