@@ -99,14 +99,11 @@ def algorithmic_bytes(cluster, pending, n_decided):
 
 
 def workload(args, rank):
-    from cranesched_b200 import synth
-    if args.config == 2:
-        return synth.config2(n_jobs=args.jobs or 100_000, n_nodes=args.nodes or 10_000, seed_id=2 + 1000 * rank)
-    if args.config == 5:
-        return synth.config5(n_jobs=args.jobs or 200_000, n_nodes=args.nodes or 5_000, seed_id=5 + 1000 * rank)
-    if args.config == 1:
-        return synth.config1()
-    raise SystemExit("bench.py --config must be 1, 2 or 5")
+    """Rank r's shard: its own config-shaped set of partitions (weak scaling)."""
+    from cranesched_b200 import sharding
+    if args.config not in (1, 2, 5):
+        raise SystemExit("bench.py --config must be 1, 2 or 5")
+    return sharding.shard_workload(args.config, rank, int(os.environ.get("WORLD_SIZE", "1")), args.jobs, args.nodes)
 
 
 def workload_name(args):

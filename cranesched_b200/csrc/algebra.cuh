@@ -241,9 +241,11 @@ CRANE_HD bool feasible(const View& req, const Row& avail, const GresDict& d, Row
 //   seconds * (double(res.cpu) / double(total.cpu)), double(cpu_t) = raw/256.0.
 // Written with explicit rounding intrinsics so nvcc never contracts into FMA.
 CRANE_HD double cost_delta(int64_t seconds, int64_t res_cpu_raw, int64_t total_cpu_raw) {
+  // x / 256.0 is an exact power-of-two scaling, so it is written as a multiply
+  // (bit-identical, and one fp64 division instead of three)
 #if defined(__CUDA_ARCH__) || defined(CRANE_EMU)
-  double a = __ddiv_rn(__ll2double_rn(res_cpu_raw), 256.0);
-  double b = __ddiv_rn(__ll2double_rn(total_cpu_raw), 256.0);
+  double a = __dmul_rn(__ll2double_rn(res_cpu_raw), 0.00390625);
+  double b = __dmul_rn(__ll2double_rn(total_cpu_raw), 0.00390625);
   return __dmul_rn(__ll2double_rn(seconds), __ddiv_rn(a, b));
 #else
   double a = (double)res_cpu_raw / 256.0;

@@ -28,7 +28,7 @@ class CraneSchedError(RuntimeError):
 
 
 def load_library(path: str | None = None) -> C.CDLL:
-    path = path or LIB_PATH
+    path = path or os.environ.get("CRANE_SCHED_LIB") or LIB_PATH  # env override: A/B builds in tools/
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):

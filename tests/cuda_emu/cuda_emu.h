@@ -17,6 +17,8 @@
 
 #include <atomic>
 #include <barrier>
+#include <condition_variable>
+#include <mutex>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -52,7 +54,14 @@ struct WarpCtx {
   uint64_t slot[32];
   explicit WarpCtx(int n) : bar(n) {}
 };
+struct NamedBar {  // CUDA named barrier: completes when `n` threads have arrived (bar.sync or bar.arrive)
+  std::mutex m;
+  std::condition_variable cv;
+  unsigned count = 0;
+  unsigned long gen = 0;
+};
 struct BlockCtx {
+  NamedBar named[16];
   std::barrier<> bar;
   std::vector<std::unique_ptr<WarpCtx>> warps;
   std::vector<unsigned char> dyn_smem;
@@ -140,6 +149,18 @@ inline T exchange(T v, int src_lane) {
   T* name = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(emu::tctx.block->dyn_smem.data()) + 15) & ~uintptr_t(15))
 
 inline void __syncthreads() { emu::tctx.block->bar.arrive_and_wait(); }
+inline void emu_named_bar(int id, int n, bool wait) {
+  emu::NamedBar& b = emu::tctx.block->named[id];
+  std::unique_lock<std::mutex> lk(b.m);
+  const unsigned long g = b.gen;
+  if (++b.count == (unsigned)n) {
+    b.count = 0;
+    ++b.gen;
+    b.cv.notify_all();
+  } else if (wait) {
+    b.cv.wait(lk, [&] { return b.gen != g; });
+  }
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::tctx.warp->bar.arrive_and_wait(); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
