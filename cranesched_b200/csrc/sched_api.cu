@@ -381,7 +381,8 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
   h->have_lists_excl = pd->excl_off != nullptr;
   if (h->have_lists_incl) {
     for (uint32_t k = 0; k < pd->incl_off[N]; ++k)
-      if (pd->incl_nodes[k] >= h->n_nodes) return fail(h, CRANE_EINVAL, "pending: included node out of range");
+      if (pd->incl_nodes[k] >= h->n_nodes && pd->incl_nodes[k] != 0xFFFFFFFFu)  // 0xFFFFFFFF = a host the cluster does not know
+        return fail(h, CRANE_EINVAL, "pending: included node out of range");
     H2D(h->d_incl_off, pd->incl_off, N + 1);
     H2D(h->d_incl_nodes, pd->incl_nodes, pd->incl_off[N]);
   }

@@ -143,7 +143,8 @@ typedef struct crane_pending {
   const crane_res_view_t* req_node;  /* req_node_res_view                    */
   const crane_res_view_t* req_task;  /* req_task_res_view                    */
   const crane_res_view_t* req_total; /* req_total_res_view                   */
-  const uint32_t* incl_off;  /* [n+1] CSR of included_nodes, or NULL          */
+  const uint32_t* incl_off;  /* [n+1] CSR of included_nodes, or NULL; the index
+                                0xFFFFFFFF stands for a host unknown to the cluster */
   const uint32_t* incl_nodes;
   const uint32_t* excl_off;  /* [n+1] CSR of excluded_nodes, or NULL          */
   const uint32_t* excl_nodes;
