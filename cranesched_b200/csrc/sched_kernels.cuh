@@ -1164,6 +1164,7 @@ struct WorkerCtx {  // lives in shared memory; read-only after set-up
   const JobQ* jobs;
   const Row* classrow;
   uint32_t* label;
+  uint32_t* ok;      // [kBatch] verdicts of the batch being evaluated
   int64_t now, max_window;
   uint32_t base, max_jobs;
 };
@@ -1191,7 +1192,7 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
   const uint32_t K = jq.node_num;
   long long result = (kind == OP_EARLY) ? (long long)t0 : 0;
 #pragma unroll 1
-  for (uint32_t k = first; k < n; k += stride) {
+  for (uint32_t k = first; k < n; k += (batch == 2 ? 0x7fffffffu : stride)) {
     const uint32_t q = sm.list[k];
 #ifdef CRANE_EMU_DEBUG
     if (q > 60000) { fprintf(stderr, "worker_step: kind=%u n=%u first=%u stride=%u k=%u q=%u tid=%u\n", kind, n, first, stride, k, q, threadIdx.x); abort(); }
@@ -1227,6 +1228,17 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
         start = t;
         result = ok ? t : kInf;
       }
+    }
+    if (batch == 2) {
+      // task `first` of a batch of `stride` one-node jobs: publish the verdict, wait
+      // for the others, and commit only if every task before this one succeeded
+      if (lane == 0) cx.ok[first] = ok ? 1u : 0u;
+      __syncthreads();
+      uint32_t f = stride;
+      for (uint32_t i = 0; i < stride; ++i)
+        if (!cx.ok[i]) { f = i; break; }
+      ok = first < f;
+      result = (long long)f;
     }
     const bool do_update = ((kind == OP_NOW_K1 || kind == OP_BF_K1) && ok) || kind == OP_UPDATE_NOW || kind == OP_UPDATE_BF;
     if (do_update) {
@@ -1301,7 +1313,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   __shared__ Row s_classrow[kMaxClasses];
   __shared__ CommitCmd s_cmd;
   __shared__ BatchTask s_task[kBatch];
-  __shared__ int64_t s_tstart[kBatch];
+  __shared__ uint32_t s_ok[kBatch];
   __shared__ double s_undo[kBatch];
   __shared__ WorkerCtx s_cx;
   __shared__ long long s_res[32];   // per-worker result of a multi-warp step
@@ -1323,7 +1335,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   if (threadIdx.x == 0) {
     s_label = 0;
     s_cx.cl = a.cl; s_cx.tl = a.tl; s_cx.out = a.out; s_cx.sm = sm; s_cx.jobs = s_jobs; s_cx.classrow = s_classrow;
-    s_cx.label = &s_label; s_cx.now = a.now; s_cx.max_window = a.max_window; s_cx.base = base; s_cx.max_jobs = a.max_jobs;
+    s_cx.label = &s_label; s_cx.ok = s_ok; s_cx.now = a.now; s_cx.max_window = a.max_window; s_cx.base = base; s_cx.max_jobs = a.max_jobs;
     for (int s = 0; s < kRing; ++s) mbar_init(&s_bar[s], 1);
     fence_mbar_init();
   }
@@ -1359,11 +1371,12 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       const CommitCmd c = s_cmd;
       if (c.kind == OP_EXIT) break;
       long long r = 0;
-      if (c.kind == OP_BATCH_P || c.kind == OP_BATCH_C) {
+      if (c.kind == OP_BATCH_P) {
         if (wid < c.n) {  // task wid of the batch: node sm.list[wid], job in ring slot s_task[wid].slot
           const BatchTask t = s_task[wid];
-          const uint32_t k = c.kind == OP_BATCH_P ? (t.mode ? OP_EARLY : OP_TEST) : (t.mode ? OP_UPDATE_BF : OP_UPDATE_NOW);
-          r = worker_step(&s_cx, k, wid + 1, t.slot, c.kind == OP_BATCH_P ? s_cx.now : s_tstart[wid], wid, 0x7fffffffu, 1);
+          r = worker_step(&s_cx, t.mode ? OP_BF_K1 : OP_NOW_K1, wid + 1, t.slot, s_cx.now, wid, c.n, 2);
+        } else {
+          __syncthreads();  // the verdict barrier inside the batch step
         }
       } else if (c.kind == OP_TEST) {
         r = worker_step(&s_cx, c.kind, c.n, c.slot, c.t0, c.first + wid, 0x7fffffffu, 0);
@@ -1754,35 +1767,13 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
 
     bool single = nt == 0;
     if (nt) {
-      // evaluate all picks in parallel (no state change) ...
+      // the workers evaluate all picks in parallel (no state change), agree on the
+      // first failing one and commit the picks before it
       if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = nt; }
       __syncthreads();
-      {
-        const BatchTask t = s_task[0];
-        const long long r0 = worker_step(&s_cx, t.mode ? OP_EARLY : OP_TEST, 1, t.slot, a.now, 0, 0x7fffffffu, 1);
-        if (lane == 0) s_res[0] = r0;
-      }
+      const BatchTask t0 = s_task[0];
+      const uint32_t f = (uint32_t)worker_step(&s_cx, t0.mode ? OP_BF_K1 : OP_NOW_K1, 1, t0.slot, a.now, 0, nt, 2);
       __syncthreads();
-      PROF(9);
-      uint32_t f = nt;  // first pick that did not work out
-      for (uint32_t t = 0; t < nt; ++t) {
-        const long long r = s_res[t];
-        int64_t start = a.now;
-        bool ok;
-        if (s_task[t].mode == 0) ok = r != 0;
-        else { ok = r != kInf && r - a.now <= a.max_window; start = r; }  // JobScheduler.h:809
-        if (!ok) { f = t; break; }
-        if (lane == 0) s_tstart[t] = start;
-      }
-      // ... commit the good prefix in parallel
-      if (lane == 0) { s_cmd.kind = OP_BATCH_C; s_cmd.n = f; }
-      __syncthreads();
-      if (f > 0) {
-        const BatchTask t = s_task[0];
-        worker_step(&s_cx, t.mode ? OP_UPDATE_BF : OP_UPDATE_NOW, 1, t.slot, s_tstart[0], 0, 0x7fffffffu, 1);
-      }
-      __syncthreads();
-      PROF(10);
       PROF_CNT(13, f);
       PROF_CNT(14, 1);
       // roll back the re-keys of the picks that were not committed, last first
