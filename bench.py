@@ -85,6 +85,21 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_commit from the committed
+    `ncu --set full` capture (profiles/r01_ncu_k_commit_summary.csv), per launch."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_k_commit_summary.csv")
+    if not os.path.exists(p):
+        return None
+    tot = 0.0
+    for line in open(p):
+        f = line.strip().split(",")
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(f[2], 1.0)
+            tot += float(f[1]) * mult
+    return tot or None
+
+
 def algorithmic_bytes(cluster, pending, n_decided):
     """B_dec(j) = job_row + M_part(j) * node_row + out_row(j),
     job_row 64 B, node_row 48 B (24 B when the cluster has no gres), out_row
@@ -262,7 +277,8 @@ def main():
             "phases_ms": {k: round(float(v), 4) for k, v in timing_last.items() if k.endswith("_ms")},
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_commit", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic() if args.config == 2 and not args.jobs else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "per decision 64 B job row + M_part x %d B node row + 16 B + 32 B x node_num "
                                  "(SURVEY.md 8d); the job loop is a dependency chain, so the binding limit is "

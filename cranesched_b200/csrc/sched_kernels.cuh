@@ -1144,6 +1144,8 @@ enum : uint32_t {
   OP_EARLY = 3,      // workers: earliest fit >= t0 over their share of list[0..n)
   OP_UPDATE_NOW = 4, // workers: allocate against the window minimum and update their share
   OP_UPDATE_BF = 5,  // workers: allocate against res_total and update their share
+  OP_NOW_MULTI = 9,  // K <= warps: worker w tests list[w]; if all K pass, each updates its node
+  OP_BF_MULTI = 10,  // K <= warps: worker w iterates the common earliest start with the others, then updates
   OP_BATCH_P = 6,    // batch of one-node jobs: worker w evaluates task w (no state change)
   OP_BATCH_C = 7,    // ... worker w < n commits task w
   OP_EXIT = 8,
@@ -1165,9 +1167,28 @@ struct WorkerCtx {  // lives in shared memory; read-only after set-up
   const Row* classrow;
   uint32_t* label;
   uint32_t* ok;      // [kBatch] verdicts of the batch being evaluated
+  long long* tbuf;   // [2][32] per-iteration earliest fits of a multi-node job
   int64_t now, max_window;
   uint32_t base, max_jobs;
 };
+
+// barrier protocol of the fused multi-node steps for a warp that holds no node
+__device__ __noinline__ void multi_idle(const WorkerCtx* cxp, uint32_t kind, uint32_t n) {
+  const WorkerCtx& cx = *cxp;
+  if (kind == 9u) {  // OP_NOW_MULTI
+    __syncthreads();
+    return;
+  }
+  int64_t T0 = cx.now;  // OP_BF_MULTI
+  for (uint32_t it = 0;; ++it) {
+    const long long* buf = cx.tbuf + (it & 1u) * 32;
+    __syncthreads();
+    int64_t tmax = T0;
+    for (uint32_t i = 0; i < n; ++i) tmax = buf[i] > tmax ? buf[i] : tmax;
+    if (tmax == kInf || tmax == T0) break;
+    T0 = tmax;
+  }
+}
 
 // The per-node work of one command on this warp's share of sm.list[first, n)
 // with the given stride: open the node's timeline once, then — depending on the
@@ -1192,14 +1213,14 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
   const uint32_t K = jq.node_num;
   long long result = (kind == OP_EARLY) ? (long long)t0 : 0;
 #pragma unroll 1
-  for (uint32_t k = first; k < n; k += (batch == 2 ? 0x7fffffffu : stride)) {
+  for (uint32_t k = first; k < n; k += ((batch == 2 || kind == OP_NOW_MULTI || kind == OP_BF_MULTI) ? 0x7fffffffu : stride)) {
     const uint32_t q = sm.list[k];
 #ifdef CRANE_EMU_DEBUG
     if (q > 60000) { fprintf(stderr, "worker_step: kind=%u n=%u first=%u stride=%u k=%u q=%u tid=%u\n", kind, n, first, stride, k, q, threadIdx.x); abort(); }
 #endif
     const uint32_t g = cx.base + q;
     const uint32_t ns = sm.nseg[q];
-    const bool from_window = kind == OP_NOW_K1 || kind == OP_TEST || kind == OP_UPDATE_NOW;
+    const bool from_window = kind == OP_NOW_K1 || kind == OP_TEST || kind == OP_UPDATE_NOW || kind == OP_NOW_MULTI;
     const Row a0 = cx.tl.avail0[g];
     Row tot;
     row_zero(tot);
@@ -1219,6 +1240,37 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
     int64_t start = t0;
     if (kind == OP_NOW_K1 || kind == OP_TEST) result = ok ? 1 : 0;
     if (kind == OP_NOW_K1) start = now;
+    if (kind == OP_NOW_MULTI) {
+      // all n nodes must pass (they are the first n candidates in cost order);
+      // the verdict barrier is shared with the idle warps (multi_idle)
+      if (lane == 0) cx.ok[first] = ok ? 1u : 0u;
+      __syncthreads();
+      bool all = true;
+      for (uint32_t i = 0; i < n; ++i) all = all && cx.ok[i] != 0;
+      ok = all;
+      result = all ? 1 : 0;
+      start = now;
+    }
+    if (kind == OP_BF_MULTI) {
+      // common earliest start of the n chosen nodes: every warp keeps its node's
+      // timeline in registers and iterates T <- max over nodes of the earliest
+      // fit >= T to the fixed point (JobScheduler.h:806-849), one barrier a round
+      int64_t T0 = now;
+      ok = false;
+      for (uint32_t it = 0;; ++it) {
+        const int64_t t = ns <= 64 ? node_earliest(nr, alloc, T0, limit) : node_earliest_big(cx.tl, g, ns, alloc, T0, limit);
+        long long* buf = cx.tbuf + (it & 1u) * 32;
+        if (lane == 0) buf[first] = t;
+        __syncthreads();
+        int64_t tmax = T0;
+        for (uint32_t i = 0; i < n; ++i) tmax = buf[i] > tmax ? buf[i] : tmax;
+        if (tmax == kInf) break;
+        if (tmax == T0) { ok = T0 - now <= cx.max_window; break; }  // JobScheduler.h:809
+        T0 = tmax;
+      }
+      start = T0;
+      result = ok ? T0 : kInf;
+    }
     if (kind == OP_BF_K1 || kind == OP_EARLY) {
       const int64_t t = ns <= 64 ? node_earliest(nr, alloc, t0, limit) : node_earliest_big(cx.tl, g, ns, alloc, t0, limit);
       if (kind == OP_EARLY) {
@@ -1240,7 +1292,8 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
       ok = first < f;
       result = (long long)f;
     }
-    const bool do_update = ((kind == OP_NOW_K1 || kind == OP_BF_K1) && ok) || kind == OP_UPDATE_NOW || kind == OP_UPDATE_BF;
+    const bool do_update = ((kind == OP_NOW_K1 || kind == OP_BF_K1 || kind == OP_NOW_MULTI || kind == OP_BF_MULTI) && ok) ||
+                           kind == OP_UPDATE_NOW || kind == OP_UPDATE_BF;
     if (do_update) {
       const int64_t end = start + limit;
       Row seg0;
@@ -1313,7 +1366,8 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   __shared__ Row s_classrow[kMaxClasses];
   __shared__ CommitCmd s_cmd;
   __shared__ BatchTask s_task[kBatch];
-  __shared__ uint32_t s_ok[kBatch];
+  __shared__ uint32_t s_ok[32];
+  __shared__ long long s_tbuf[2][32];
   __shared__ double s_undo[kBatch];
   __shared__ WorkerCtx s_cx;
   __shared__ long long s_res[32];   // per-worker result of a multi-warp step
@@ -1335,7 +1389,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   if (threadIdx.x == 0) {
     s_label = 0;
     s_cx.cl = a.cl; s_cx.tl = a.tl; s_cx.out = a.out; s_cx.sm = sm; s_cx.jobs = s_jobs; s_cx.classrow = s_classrow;
-    s_cx.label = &s_label; s_cx.ok = s_ok; s_cx.now = a.now; s_cx.max_window = a.max_window; s_cx.base = base; s_cx.max_jobs = a.max_jobs;
+    s_cx.label = &s_label; s_cx.ok = s_ok; s_cx.tbuf = &s_tbuf[0][0]; s_cx.now = a.now; s_cx.max_window = a.max_window; s_cx.base = base; s_cx.max_jobs = a.max_jobs;
     for (int s = 0; s < kRing; ++s) mbar_init(&s_bar[s], 1);
     fence_mbar_init();
   }
@@ -1378,6 +1432,9 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         } else {
           __syncthreads();  // the verdict barrier inside the batch step
         }
+      } else if (c.kind == OP_NOW_MULTI || c.kind == OP_BF_MULTI) {
+        if (wid < c.n) r = worker_step(&s_cx, c.kind, c.n, c.slot, c.t0, wid, 1, 0);
+        else multi_idle(&s_cx, c.kind, c.n);
       } else if (c.kind == OP_TEST) {
         r = worker_step(&s_cx, c.kind, c.n, c.slot, c.t0, c.first + wid, 0x7fffffffu, 0);
       } else {
@@ -1451,10 +1508,92 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     bool placed = false;
     uint32_t nsel = 0;  // nodes selected for an immediate start (in sm.list[0..nsel))
 
+    // ---- multi-node job that fits the CTA (K <= warps): fused steps ---------
+    // Immediate start: the first K pre-filter candidates in cost order are
+    // tested in parallel; if all pass they are the reference's pick and are
+    // updated in the same step. With fewer than K candidates the job can only
+    // be backfilled: the first K capable nodes iterate their common earliest
+    // start with their timelines resident in registers.
+    bool handled = false;
+    auto fused = [&](uint32_t kind) -> long long {
+      if (lane == 0) { s_cmd.kind = kind; s_cmd.n = K; s_cmd.slot = slot; s_cmd.first = 0; s_cmd.t0 = a.now; }
+      __syncthreads();
+      const long long r = worker_step(&s_cx, kind, K, slot, a.now, 0, 1, 0);
+      __syncthreads();
+      return r;
+    };
+    if (K > 1 && K <= nw && K <= mp) {
+      uint32_t c = 0;  // pre-filter candidates found, in cost order, in sm.list[0..c)
+      for (uint32_t b = first_bucket; c < K;) {
+        // next bucket whose bounds admit a candidate (32 buckets per probe)
+        uint32_t nbk = 0xffffffffu;
+        for (uint32_t b0 = b; b0 < sm.nb && nbk == 0xffffffffu; b0 += 32) {
+          const uint32_t bb = b0 + lane;
+          bool prom = false;
+          if (bb < sm.nb && sm.bcnt[bb])
+            prom = exclusive || ((jflags & 2u) ? (sm.bmax_cpug[bb] >= req_cpu && gres_counts_ok(sm.bmax_g[bb], spec8, gnames, jq.name_need))
+                                               : sm.bmax_cpu[bb] >= req_cpu);
+          const unsigned pm = __ballot_sync(kFullMask, prom);
+          if (pm) nbk = b0 + (uint32_t)__ffs((int)pm) - 1u;
+        }
+        if (nbk == 0xffffffffu) break;
+        b = nbk;
+        const uint32_t n = sm.bcnt[b];
+        const uint16_t* B = sm.bk + (size_t)b * kBucket;
+        for (uint32_t h = 0; h < 2 && c < K; ++h) {
+          const uint32_t idx = lane + 32 * h;
+          bool cand = false;
+          uint32_t q = 0;
+          if (idx < n) {
+            q = B[idx];
+            cand = ((bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
+            if (cand && !exclusive)
+              cand = sm.cpu0[q] >= req_cpu && (!(jflags & 2u) || gres_counts_ok(sm.gcnt[q], spec8, gnames, jq.name_need));
+          }
+          const unsigned cm = __ballot_sync(kFullMask, cand);
+          const uint32_t rank = c + (uint32_t)__popc(cm & ((1u << lane) - 1u));
+          if (cand && rank < K) sm.list[rank] = (uint16_t)q;
+          c += (uint32_t)__popc(cm);
+        }
+        ++b;
+      }
+      __syncwarp();
+      if (c >= K) {
+        if (fused(OP_NOW_MULTI)) { placed = true; start_time = a.now; handled = true; nsel = K; }
+        // else: some candidate failed the exact test -> the general path below
+      } else {
+        // fewer than K candidates: no immediate start is possible
+        handled = true;
+        uint32_t cum = 0;
+        for (uint32_t b = first_bucket; b < sm.nb && cum < K; ++b) {
+          const uint16_t* B = sm.bk + (size_t)b * kBucket;
+          const uint32_t n = sm.bcnt[b];
+          for (uint32_t h = 0; h < 2 && cum < K; ++h) {
+            const uint32_t idx = lane + 32 * h;
+            bool cap = false;
+            uint32_t q = 0;
+            if (idx < n) {
+              q = B[idx];
+              cap = ((bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
+            }
+            const unsigned m = __ballot_sync(kFullMask, cap);
+            const uint32_t rank = cum + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            if (cap && rank < K) sm.list[rank] = (uint16_t)q;
+            cum += (uint32_t)__popc(m);
+          }
+        }
+        __syncwarp();
+        if (cum >= K) {
+          const long long t = fused(OP_BF_MULTI);
+          if (t != kInf) { placed = true; start_time = t; }
+        }
+      }
+    }
+
     // ---- immediate start: walk the buckets in cost order -------------------
     // (JobScheduler.cpp:5224-5336). A bucket whose bounds cannot satisfy the
     // pre-filter holds no candidate and is skipped.
-    if (K <= mp) {
+    if (K <= mp && !handled) {
       uint32_t b = first_bucket;
       while (nsel < K) {
         // next bucket that may hold a candidate
@@ -1559,7 +1698,9 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     }
     PROF(2);
 
-    if (nsel >= K && K <= mp) {
+    if (handled) {
+      // the fused step did everything
+    } else if (nsel >= K && K <= mp) {
       placed = true;
       start_time = a.now;
       PROF_CNT(10, 1);
