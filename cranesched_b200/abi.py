@@ -28,12 +28,24 @@ REASON_PRIORITY = 1
 REASON_RESOURCE = 2
 REASON_RESERVED = 3
 REASON_PART_NOT_FOUND = 4
+REASON_QOS_CPU = 16
+REASON_QOS_JOBS = 17
+REASON_QOS_WALL = 18
+REASON_QOS_MEM = 19
+REASON_QOS_GRES = 20
+REASON_QOS_INVALID = 21
 REASON_STR = {
     0: "",
     1: "Priority",
     2: "Resource",
     3: "Resource Reserved",
     4: "Partition Not Found",
+    16: "QosCpuResourceLimit",
+    17: "QosJobsResourceLimit",
+    18: "QosWallTimeLimit",
+    19: "QosMemResourceLimit",
+    20: "QosGresResourceLimit",
+    21: "InvalidQOS",
 }
 
 # ResourceInNodeV3 as bit masks (PublicHeader.h:562-615) -- 72 bytes
@@ -57,6 +69,29 @@ RES_VIEW = np.dtype(
     ]
 )
 assert RES_IN_NODE.itemsize == 72 and RES_VIEW.itemsize == 56
+# crane_tres_limit_t: a ResourceView limit of struct Qos (Account/AccountDefs.h:27-50) -- 64 bytes
+TRES_LIMIT = np.dtype(
+    [
+        ("view", RES_VIEW),
+        ("gres_name_present", "u1"),
+        ("gres_spec_present", "u1"),
+        ("pad", "u1", (6,)),
+    ]
+)
+# crane_meta_resource_t: MetaResource (Accounting/AccountMetaContainer.h:30-47) -- 104 bytes
+META_RESOURCE = np.dtype(
+    [
+        ("cpu_raw", "<i8"),
+        ("mem", "<u8"),
+        ("mem_sw", "<u8"),
+        ("gres_total", "<u4", (GRES_NAMES,)),
+        ("gres_spec", "<u4", (GRES_ENTRIES,)),
+        ("jobs_count", "<u4"),
+        ("pad", "<u4"),
+        ("wall_time", "<i8"),
+    ]
+)
+assert TRES_LIMIT.itemsize == 64 and META_RESOURCE.itemsize == 104
 
 _p = C.c_void_p
 
@@ -147,6 +182,28 @@ class PlacementsC(C.Structure):
         ("alloc_node", _p),
         ("alloc_ntasks", _p),
         ("alloc_res", _p),
+    ]
+
+
+class QosTableC(C.Structure):
+    _fields_ = [
+        ("n_qos", C.c_uint32),
+        ("n_users", C.c_uint32),
+        ("n_accounts", C.c_uint32),
+        ("valid", _p),
+        ("max_jobs_per_user", _p),
+        ("max_jobs_per_account", _p),
+        ("max_jobs", _p),
+        ("max_cpus_per_user_raw", _p),
+        ("max_wall", _p),
+        ("max_tres_per_user", _p),
+        ("max_tres_per_account", _p),
+        ("max_tres", _p),
+        ("chain_off", _p),
+        ("chain_acct", _p),
+        ("user_usage", _p),
+        ("account_usage", _p),
+        ("qos_usage", _p),
     ]
 
 
@@ -411,6 +468,72 @@ class Placements:
                 out.append(f"{f}: {len(idx)} mismatches, first at {idx[:5].tolist()}: "
                            f"{getattr(self, f)[idx[0]]} vs {getattr(other, f)[idx[0]]}")
         return out
+
+
+@dataclass
+class QosTable:
+    """struct Qos limits (Account/AccountDefs.h:27-50), the pending jobs' account
+    chains and the usage maps of AccountMetaContainer (m_user_meta_map_,
+    m_account_meta_map_, m_qos_meta_map_) as dense tables."""
+
+    n_users: int
+    n_accounts: int
+    valid: np.ndarray
+    max_jobs_per_user: np.ndarray
+    max_jobs_per_account: np.ndarray
+    max_jobs: np.ndarray
+    max_cpus_per_user_raw: np.ndarray
+    max_wall: np.ndarray
+    max_tres_per_user: np.ndarray
+    max_tres_per_account: np.ndarray
+    max_tres: np.ndarray
+    chain_off: np.ndarray
+    chain_acct: np.ndarray
+    user_usage: np.ndarray | None = None
+    account_usage: np.ndarray | None = None
+    qos_usage: np.ndarray | None = None
+
+    def __post_init__(self):
+        q = len(self.valid)
+        self.valid = _arr(self.valid, np.uint8, q)
+        self.max_jobs_per_user = _arr(self.max_jobs_per_user, np.uint32, q)
+        self.max_jobs_per_account = _arr(self.max_jobs_per_account, np.uint32, q)
+        self.max_jobs = _arr(self.max_jobs, np.uint32, q)
+        self.max_cpus_per_user_raw = _arr(self.max_cpus_per_user_raw, np.int64, q)
+        self.max_wall = _arr(self.max_wall, np.int64, q)
+        self.max_tres_per_user = _arr(self.max_tres_per_user, TRES_LIMIT, q)
+        self.max_tres_per_account = _arr(self.max_tres_per_account, TRES_LIMIT, q)
+        self.max_tres = _arr(self.max_tres, TRES_LIMIT, q)
+        self.chain_off = _arr(self.chain_off, np.uint32)
+        self.chain_acct = _arr(self.chain_acct, np.uint32)
+        if self.user_usage is None:
+            self.user_usage = np.zeros(self.n_users * q, META_RESOURCE)
+        if self.account_usage is None:
+            self.account_usage = np.zeros(self.n_accounts * q, META_RESOURCE)
+        if self.qos_usage is None:
+            self.qos_usage = np.zeros(q, META_RESOURCE)
+        self.user_usage = _arr(self.user_usage, META_RESOURCE, self.n_users * q)
+        self.account_usage = _arr(self.account_usage, META_RESOURCE, self.n_accounts * q)
+        self.qos_usage = _arr(self.qos_usage, META_RESOURCE, q)
+
+    @property
+    def n_qos(self):
+        return len(self.valid)
+
+    def copy(self) -> "QosTable":
+        import copy
+
+        return copy.deepcopy(self)
+
+    def as_c(self) -> QosTableC:
+        return QosTableC(
+            self.n_qos, self.n_users, self.n_accounts, _ptr(self.valid),
+            _ptr(self.max_jobs_per_user), _ptr(self.max_jobs_per_account), _ptr(self.max_jobs),
+            _ptr(self.max_cpus_per_user_raw), _ptr(self.max_wall), _ptr(self.max_tres_per_user),
+            _ptr(self.max_tres_per_account), _ptr(self.max_tres), _ptr(self.chain_off),
+            _ptr(self.chain_acct), _ptr(self.user_usage), _ptr(self.account_usage),
+            _ptr(self.qos_usage),
+        )
 
 
 def _pinned_empty(shape, dt):

@@ -25,6 +25,7 @@
 
 #include "../../include/crane_sched.h"
 #include "sched_kernels.cuh"
+#include "qos_kernels.cuh"
 
 using namespace crane;
 
@@ -114,6 +115,13 @@ struct crane_sched {
   DBuf<uint32_t> d_out_nalloc, d_out_node, d_out_ntasks;
   DBuf<Row> d_out_res;
   bool uploaded = false, ran = false;
+  // QoS post-filter (R12)
+  bool have_qos_cols = false;
+  DBuf<uint32_t> d_qos, d_user, d_q_u32, d_q_chain_off, d_q_chain;
+  DBuf<int64_t> d_q_i64;
+  DBuf<uint8_t> d_q_valid;
+  DBuf<crane_tres_limit_t> d_q_tres;
+  DBuf<crane_meta_resource_t> d_q_user_usage, d_q_acct_usage, d_q_qos_usage;
 };
 
 namespace {
@@ -218,7 +226,8 @@ void crane_sched_destroy(crane_sched_t* h) {
   REL(d_acc_present); REL(d_bounds); REL(d_acc_service); REL(d_prio); REL(d_keys_a); REL(d_keys_b); REL(d_vals_a);
   REL(d_vals_b); REL(d_hist); REL(d_part_count); REL(d_part_job_off); REL(d_bitmap); REL(d_jobq); REL(d_reason);
   REL(d_out_prio); REL(d_out_start); REL(d_out_end); REL(d_out_nalloc); REL(d_out_node); REL(d_out_ntasks);
-  REL(d_out_res); REL(d_prof);
+  REL(d_out_res); REL(d_prof); REL(d_qos); REL(d_user); REL(d_q_u32); REL(d_q_chain_off); REL(d_q_chain);
+  REL(d_q_i64); REL(d_q_valid); REL(d_q_tres); REL(d_q_user_usage); REL(d_q_acct_usage); REL(d_q_qos_usage);
 #undef REL
   for (auto& e : h->ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -371,6 +380,11 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
   H2D(h->d_part_prio, pd->partition_priority, N);
   H2D(h->d_qos_prio, pd->qos_priority, N);
   H2D(h->d_account, pd->account, N);
+  h->have_qos_cols = pd->qos != nullptr && pd->user != nullptr;
+  if (h->have_qos_cols) {
+    H2D(h->d_qos, pd->qos, N);
+    H2D(h->d_user, pd->user, N);
+  }
   h->have_mandated = pd->mandated_priority != nullptr;
   if (h->have_mandated) H2D(h->d_mandated, pd->mandated_priority, N);
   H2D(h->d_req_node, reinterpret_cast<const View*>(pd->req_node), N);
@@ -739,6 +753,79 @@ int crane_sched_debug_profile(crane_sched_t* h, unsigned long long* dst, size_t 
   size_t n = std::min(cap, (size_t)h->n_parts * 16);
   CU(cudaStreamSynchronize(h->stream));
   if (n) CU(cudaMemcpy(dst, h->d_prof.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return CRANE_OK;
+}
+
+int crane_sched_qos_filter(crane_sched_t* h, const crane_qos_table_t* qt, uint8_t* reason) {
+  if (!h || !qt || !reason) return CRANE_EINVAL;
+  if (!h->ran) return fail(h, CRANE_EINVAL, "qos_filter: run first");
+  if (!h->have_qos_cols) return fail(h, CRANE_EINVAL, "qos_filter: pending.qos / pending.user were not uploaded");
+  CU(cudaSetDevice(h->device));
+  const uint32_t N = h->n_pending, Q = qt->n_qos, U = qt->n_users, A = qt->n_accounts;
+  if (Q == 0 || Q > 65535) return fail(h, CRANE_EINVAL, "qos_filter: n_qos out of range");
+  if (!qt->valid || !qt->max_jobs_per_user || !qt->max_jobs_per_account || !qt->max_jobs ||
+      !qt->max_cpus_per_user_raw || !qt->max_wall || !qt->max_tres_per_user || !qt->max_tres_per_account ||
+      !qt->max_tres || !qt->chain_off || !qt->user_usage || !qt->qos_usage || (A && !qt->account_usage))
+    return fail(h, CRANE_EINVAL, "qos_filter: null column");
+  // the levels of one job are checked lane-parallel: user + chain + qos <= 32
+  // lanes, and one usage entry per lane (a chain never repeats an account)
+  for (uint32_t i = 0; i < N; ++i) {
+    const uint32_t c0 = qt->chain_off[i], c1 = qt->chain_off[i + 1];
+    if (c1 < c0 || c1 - c0 > 30) return fail(h, CRANE_ENOSYS, "qos_filter: pending[%u]: account chain longer than 30", i);
+    for (uint32_t a = c0; a < c1; ++a) {
+      if (qt->chain_acct[a] >= A) return fail(h, CRANE_EINVAL, "qos_filter: pending[%u]: account out of range", i);
+      for (uint32_t b = c0; b < a; ++b)
+        if (qt->chain_acct[a] == qt->chain_acct[b])
+          return fail(h, CRANE_EINVAL, "qos_filter: pending[%u]: account repeated in chain", i);
+    }
+  }
+  // user ids are checked on the device side of the table: against n_users here
+  // (pending.user was validated only for presence at upload)
+  {
+    std::vector<uint32_t> users(N);
+    if (N) CU(cudaMemcpyAsync(users.data(), h->d_user.p, (size_t)N * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (uint32_t i = 0; i < N; ++i)
+      if (users[i] >= U) return fail(h, CRANE_EINVAL, "qos_filter: pending[%u]: user out of range", i);
+  }
+  std::vector<uint32_t> u32(3 * (size_t)Q);
+  std::vector<int64_t> i64(2 * (size_t)Q);
+  std::vector<crane_tres_limit_t> tres(3 * (size_t)Q);
+  for (uint32_t k = 0; k < Q; ++k) {
+    u32[k] = qt->max_jobs_per_user[k]; u32[Q + k] = qt->max_jobs_per_account[k]; u32[2 * Q + k] = qt->max_jobs[k];
+    i64[k] = qt->max_cpus_per_user_raw[k]; i64[Q + k] = qt->max_wall[k];
+    tres[k] = qt->max_tres_per_user[k]; tres[Q + k] = qt->max_tres_per_account[k]; tres[2 * Q + k] = qt->max_tres[k];
+  }
+  H2D(h->d_q_u32, u32.data(), u32.size());
+  H2D(h->d_q_i64, i64.data(), i64.size());
+  H2D(h->d_q_tres, tres.data(), tres.size());
+  H2D(h->d_q_valid, qt->valid, Q);
+  H2D(h->d_q_chain_off, qt->chain_off, N + 1);
+  H2D(h->d_q_chain, qt->chain_acct, qt->chain_off[N]);
+  H2D(h->d_q_user_usage, qt->user_usage, (size_t)U * Q);
+  H2D(h->d_q_acct_usage, qt->account_usage, (size_t)A * Q);
+  H2D(h->d_q_qos_usage, qt->qos_usage, Q);
+  QosDev q{};
+  q.n_qos = Q; q.n_users = U; q.n_accounts = A; q.n_jobs = N;
+  q.valid = h->d_q_valid.p;
+  q.max_jobs_per_user = h->d_q_u32.p; q.max_jobs_per_account = h->d_q_u32.p + Q; q.max_jobs = h->d_q_u32.p + 2 * Q;
+  q.max_cpus_per_user_raw = h->d_q_i64.p; q.max_wall = h->d_q_i64.p + Q;
+  q.tres_user = h->d_q_tres.p; q.tres_account = h->d_q_tres.p + Q; q.tres_qos = h->d_q_tres.p + 2 * Q;
+  q.chain_off = h->d_q_chain_off.p; q.chain_acct = h->d_q_chain.p;
+  q.user_usage = h->d_q_user_usage.p; q.account_usage = h->d_q_acct_usage.p; q.qos_usage = h->d_q_qos_usage.p;
+  q.qos = h->d_qos.p; q.user = h->d_user.p; q.time_limit = h->d_time_limit.p;
+  q.n_alloc = h->d_out_nalloc.p; q.alloc_off = h->d_alloc_off.p; q.alloc_res = h->d_out_res.p;
+  q.reason = h->d_reason.p;
+  if (N) {
+    CRANE_LAUNCH(k_qos_filter, Q + 1, 32, 0, h->stream, q, h->dict);
+    CU(cudaGetLastError());
+    h->timing.kernel_launches += 1;
+  }
+  if (N) CU(cudaMemcpyAsync(reason, h->d_reason.p, N, cudaMemcpyDeviceToHost, h->stream));
+  if ((size_t)U * Q) CU(cudaMemcpyAsync(qt->user_usage, h->d_q_user_usage.p, (size_t)U * Q * sizeof(crane_meta_resource_t), cudaMemcpyDeviceToHost, h->stream));
+  if ((size_t)A * Q) CU(cudaMemcpyAsync(qt->account_usage, h->d_q_acct_usage.p, (size_t)A * Q * sizeof(crane_meta_resource_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(qt->qos_usage, h->d_q_qos_usage.p, (size_t)Q * sizeof(crane_meta_resource_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return CRANE_OK;
 }
 

@@ -57,6 +57,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.crane_sched_sync.argtypes = [C.c_void_p, P(C.c_float)]
     lib.crane_sched_get_timing.restype = C.c_int
     lib.crane_sched_get_timing.argtypes = [C.c_void_p, P(abi.TimingC)]
+    lib.crane_sched_qos_filter.restype = C.c_int
+    lib.crane_sched_qos_filter.argtypes = [C.c_void_p, P(abi.QosTableC), C.c_void_p]
     lib.crane_sched_debug_bitmap.restype = C.c_int
     lib.crane_sched_debug_bitmap.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_uint32), P(C.c_uint32)]
     lib.crane_sched_debug_profile.restype = C.c_int
@@ -68,6 +70,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 EXPORTS = ("crane_sched_create", "crane_sched_destroy", "crane_sched_last_error",
            "crane_sched_set_cluster", "crane_sched_node_select", "crane_sched_upload",
            "crane_sched_run", "crane_sched_fetch", "crane_sched_sync", "crane_sched_get_timing",
+           "crane_sched_qos_filter",
            "crane_sched_debug_bitmap", "crane_sched_debug_profile")
 
 
@@ -131,6 +134,13 @@ class GpuScheduler:
         c_out = out.as_c()
         self._check(self._lib.crane_sched_fetch(self._h, C.byref(c_out)))
         return out
+
+    def qos_filter(self, qos: abi.QosTable, reason: np.ndarray) -> np.ndarray:
+        """CheckAndMallocQosResource pass of the commit loop (JobScheduler.cpp:1262)
+        over the placements of the last run; updates `reason` and qos.*_usage."""
+        c_q = qos.as_c()
+        self._check(self._lib.crane_sched_qos_filter(self._h, C.byref(c_q), reason.ctypes.data))
+        return reason
 
     def timing(self) -> dict:
         t = abi.TimingC()

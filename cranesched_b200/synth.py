@@ -415,4 +415,69 @@ def random_case(seed, n_jobs=300, n_nodes=48, n_parts=3, n_running=40, fifo=Fals
     return cfg, cluster, running, pend, NOW
 
 
+def random_qos(seed, cluster, pend, tight=1.0, n_parents=4, invalid_frac=0.1):
+    """QoS limits + account chains + (partly pre-filled) usage for a pending table
+    (config 3's QoS filter). Accounts 0..A-1 are the leaves the
+    jobs name; each has a parent A + a % n_parents and all share the root; a
+    job's chain is [leaf, parent, root]. `tight` scales the limits: ~1 makes every
+    reason code occur, large values let everything through."""
+    from .abi import META_RESOURCE, TRES_LIMIT, QosTable
+
+    rng = np.random.default_rng(1000 + seed)
+    n = pend.n
+    n_qos = int(pend.qos.max()) + 1 if n else 1
+    n_users = int(pend.user.max()) + 1 if n else 1
+    leaves = int(pend.account.max()) + 1 if n else 1
+    n_accounts = leaves + n_parents + 1
+    chain_off = (np.arange(n + 1, dtype=np.uint32) * 3).astype(np.uint32)
+    chain = np.empty((n, 3), np.uint32)
+    chain[:, 0] = pend.account
+    chain[:, 1] = leaves + pend.account % n_parents
+    chain[:, 2] = leaves + n_parents
+    # some jobs with a shorter / empty chain
+    short = rng.random(n) < 0.1
+    lens = np.where(short, rng.integers(0, 3, n), 3).astype(np.uint32)
+    chain_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    chain_acct = np.concatenate([chain[i, :lens[i]] for i in range(n)]) if n else np.zeros(0, np.uint32)
+    per_q = max(1, n // n_qos)
+    big = np.iinfo(np.int64).max // 4
+
+    def lim(scale_cpu, scale_gres):
+        t = np.zeros(n_qos, TRES_LIMIT)
+        t["view"]["cpu_raw"] = np.where(rng.random(n_qos) < 0.3, big, (rng.integers(8, 64, n_qos) * 256 * scale_cpu * tight).astype(np.int64))
+        t["view"]["mem"] = np.where(rng.random(n_qos) < 0.3, np.uint64(1) << np.uint64(62),
+                                    (rng.integers(32, 256, n_qos) * scale_cpu * tight).astype(np.uint64) << np.uint64(30))
+        t["view"]["mem_sw"] = 0
+        t["gres_name_present"] = rng.integers(0, 4, n_qos)
+        t["gres_spec_present"] = rng.integers(0, 1 << max(cluster.n_gres_entries, 1), n_qos)
+        t["view"]["gres_total"] = np.minimum(65535, rng.integers(1, 16, (n_qos, 8)) * scale_gres * tight).astype(np.uint16)
+        t["view"]["gres_spec"] = np.minimum(65535, rng.integers(1, 12, (n_qos, GRES_ENTRIES)) * scale_gres * tight).astype(np.uint16)
+        return t
+
+    q = QosTable(
+        n_users=n_users, n_accounts=n_accounts,
+        valid=(rng.random(n_qos) >= invalid_frac).astype(np.uint8),
+        max_jobs_per_user=np.minimum(2**31, rng.integers(1, 6, n_qos) * tight).astype(np.uint32),
+        max_jobs_per_account=np.minimum(2**31, rng.integers(4, 24, n_qos) * tight).astype(np.uint32),
+        max_jobs=np.minimum(2**31, rng.integers(per_q // 8 + 1, per_q + 2, n_qos) * tight).astype(np.uint32),
+        max_cpus_per_user_raw=np.minimum(big, rng.integers(16, 128, n_qos) * 256 * tight).astype(np.int64),
+        max_wall=np.where(rng.random(n_qos) < 0.4, 0, (rng.integers(4, 64, n_qos) * 3600 * tight)).astype(np.int64),
+        max_tres_per_user=lim(1, 1), max_tres_per_account=lim(4, 3), max_tres=lim(16, 8),
+        chain_off=chain_off, chain_acct=chain_acct,
+    )
+    # usage left behind by jobs that are already running
+    for arr, p in ((q.user_usage, 0.15), (q.account_usage, 0.3), (q.qos_usage, 0.5)):
+        m = rng.random(len(arr)) < p
+        k = int(m.sum())
+        arr["cpu_raw"][m] = rng.integers(0, 16, k) * 256
+        arr["mem"][m] = rng.integers(0, 32, k).astype(np.uint64) << np.uint64(30)
+        arr["jobs_count"][m] = rng.integers(0, 3, k)
+        arr["wall_time"][m] = rng.integers(0, 7200, k)
+        for e in range(cluster.n_gres_entries):
+            c = rng.integers(0, 3, k).astype(np.uint32)
+            arr["gres_spec"][m, e] = c
+            arr["gres_total"][m, cluster.gres_entry_name[e]] += c
+    return q
+
+
 CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5}

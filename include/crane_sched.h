@@ -158,6 +158,13 @@ enum {
   CRANE_REASON_RESOURCE = 2,       /* "Resource"                              */
   CRANE_REASON_RESERVED = 3,       /* "Resource Reserved"                     */
   CRANE_REASON_PART_NOT_FOUND = 4, /* "Partition Not Found"                   */
+  /* written by crane_sched_qos_filter (Accounting/AccountMetaContainer.cpp:382-531) */
+  CRANE_REASON_QOS_CPU = 16,       /* "QosCpuResourceLimit"                   */
+  CRANE_REASON_QOS_JOBS = 17,      /* "QosJobsResourceLimit"                  */
+  CRANE_REASON_QOS_WALL = 18,      /* "QosWallTimeLimit"                      */
+  CRANE_REASON_QOS_MEM = 19,       /* "QosMemResourceLimit"                   */
+  CRANE_REASON_QOS_GRES = 20,      /* "QosGresResourceLimit"                  */
+  CRANE_REASON_QOS_INVALID = 21,   /* "InvalidQOS"                            */
 };
 
 /* The fields NodeSelect writes into PdJobInScheduler (JobScheduler.h:116-132).
@@ -229,6 +236,62 @@ int crane_sched_fetch(crane_sched_t* h, crane_placements_t* out);
 int crane_sched_sync(crane_sched_t* h, float* run_ms);
 
 int crane_sched_get_timing(const crane_sched_t* h, crane_sched_timing_t* t);
+
+/* ---- QoS post-filter (R12) ------------------------------------------------ */
+/* A ResourceView limit of struct Qos (Account/AccountDefs.h:27-50): max_tres,
+ * max_tres_per_user, max_tres_per_account. A gres name / type that is absent
+ * from the limit map is "unlimited"; presence is carried by the two masks
+ * (bit g = name g present, bit e = dictionary entry e present in `specified`). */
+typedef struct crane_tres_limit {
+  crane_res_view_t view;
+  uint8_t gres_name_present;
+  uint8_t gres_spec_present;
+  uint8_t pad[6];
+} crane_tres_limit_t;
+
+/* MetaResource (Accounting/AccountMetaContainer.h:30-47): running usage of one
+ * (user,qos), (account,qos) or qos. */
+typedef struct crane_meta_resource {
+  int64_t cpu_raw;
+  uint64_t mem;
+  uint64_t mem_sw;
+  uint32_t gres_total[CRANE_GRES_NAMES];
+  uint32_t gres_spec[CRANE_GRES_ENTRIES];
+  uint32_t jobs_count;
+  uint32_t pad;
+  int64_t wall_time;
+} crane_meta_resource_t;
+
+typedef struct crane_qos_table {
+  uint32_t n_qos, n_users, n_accounts;
+  /* limits, indexed by qos id (struct Qos, AccountDefs.h:27-50) */
+  const uint8_t* valid;                 /* 0 -> "InvalidQOS" (deleted / unknown) */
+  const uint32_t* max_jobs_per_user;
+  const uint32_t* max_jobs_per_account;
+  const uint32_t* max_jobs;
+  const int64_t* max_cpus_per_user_raw;
+  const int64_t* max_wall;              /* seconds; 0 = unlimited               */
+  const crane_tres_limit_t* max_tres_per_user;
+  const crane_tres_limit_t* max_tres_per_account;
+  const crane_tres_limit_t* max_tres;
+  /* account chain of every pending job (PdJobInScheduler::account_chain),
+   * CSR over account ids, in chain order */
+  const uint32_t* chain_off;            /* [n_pending + 1]                      */
+  const uint32_t* chain_acct;
+  /* usage, read and updated in place (host memory) */
+  crane_meta_resource_t* user_usage;    /* [n_users][n_qos]                     */
+  crane_meta_resource_t* account_usage; /* [n_accounts][n_qos]                  */
+  crane_meta_resource_t* qos_usage;     /* [n_qos]                              */
+} crane_qos_table_t;
+
+/* Replaces: the CheckAndMallocQosResource calls of the commit loop
+ * (JobScheduler.cpp:1262 -> Accounting/AccountMetaContainer.cpp:164-191, 382-531, 546-587)
+ * for the placements of the last crane_sched_run: in job-id (input) order, every
+ * job that NodeSelect starts now is checked against its (user,qos), account
+ * chain and qos limits and, if it passes, added to the usage; a job that fails
+ * gets the QoS reason code (it keeps the timeline reservation it made, as in
+ * the reference). `reason` ([n_pending], host) receives the updated reasons. */
+int crane_sched_qos_filter(crane_sched_t* h, const crane_qos_table_t* qos, uint8_t* reason);
 
 /* Capability bitmap of the last run (the jobs x nodes feasibility bitmap):
  * bit (rank r, local node q) set iff the r-th job in priority order can run

@@ -1208,6 +1208,165 @@ extern "C" int crane_oracle_timeline_update(
 // Known-answer tests. Cases 1-14 port
 // /root/reference/test/Utilities/dedicated_resource_test.cpp:27-171.
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// QoS post-filter (R12): Accounting/AccountMetaContainer.cpp
+// ---------------------------------------------------------------------------
+namespace {
+
+// GresMap (PublicHeader.h:490-508) keyed by dictionary ids. A key exists iff
+// its count is non-zero (deviation D8: the reference iterates an unordered_map
+// whose zero-count keys and order are unspecified; here names and types are
+// walked in dictionary order).
+struct QGresCount {
+  uint64_t total = 0;
+  std::map<uint32_t, uint64_t> specified;
+};
+using QGresMap = std::map<uint32_t, QGresCount>;
+struct QView {
+  int64_t cpu_raw = 0;
+  uint64_t mem = 0, mem_sw = 0;
+  QGresMap gres;
+};
+
+QView qview_of_usage(const crane_cluster_t* cl, const crane_meta_resource_t& u) {
+  QView v;
+  v.cpu_raw = u.cpu_raw; v.mem = u.mem; v.mem_sw = u.mem_sw;
+  for (uint32_t e = 0; e < cl->n_gres_entries; ++e) {
+    uint32_t g = cl->gres_entry_name[e];
+    if (u.gres_total[g]) v.gres[g].total = u.gres_total[g];
+    if (u.gres_spec[e]) v.gres[g].specified[e] = u.gres_spec[e];
+  }
+  return v;
+}
+QView qview_of_limit(const crane_cluster_t* cl, const crane_tres_limit_t& l) {
+  QView v;
+  v.cpu_raw = l.view.cpu_raw; v.mem = l.view.mem; v.mem_sw = l.view.mem_sw;
+  for (uint32_t e = 0; e < cl->n_gres_entries; ++e) {
+    uint32_t g = cl->gres_entry_name[e];
+    if (!((l.gres_name_present >> g) & 1)) continue;
+    v.gres[g].total = l.view.gres_total[g];
+    if ((l.gres_spec_present >> e) & 1) v.gres[g].specified[e] = l.view.gres_spec[e];
+  }
+  return v;
+}
+// ResourceV3::View (PublicHeader.cpp:946-952, 399-427)
+QView qview_of_alloc(const crane_cluster_t* cl, const crane_res_in_node_t* rows, uint32_t n) {
+  QView v;
+  for (uint32_t k = 0; k < n; ++k) {
+    v.cpu_raw += rows[k].cpu_raw;
+    v.mem += rows[k].mem;
+    v.mem_sw += rows[k].mem_sw;
+    for (uint32_t e = 0; e < cl->n_gres_entries; ++e) {
+      uint64_t cnt = (uint64_t)__builtin_popcount(rows[k].gres[e]);
+      if (!cnt) continue;
+      QGresCount& gc = v.gres[cl->gres_entry_name[e]];
+      gc.total += cnt;
+      gc.specified[e] += cnt;
+    }
+  }
+  return v;
+}
+// ResourceView::operator+=(ResourceView) (PublicHeader.cpp:448-456)
+void qview_add(QView& a, const QView& b) {
+  a.cpu_raw += b.cpu_raw; a.mem += b.mem; a.mem_sw += b.mem_sw;
+  for (const auto& [g, gc] : b.gres) {
+    QGresCount& d = a.gres[g];
+    d.total += gc.total;
+    for (const auto& [e, c] : gc.specified) d.specified[e] += c;
+  }
+}
+// AccountMetaContainer::CheckGres_ (AccountMetaContainer.cpp:509-531)
+bool q_check_gres(const QGresMap& req, const QGresMap& total) {
+  for (const auto& [name, lhs] : req) {
+    auto rhs_it = total.find(name);
+    if (rhs_it == total.end()) return true;
+    const QGresCount& rhs = rhs_it->second;
+    if (lhs.total > rhs.total) return false;
+    for (const auto& [type, lhs_cnt] : lhs.specified) {
+      auto t_it = rhs.specified.find(type);
+      if (t_it == rhs.specified.end()) return true;
+      if (lhs_cnt > t_it->second) return false;
+    }
+  }
+  return true;
+}
+// AccountMetaContainer::CheckTres_ (AccountMetaContainer.cpp:493-507)
+uint8_t q_check_tres(const QView& req, const QView& total) {
+  if (req.cpu_raw > total.cpu_raw) return CRANE_REASON_QOS_CPU;
+  if (req.mem > total.mem) return CRANE_REASON_QOS_MEM;
+  if (!q_check_gres(req.gres, total.gres)) return CRANE_REASON_QOS_GRES;
+  return CRANE_REASON_NONE;
+}
+// MetaResource::operator+= (AccountMetaContainer.cpp:33-39)
+void q_malloc(const crane_cluster_t* cl, crane_meta_resource_t& u, const QView& a, int64_t wall) {
+  u.cpu_raw += a.cpu_raw; u.mem += a.mem; u.mem_sw += a.mem_sw;
+  for (const auto& [g, gc] : a.gres) {
+    u.gres_total[g] += (uint32_t)gc.total;
+    for (const auto& [e, c] : gc.specified) u.gres_spec[e] += (uint32_t)c;
+  }
+  (void)cl;
+  u.jobs_count += 1;
+  u.wall_time += wall;
+}
+
+}  // namespace
+
+extern "C" int crane_oracle_qos_filter(const crane_cluster_t* cl, const crane_pending_t* pd,
+                                       crane_placements_t* out, const crane_qos_table_t* qt) {
+  if (!cl || !pd || !out || !qt) return CRANE_EINVAL;
+  for (uint32_t i = 0; i < pd->n; ++i) {  // commit loop order = job-id order (JS.cpp:1192)
+    if (out->reason[i] != CRANE_REASON_NONE || out->n_alloc[i] == 0) continue;
+    const uint32_t q = pd->qos[i], user = pd->user[i];
+    // CheckAndMallocQosResource (AccountMetaContainer.cpp:164-191)
+    if (q >= qt->n_qos || !qt->valid[q]) { out->reason[i] = CRANE_REASON_QOS_INVALID; continue; }
+    if (user >= qt->n_users) return CRANE_EINVAL;
+    const QView alloc = qview_of_alloc(cl, out->alloc_res + out->alloc_off[i], out->n_alloc[i]);
+    const int64_t tl = pd->time_limit[i];
+    const int64_t max_wall = qt->max_wall[q];
+    uint8_t result = CRANE_REASON_NONE;
+    // CheckQosResource_ (AccountMetaContainer.cpp:382-491): user
+    {
+      crane_meta_resource_t& val = qt->user_usage[(size_t)user * qt->n_qos + q];
+      QView use = alloc;
+      qview_add(use, qview_of_usage(cl, val));
+      if (use.cpu_raw > qt->max_cpus_per_user_raw[q]) result = CRANE_REASON_QOS_CPU;
+      else if ((uint64_t)val.jobs_count + 1 > qt->max_jobs_per_user[q]) result = CRANE_REASON_QOS_JOBS;
+      else if (max_wall > 0 && val.wall_time + tl > max_wall) result = CRANE_REASON_QOS_WALL;
+      else result = q_check_tres(use, qview_of_limit(cl, qt->max_tres_per_user[q]));
+    }
+    // account chain
+    if (result == CRANE_REASON_NONE) {
+      for (uint32_t c = qt->chain_off[i]; c < qt->chain_off[i + 1]; ++c) {
+        uint32_t a = qt->chain_acct[c];
+        if (a >= qt->n_accounts) return CRANE_EINVAL;
+        crane_meta_resource_t& val = qt->account_usage[(size_t)a * qt->n_qos + q];
+        QView use = alloc;
+        qview_add(use, qview_of_usage(cl, val));
+        if ((uint64_t)val.jobs_count + 1 > qt->max_jobs_per_account[q]) result = CRANE_REASON_QOS_JOBS;
+        else if (max_wall > 0 && val.wall_time + tl > max_wall) result = CRANE_REASON_QOS_WALL;
+        else result = q_check_tres(use, qview_of_limit(cl, qt->max_tres_per_account[q]));
+        if (result != CRANE_REASON_NONE) break;
+      }
+    }
+    // qos
+    if (result == CRANE_REASON_NONE) {
+      crane_meta_resource_t& val = qt->qos_usage[q];
+      QView use = alloc;
+      qview_add(use, qview_of_usage(cl, val));
+      if ((uint64_t)val.jobs_count + 1 > qt->max_jobs[q]) result = CRANE_REASON_QOS_JOBS;
+      else if (max_wall > 0 && val.wall_time + tl > max_wall) result = CRANE_REASON_QOS_WALL;
+      else result = q_check_tres(use, qview_of_limit(cl, qt->max_tres[q]));
+    }
+    if (result != CRANE_REASON_NONE) { out->reason[i] = result; continue; }
+    // DoMallocResource_ (AccountMetaContainer.cpp:546-587)
+    q_malloc(cl, qt->user_usage[(size_t)user * qt->n_qos + q], alloc, tl);
+    for (uint32_t c = qt->chain_off[i]; c < qt->chain_off[i + 1]; ++c)
+      q_malloc(cl, qt->account_usage[(size_t)qt->chain_acct[c] * qt->n_qos + q], alloc, tl);
+    q_malloc(cl, qt->qos_usage[q], alloc, tl);
+  }
+  return CRANE_OK;
+}
+
 extern "C" int crane_oracle_selftest(char* log, size_t log_cap) {
   int failed = 0;
   size_t used = 0;

@@ -60,6 +60,16 @@ int crane_oracle_timeline_update(const crane_cluster_t* dict, int64_t* times,
                                  uint32_t cap, int64_t start, int64_t end,
                                  const crane_res_in_node_t* res);
 
+/* Restates the CheckAndMallocQosResource pass of the commit loop
+ * (JobScheduler.cpp:1262; Accounting/AccountMetaContainer.cpp:164-191,
+ * 382-531, 546-587) over the placements NodeSelect produced: job-id order,
+ * jobs with reason NONE only; updates placements->reason and the usage tables
+ * of `qos` in place. */
+int crane_oracle_qos_filter(const crane_cluster_t* dict,
+                            const crane_pending_t* pending,
+                            crane_placements_t* placements,
+                            const crane_qos_table_t* qos);
+
 /* Ports test/Utilities/dedicated_resource_test.cpp:27-171 (14 cases) plus
  * hand-derived micro-cases. Returns the number of failed cases; fills `log`
  * (if non-NULL) with one line per failure. */

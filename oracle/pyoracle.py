@@ -43,6 +43,10 @@ def lib():
         _lib.crane_oracle_timeline_update.argtypes = [
             C.POINTER(abi.ClusterC), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32,
             C.c_int64, C.c_int64, C.c_void_p]
+        _lib.crane_oracle_qos_filter.restype = C.c_int
+        _lib.crane_oracle_qos_filter.argtypes = [
+            C.POINTER(abi.ClusterC), C.POINTER(abi.PendingC), C.POINTER(abi.PlacementsC),
+            C.POINTER(abi.QosTableC)]
         _lib.crane_oracle_selftest.restype = C.c_int
         _lib.crane_oracle_selftest.argtypes = [C.c_char_p, C.c_size_t]
     return _lib
@@ -85,6 +89,15 @@ def res_le(cluster: abi.Cluster, a: np.ndarray, b: np.ndarray) -> bool:
     b = np.ascontiguousarray(b, abi.RES_IN_NODE)
     c = cluster.as_c()
     return bool(lib().crane_oracle_res_le(C.byref(c), a.ctypes.data, b.ctypes.data))
+
+
+def qos_filter(cluster: abi.Cluster, pending: abi.Pending, out: abi.Placements, qos: abi.QosTable):
+    """In place on out.reason and qos.*_usage."""
+    c_cl, c_pd, c_out, c_q = cluster.as_c(), pending.as_c(), out.as_c(), qos.as_c()
+    rc = lib().crane_oracle_qos_filter(C.byref(c_cl), C.byref(c_pd), C.byref(c_out), C.byref(c_q))
+    if rc != 0:
+        raise RuntimeError(f"crane_oracle_qos_filter rc={rc}")
+    return out
 
 
 def selftest():
