@@ -14,9 +14,12 @@ from cranesched_b200.scheduler import GpuScheduler
 def _tiny():
     """4 single-node jobs, 1 partition of 4 big nodes, everything placed now."""
     cfg, cluster, running, pend, now = synth.config1(n_jobs=4, n_nodes=4)
-    pend.qos[:] = 0
-    pend.user[:] = [0, 0, 1, 1]
-    pend.account[:] = [0, 0, 1, 1]
+    pend.qos = np.zeros(4, np.uint32)  # fresh arrays: config1 shares one zeros column
+    pend.user = np.array([0, 0, 1, 1], np.uint32)
+    pend.account = np.array([0, 0, 1, 1], np.uint32)
+    for col in ("req_node", "req_task", "req_total", "node_num", "ntasks", "ntasks_per_node_min",
+                "ntasks_per_node_max", "exclusive"):
+        getattr(pend, col)[:] = getattr(pend, col)[0]  # every job asks the same
     return cfg, cluster, running, pend, now
 
 
@@ -97,7 +100,7 @@ def test_oracle_gres_limit_semantics(oracle):
     started = out.reason == 0
     gpu_jobs = np.flatnonzero(started & (pend.req_total["gres_total"][:, 0] > 0))
     assert len(gpu_jobs) >= 2
-    pend.qos[:] = 0
+    pend.qos = np.zeros(pend.n, np.uint32)
     base = synth.random_qos(1, cluster, pend, tight=1e6, invalid_frac=0.0)
     base.user_usage[:] = 0
     base.account_usage[:] = 0
@@ -154,10 +157,10 @@ def test_emulated_kernel_matches_oracle(oracle, emu_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed,tight", [(31, 1.0), (32, 3.0), (33, 0.5)])
-def test_gpu_matches_oracle(oracle, seed, tight):
+@pytest.mark.parametrize("seed,tight,invalid", [(31, 1.0, 0.0), (32, 3.0, 0.1), (33, 0.5, 0.4)])
+def test_gpu_matches_oracle(oracle, seed, tight, invalid):
     case = synth.random_case(seed, n_jobs=1500, n_nodes=160, n_parts=4, n_running=60)
-    table = synth.random_qos(seed, case[1], case[3], tight=tight)
+    table = synth.random_qos(seed, case[1], case[3], tight=tight, invalid_frac=invalid)
     ref = _parity(oracle, None, case, table)
     codes = set(np.unique(ref.reason).tolist())
     assert codes & {16, 17, 18, 19, 20, 21}
