@@ -656,8 +656,8 @@ struct CommitArgs {
 };
 
 constexpr int kRing = 16;            // prefetch ring depth (jobs)
-constexpr int kBatch = 8;            // one-node jobs dispatched together (<= warps per CTA)
-constexpr int kCommitThreads = 256;  // CTA size of k_commit: driver warp + 7 helpers
+constexpr int kBatch = 8;            // one-node jobs dispatched together (one helper warp each)
+constexpr int kCommitThreads = 288;  // CTA size of k_commit: driver warp + 8 helpers
 constexpr int kBucket = 64;          // bucket capacity of the cost order
 constexpr int kBucketFill = 32;      // entries per bucket after a (re)build
 
@@ -669,8 +669,10 @@ struct CommitSmem {
   long long* bmax_cpu;         // [nb]  >= cpu0 of every node in the bucket
   long long* bmax_cpug;        // [nb]  >= cpu0 of every node in the bucket that still has a free gres slot
   unsigned long long* bmax_g;  // [nb]  >= gcnt (per byte) of every node in the bucket
+  uint32_t* block;             // [nb]  bucket lock of the parallel inserts
   uint16_t* bk;                // [nb][kBucket] node ids, ascending (cost, node); buckets ascending
   uint16_t* bcnt;              // [nb]
+  uint16_t* blast;             // [nb]  last (largest-key) node of the bucket, 0xffff = empty
   uint16_t* bkt;               // [mp]  bucket of a node
   uint16_t* list;              // [mp]  nodes handed to the workers / selected nodes of the job
   uint16_t* tmp;               // [mp]  scratch of (re)builds
@@ -678,16 +680,17 @@ struct CommitSmem {
   uint8_t* skip;               // [mp]
   uint8_t* cls;                // [mp]
   uint8_t* bexact;             // [nb]  bounds are the exact maxima (nothing inserted since the last tightening)
+  uint8_t* pend;               // [mp]  picked by the batch in flight: out of the order until re-inserted
   uint32_t nb;
 };
 __host__ __device__ inline uint32_t commit_nbuckets(uint32_t mp) { return (mp + kBucketFill - 1) / kBucketFill + 1; }
 __host__ __device__ inline size_t commit_smem_bytes(uint32_t mp, uint32_t words) {
   const size_t nb = commit_nbuckets(mp);
   size_t b = (size_t)kRing * words * 4;
-  b += (size_t)mp * 8 * 3 + nb * 8 * 3 + nb;
-  b += nb * kBucket * 2 + nb * 2;
+  b += (size_t)mp * 8 * 3 + nb * 8 * 3 + nb * 4 + nb;
+  b += nb * kBucket * 2 + nb * 2 * 2;
   b += (size_t)mp * 2 * 4;
-  b += (size_t)mp * 2;
+  b += (size_t)mp * 3;
   return b + 128;
 }
 
@@ -1044,55 +1047,122 @@ __device__ __forceinline__ void bucket_remove(CommitSmem& sm, uint32_t u) {
   // entries after idx move one slot down (values are already in registers)
   if (lane > idx && lane < n) B[lane - 1] = e0;
   if (lane + 32 > idx && lane + 32 < n) B[lane + 31] = e1;
-  if (lane == 0) sm.bcnt[b] = (uint16_t)(n - 1);
+  __syncwarp();
+  if (lane == 0) {
+    sm.bcnt[b] = (uint16_t)(n - 1);
+    sm.blast[b] = n > 1 ? B[n - 2] : (uint16_t)0xffff;
+  }
   __syncwarp();
 }
 
-__device__ __forceinline__ bool bucket_insert(CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
+// Removes every node flagged in sm.pend — the picks list[0..np) of the batch in
+// flight — from its bucket, one pass per distinct bucket. Driver warp only.
+__device__ __noinline__ void bucket_remove_pending(CommitSmem& sm, uint32_t np) {
+  const uint32_t lane = lane_id();
+  const uint32_t myb = lane < np ? (uint32_t)sm.bkt[sm.list[lane]] : 0xffffffffu;
+  unsigned todo = __ballot_sync(kFullMask, lane < np);
+  while (todo) {
+    const uint32_t b = __shfl_sync(kFullMask, myb, __ffs((int)todo) - 1);
+    todo &= ~__ballot_sync(kFullMask, myb == b);
+    uint16_t* B = sm.bk + (size_t)b * kBucket;
+    const uint32_t n = sm.bcnt[b];
+    const uint16_t e0 = lane < n ? B[lane] : (uint16_t)0xffff;
+    const uint16_t e1 = lane + 32 < n ? B[lane + 32] : (uint16_t)0xffff;
+    const bool r0 = lane < n && sm.pend[e0], r1 = lane + 32 < n && sm.pend[e1];
+    const unsigned m0 = __ballot_sync(kFullMask, r0), m1 = __ballot_sync(kFullMask, r1);
+    const unsigned below = (1u << lane) - 1u;
+    if (lane < n && !r0) B[lane - (uint32_t)__popc(m0 & below)] = e0;
+    if (lane + 32 < n && !r1) B[lane + 32 - (uint32_t)__popc(m0) - (uint32_t)__popc(m1 & below)] = e1;
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t nn = n - (uint32_t)__popc(m0) - (uint32_t)__popc(m1);
+      sm.bcnt[b] = (uint16_t)nn;
+      sm.blast[b] = nn ? B[nn - 1] : (uint16_t)0xffff;
+    }
+    __syncwarp();
+  }
+}
+
+template <bool kLocked>
+__device__ __forceinline__ bool bucket_insert_t(CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
   const uint32_t lane = lane_id();
   // first non-empty bucket >= from_bucket whose last key is >= the new key;
-  // if there is none, the last non-empty bucket
+  // if there is none, the last non-empty bucket. The search reads only blast[]
+  // and cost[]: with concurrent (locked) inserts elsewhere a bucket's last node
+  // changes only for the last non-empty bucket, where either view gives the
+  // same target.
   uint32_t tb = 0xffffffffu, last_nonempty = 0xffffffffu;
-  for (uint32_t b0 = from_bucket; b0 < sm.nb && tb == 0xffffffffu; b0 += 32) {
-    const uint32_t b = b0 + lane;
-    bool nonempty = false, ge = false;
-    if (b < sm.nb) {
-      const uint32_t n = sm.bcnt[b];
-      if (n) {
-        nonempty = true;
-        const uint32_t o = sm.bk[(size_t)b * kBucket + n - 1];
-        ge = !key_lt(sm.cost[o], o, new_cost, u);
+  for (uint32_t start = from_bucket;; start = 0) {
+    for (uint32_t b0 = start; b0 < sm.nb && tb == 0xffffffffu; b0 += 32) {
+      const uint32_t b = b0 + lane;
+      bool nonempty = false, ge = false;
+      if (b < sm.nb) {
+        const uint32_t o = sm.blast[b];
+        if (o != 0xffffu) {
+          nonempty = true;
+          ge = !key_lt(sm.cost[o], o, new_cost, u);
+        }
       }
+      const unsigned mg = __ballot_sync(kFullMask, ge), mn = __ballot_sync(kFullMask, nonempty);
+      if (mg) tb = b0 + (uint32_t)__ffs((int)mg) - 1u;
+      if (mn) last_nonempty = b0 + 31u - (uint32_t)__clz((int)mn);
     }
-    const unsigned mg = __ballot_sync(kFullMask, ge), mn = __ballot_sync(kFullMask, nonempty);
-    if (mg) tb = b0 + (uint32_t)__ffs((int)mg) - 1u;
-    if (mn) last_nonempty = b0 + 31u - (uint32_t)__clz((int)mn);
+    if (tb != 0xffffffffu) break;
+    if (last_nonempty != 0xffffffffu) { tb = last_nonempty; break; }
+    // nothing at or after u's old bucket (its tail was removed with it): the
+    // nodes before it are the whole order now
+    if (start == 0) { tb = from_bucket; break; }
   }
-  if (tb == 0xffffffffu) tb = last_nonempty != 0xffffffffu ? last_nonempty : from_bucket;
+  if (kLocked) {
+    if (lane == 0) {
+      while (atomicCAS(&sm.block[tb], 0u, 1u) != 0u) {}
+      __threadfence_block();
+    }
+    __syncwarp();
+  }
   uint16_t* B = sm.bk + (size_t)tb * kBucket;
   const uint32_t n = sm.bcnt[tb];
-  if (n >= (uint32_t)kBucket) return false;
-  const uint16_t e0 = lane < n ? B[lane] : (uint16_t)0xffff;
-  const uint16_t e1 = lane + 32 < n ? B[lane + 32] : (uint16_t)0xffff;
-  const bool l0 = lane < n && key_lt(sm.cost[e0], e0, new_cost, u);
-  const bool l1 = lane + 32 < n && key_lt(sm.cost[e1], e1, new_cost, u);
-  const uint32_t pos = (uint32_t)__popc(__ballot_sync(kFullMask, l0)) + (uint32_t)__popc(__ballot_sync(kFullMask, l1));
-  if (lane >= pos && lane < n) B[lane + 1] = e0;
-  if (lane + 32 >= pos && lane + 32 < n) B[lane + 33] = e1;
-  if (lane == 0) {
-    B[pos] = (uint16_t)u;
-    sm.bcnt[tb] = (uint16_t)(n + 1);
-    sm.bkt[u] = (uint16_t)tb;
-    sm.cost[u] = new_cost;
-    const long long c = sm.cpu0[u];
-    const unsigned long long gc = sm.gcnt[u];
-    if (c > sm.bmax_cpu[tb]) sm.bmax_cpu[tb] = c;
-    if (gc && c > sm.bmax_cpug[tb]) sm.bmax_cpug[tb] = c;
-    sm.bmax_g[tb] = vmax8(sm.bmax_g[tb], gc);
-    sm.bexact[tb] = 0;
+  bool done = false;
+  if (n < (uint32_t)kBucket) {
+    const uint16_t e0 = lane < n ? B[lane] : (uint16_t)0xffff;
+    const uint16_t e1 = lane + 32 < n ? B[lane + 32] : (uint16_t)0xffff;
+    const bool l0 = lane < n && key_lt(sm.cost[e0], e0, new_cost, u);
+    const bool l1 = lane + 32 < n && key_lt(sm.cost[e1], e1, new_cost, u);
+    const uint32_t pos = (uint32_t)__popc(__ballot_sync(kFullMask, l0)) + (uint32_t)__popc(__ballot_sync(kFullMask, l1));
+    if (lane == 0) sm.cost[u] = new_cost;  // before u becomes visible in the bucket
+    if (lane >= pos && lane < n) B[lane + 1] = e0;
+    if (lane + 32 >= pos && lane + 32 < n) B[lane + 33] = e1;
+    if (kLocked) __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+      B[pos] = (uint16_t)u;
+      sm.bcnt[tb] = (uint16_t)(n + 1);
+      if (pos == n) sm.blast[tb] = (uint16_t)u;
+      sm.bkt[u] = (uint16_t)tb;
+      const long long c = sm.cpu0[u];
+      const unsigned long long gc = sm.gcnt[u];
+      if (c > sm.bmax_cpu[tb]) sm.bmax_cpu[tb] = c;
+      if (gc && c > sm.bmax_cpug[tb]) sm.bmax_cpug[tb] = c;
+      sm.bmax_g[tb] = vmax8(sm.bmax_g[tb], gc);
+      sm.bexact[tb] = 0;
+    }
+    done = true;
   }
   __syncwarp();
-  return true;
+  if (kLocked) {
+    if (lane == 0) {
+      __threadfence_block();
+      atomicExch(&sm.block[tb], 0u);
+    }
+  }
+  return done;
+}
+__device__ __forceinline__ bool bucket_insert(CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
+  return bucket_insert_t<false>(sm, u, new_cost, from_bucket);
+}
+// the same, callable by several warps at once for different nodes
+__device__ __noinline__ bool bucket_insert_locked(CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
+  return bucket_insert_t<true>(sm, u, new_cost, from_bucket);
 }
 
 // Deal sm.tmp[0..total) (already in (cost, node) order) out to the buckets,
@@ -1118,7 +1188,10 @@ __device__ __noinline__ void bucket_deal(CommitSmem& sm, uint32_t total) {
       mcg = ocg > mcg ? ocg : mcg;
       mg = vmax8(mg, __shfl_xor_sync(kFullMask, mg, o));
     }
-    if (lane == 0) { sm.bcnt[b] = (uint16_t)n; sm.bmax_cpu[b] = mc; sm.bmax_cpug[b] = mcg; sm.bmax_g[b] = mg; sm.bexact[b] = 1; }
+    if (lane == 0) {
+      sm.bcnt[b] = (uint16_t)n; sm.bmax_cpu[b] = mc; sm.bmax_cpug[b] = mcg; sm.bmax_g[b] = mg; sm.bexact[b] = 1;
+      sm.blast[b] = n ? sm.tmp[lo + n - 1] : (uint16_t)0xffff;
+    }
   }
   __syncwarp();
 }
@@ -1147,7 +1220,7 @@ enum : uint32_t {
   OP_NOW_MULTI = 9,  // K <= warps: worker w tests list[w]; if all K pass, each updates its node
   OP_BF_MULTI = 10,  // K <= warps: worker w iterates the common earliest start with the others, then updates
   OP_BATCH_P = 6,    // batch of one-node jobs: worker w evaluates task w (no state change)
-  OP_BATCH_C = 7,    // ... worker w < n commits task w
+  OP_REINSERT = 11,  // helper t < n re-inserts list[t] (flagged pend) at s_newcost[t]
   OP_EXIT = 8,
 };
 struct BatchTask {
@@ -1351,15 +1424,18 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     sm.bmax_cpu = reinterpret_cast<long long*>(ptr); ptr += (size_t)sm.nb * 8;
     sm.bmax_cpug = reinterpret_cast<long long*>(ptr); ptr += (size_t)sm.nb * 8;
     sm.bmax_g = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)sm.nb * 8;
+    sm.block = reinterpret_cast<uint32_t*>(ptr); ptr += (size_t)sm.nb * 4;
     sm.bk = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)sm.nb * kBucket * 2;
     sm.bcnt = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)sm.nb * 2;
+    sm.blast = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)sm.nb * 2;
     sm.bkt = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.list = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.tmp = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.nseg = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
     sm.skip = ptr; ptr += mp;
     sm.cls = ptr; ptr += mp;
-    sm.bexact = ptr;
+    sm.bexact = ptr; ptr += sm.nb;
+    sm.pend = ptr;
   }
   __shared__ JobQ s_jobs[kRing];
   __shared__ __align__(8) uint64_t s_bar[kRing];
@@ -1368,7 +1444,8 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   __shared__ BatchTask s_task[kBatch];
   __shared__ uint32_t s_ok[32];
   __shared__ long long s_tbuf[2][32];
-  __shared__ double s_undo[kBatch];
+  __shared__ double s_newcost[kBatch];
+  __shared__ uint32_t s_ovf[kBatch];
   __shared__ WorkerCtx s_cx;
   __shared__ long long s_res[32];   // per-worker result of a multi-warp step
   __shared__ uint32_t s_label;
@@ -1383,9 +1460,10 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     sm.skip[q] = a.tl.skip[g];
     sm.nseg[q] = (uint16_t)a.tl.n[g];
     sm.cls[q] = a.cl.slot_class[g];
+    sm.pend[q] = 0;
   }
   if (threadIdx.x < kMaxClasses) s_classrow[threadIdx.x] = a.cl.class_rows[(size_t)part * kMaxClasses + threadIdx.x];
-  for (uint32_t b = threadIdx.x; b < sm.nb; b += blockDim.x) sm.bcnt[b] = 0;
+  for (uint32_t b = threadIdx.x; b < sm.nb; b += blockDim.x) { sm.bcnt[b] = 0; sm.block[b] = 0; }
   if (threadIdx.x == 0) {
     s_label = 0;
     s_cx.cl = a.cl; s_cx.tl = a.tl; s_cx.out = a.out; s_cx.sm = sm; s_cx.jobs = s_jobs; s_cx.classrow = s_classrow;
@@ -1426,11 +1504,33 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       if (c.kind == OP_EXIT) break;
       long long r = 0;
       if (c.kind == OP_BATCH_P) {
-        if (wid < c.n) {  // task wid of the batch: node sm.list[wid], job in ring slot s_task[wid].slot
-          const BatchTask t = s_task[wid];
-          r = worker_step(&s_cx, t.mode ? OP_BF_K1 : OP_NOW_K1, wid + 1, t.slot, s_cx.now, wid, c.n, 2);
+        const uint32_t t = wid - 1;  // task t of the batch: node sm.list[t], job in ring slot s_task[t].slot
+        if (t < c.n) {
+          const BatchTask tk = s_task[t];
+          r = worker_step(&s_cx, tk.mode ? OP_BF_K1 : OP_NOW_K1, t + 1, tk.slot, s_cx.now, t, c.n, 2);
+          if (c.first) {
+            // back into the order: at the new cost if the pick was committed
+            const uint32_t q = sm.list[t];
+            const double nc = t < (uint32_t)r ? s_newcost[t] : sm.cost[q];
+            const bool ins = bucket_insert_locked(s_cx.sm, q, nc, sm.bkt[q]);
+            if (lane == 0) {
+              s_ovf[t] = ins ? 0u : 1u;
+              if (ins) sm.pend[q] = 0;
+            }
+          }
         } else {
           __syncthreads();  // the verdict barrier inside the batch step
+        }
+      } else if (c.kind == OP_REINSERT) {
+        const uint32_t t = wid - 1;
+        if (t < c.n) {
+          const uint32_t q = sm.list[t];
+          bool ins = true;
+          if (sm.pend[q]) ins = bucket_insert_locked(s_cx.sm, q, s_newcost[t], sm.bkt[q]);
+          if (lane == 0) {
+            s_ovf[t] = ins ? 0u : 1u;
+            if (ins) sm.pend[q] = 0;
+          }
         }
       } else if (c.kind == OP_NOW_MULTI || c.kind == OP_BF_MULTI) {
         if (wid < c.n) r = worker_step(&s_cx, c.kind, c.n, c.slot, c.t0, wid, 1, 0);
@@ -1768,14 +1868,41 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       }
       // cost += (end-start) * cpu ratio (JobScheduler.h:46-52); the allocation's
       // cpu is the job's per-node request, or the node total for exclusive jobs
+      if (K > 1 && K <= (uint32_t)kBatch && K < nw && mp >= 64) {
+        // the K nodes move in parallel: out of the order in one pass per bucket,
+        // back in by one helper each
+        if (lane < K) {
+          const uint32_t q = sm.list[lane];
+          const int64_t tot_cpu = sm.cls[q] != 0xff ? s_classrow[sm.cls[q]].cpu_raw : a.cl.slot_total[base + q].cpu_raw;
+          const double oc = sm.cost[q];
+          const double nc = __dadd_rn(oc, cost_delta(limit, exclusive ? tot_cpu : req_cpu, tot_cpu));
+          s_newcost[lane] = nc;
+          if (nc > oc) sm.pend[q] = 1;
+        }
+        __syncwarp();
+        bucket_remove_pending(sm, K);
+        if (lane == 0) { s_cmd.kind = OP_REINSERT; s_cmd.n = K; }
+        __syncthreads();
+        __syncthreads();
+        for (uint32_t t = 0; t < K; ++t) {
+          if (!s_ovf[t]) continue;
+          const uint32_t q = sm.list[t];
+          bucket_rebuild(sm);
+          first_bucket = 0;
+          bucket_insert(sm, q, s_newcost[t], 0);
+          if (lane == 0) sm.pend[q] = 0;
+          __syncwarp();
+        }
+      } else {
 #pragma unroll 1
-      for (uint32_t k = 0; k < K; ++k) {
-        const uint32_t q = sm.list[k];
-        const int64_t tot_cpu = sm.cls[q] != 0xff ? s_classrow[sm.cls[q]].cpu_raw : a.cl.slot_total[base + q].cpu_raw;
-        const double delta = cost_delta(limit, exclusive ? tot_cpu : req_cpu, tot_cpu);
-        const double oc = sm.cost[q];
-        const double nc = __dadd_rn(oc, delta);
-        if (nc > oc) rekey(q, nc, sm.bkt[q]);
+        for (uint32_t k = 0; k < K; ++k) {
+          const uint32_t q = sm.list[k];
+          const int64_t tot_cpu = sm.cls[q] != 0xff ? s_classrow[sm.cls[q]].cpu_raw : a.cl.slot_total[base + q].cpu_raw;
+          const double delta = cost_delta(limit, exclusive ? tot_cpu : req_cpu, tot_cpu);
+          const double oc = sm.cost[q];
+          const double nc = __dadd_rn(oc, delta);
+          if (nc > oc) rekey(q, nc, sm.bkt[q]);
+        }
       }
       PROF(7);
     } else {
@@ -1787,18 +1914,21 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   // For up to kBatch consecutive one-node jobs the driver picks each job's node
   // as the reference would (first pre-filter candidate in cost order for an
   // immediate start, else the first capable node for a backfill), assuming the
-  // jobs before it in the batch get placed, and re-keys that node at once.
-  // The workers then evaluate all picks in parallel without touching state;
-  // picks up to the first failure are committed in parallel, the rest is rolled
-  // back (re-key undone) and the failing job takes the one-job path. A job
-  // whose pick is already in the batch ends the batch (it needs that node's
-  // updated timeline).
+  // jobs before it in the batch get placed. The order itself is not touched
+  // while picking: a picked node is flagged (sm.pend) and skipped by the later
+  // picks, and a later job whose pick would have been an earlier pick at its
+  // new cost ends the batch (it needs that node's updated timeline). Then, in
+  // one step: the driver takes the picked nodes out of the order while the
+  // helpers evaluate all picks in parallel; picks up to the first failure are
+  // committed, and every helper puts its node back — at the new cost if its
+  // pick was committed, where it was otherwise. The failing job takes the
+  // one-job path.
   uint32_t ji = 0;
   while (ji < njobs) {
     ensure_issued(ji);
     uint32_t nt = 0;
     PROF(1);
-    while (nt < (uint32_t)kBatch && nt < nw && ji + nt < njobs) {
+    while (nt < (uint32_t)kBatch && nt + 1 < nw && ji + nt < njobs) {
       const uint32_t j = ji + nt;
       const uint32_t slot = j % kRing;
       mbar_wait(&s_bar[slot], (j / kRing) & 1u);
@@ -1811,6 +1941,17 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       const uint64_t spec8 = jq.spec8;
       const uint32_t gnames = (jflags >> 8) & 0xffu;
       while (first_bucket + 1 < sm.nb && sm.bcnt[first_bucket] == 0) ++first_bucket;
+      // the earlier picks of this batch, one per lane: can this job use the node?
+      bool p_cap = false, p_cand = false;
+      uint32_t p_node = 0;
+      double p_cost = 0.0;
+      if (lane < nt) {
+        p_node = sm.list[lane];
+        p_cost = s_newcost[lane];
+        p_cap = ((bits[p_node >> 5] >> (p_node & 31)) & 1u) && !sm.skip[p_node];
+        p_cand = p_cap && (exclusive || (sm.cpu0[p_node] >= req_cpu &&
+                                         (!(jflags & 2u) || gres_counts_ok(sm.gcnt[p_node], spec8, gnames, jq.name_need))));
+      }
       // (1) first node in cost order that passes capability + pre-filter
       uint32_t q = 0xffffffffu, mode = 0;
       for (uint32_t b = first_bucket; q == 0xffffffffu;) {
@@ -1828,20 +1969,23 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         b = nbk;
         const uint16_t* B = sm.bk + (size_t)b * kBucket;
         const uint32_t n = sm.bcnt[b];
+        bool any_pend = false;
         for (uint32_t h = 0; h < 2 && q == 0xffffffffu; ++h) {
           const uint32_t idx = lane + 32 * h;
-          bool cand = false;
+          bool cand = false, pn = false;
           uint32_t qq = 0;
           if (idx < n) {
             qq = B[idx];
-            cand = ((bits[qq >> 5] >> (qq & 31)) & 1u) && !sm.skip[qq];
+            pn = sm.pend[qq] != 0;
+            cand = !pn && ((bits[qq >> 5] >> (qq & 31)) & 1u) && !sm.skip[qq];
             if (cand && !exclusive)
               cand = sm.cpu0[qq] >= req_cpu && (!(jflags & 2u) || gres_counts_ok(sm.gcnt[qq], spec8, gnames, jq.name_need));
           }
           const unsigned cm = __ballot_sync(kFullMask, cand);
+          any_pend = any_pend || __any_sync(kFullMask, pn);
           if (cm) q = __shfl_sync(kFullMask, qq, __ffs((int)cm) - 1);
         }
-        if (q == 0xffffffffu && !sm.bexact[b]) {
+        if (q == 0xffffffffu && !sm.bexact[b] && !any_pend) {
           long long mc = INT64_MIN, mcg = INT64_MIN;
           unsigned long long mg = 0;
           for (uint32_t h = 0; h < 2; ++h) {
@@ -1866,8 +2010,14 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         }
         ++b;
       }
-      // (2) else the first capable node (backfill)
-      if (q == 0xffffffffu) {
+      bool clash = false;
+      if (q != 0xffffffffu) {
+        // an earlier pick that this job could use and that sorts before q at its new cost
+        clash = __any_sync(kFullMask, p_cand && key_lt(p_cost, p_node, sm.cost[q], q));
+      } else if (__any_sync(kFullMask, p_cand)) {
+        clash = true;
+      } else {
+        // (2) else the first capable node (backfill)
         mode = 1;
         for (uint32_t b = first_bucket; b < sm.nb && q == 0xffffffffu; ++b) {
           const uint16_t* B = sm.bk + (size_t)b * kBucket;
@@ -1878,57 +2028,58 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
             uint32_t qq = 0;
             if (idx < n) {
               qq = B[idx];
-              cap = ((bits[qq >> 5] >> (qq & 31)) & 1u) && !sm.skip[qq];
+              cap = !sm.pend[qq] && ((bits[qq >> 5] >> (qq & 31)) & 1u) && !sm.skip[qq];
             }
             const unsigned cm = __ballot_sync(kFullMask, cap);
             if (cm) q = __shfl_sync(kFullMask, qq, __ffs((int)cm) - 1);
           }
         }
+        if (q != 0xffffffffu) clash = __any_sync(kFullMask, p_cap && key_lt(p_cost, p_node, sm.cost[q], q));
+        else clash = __any_sync(kFullMask, p_cap);
       }
       PROF(3);
-      if (q == 0xffffffffu) break;  // no capable node at all: the one-job path reports "Resource"
-      bool clash = false;
-      for (uint32_t t = 0; t < nt; ++t) clash = clash || sm.list[t] == q;
-      if (clash) break;
-      // speculative re-key (cost += (end-start) * cpu ratio, JobScheduler.h:46-52)
+      if (clash || q == 0xffffffffu) break;  // no capable node at all: the one-job path reports "Resource"
+      // the pick's cost once the job is placed (cost += (end-start) * cpu ratio, JobScheduler.h:46-52)
       const int64_t tot_cpu = sm.cls[q] != 0xff ? s_classrow[sm.cls[q]].cpu_raw : a.cl.slot_total[base + q].cpu_raw;
-      const double oc = sm.cost[q];
-      const double nc = __dadd_rn(oc, cost_delta(jq.time_limit, exclusive ? tot_cpu : req_cpu, tot_cpu));
+      const double nc = __dadd_rn(sm.cost[q], cost_delta(jq.time_limit, exclusive ? tot_cpu : req_cpu, tot_cpu));
       if (lane == 0) {
         s_task[nt].slot = slot;
         s_task[nt].mode = mode;
         sm.list[nt] = (uint16_t)q;
-        s_undo[nt] = oc;
+        s_newcost[nt] = nc;
+        sm.pend[q] = 1;
       }
       __syncwarp();
-      if (nc > oc) rekey(q, nc, sm.bkt[q]);
       ++nt;
       PROF(6);
     }
 
     bool single = nt == 0;
     if (nt) {
-      // the workers evaluate all picks in parallel (no state change), agree on the
-      // first failing one and commit the picks before it
-      if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = nt; }
-      __syncthreads();
-      const BatchTask t0 = s_task[0];
-      const uint32_t f = (uint32_t)worker_step(&s_cx, t0.mode ? OP_BF_K1 : OP_NOW_K1, 1, t0.slot, a.now, 0, nt, 2);
-      __syncthreads();
+      const bool par = mp >= 64;  // the order never runs empty under the parallel inserts
+      if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = nt; s_cmd.first = par ? 1u : 0u; }
+      __syncthreads();                  // the helpers start evaluating
+      bucket_remove_pending(sm, nt);    // meanwhile the picks leave the order
+      __syncthreads();                  // verdicts are in; the order is ready for the inserts
+      uint32_t f = nt;
+      for (uint32_t i = 0; i < nt; ++i)
+        if (!s_ok[i]) { f = i; break; }
+      PROF(9);
+      __syncthreads();                  // commits and re-inserts are done
       PROF_CNT(13, f);
       PROF_CNT(14, 1);
-      // roll back the re-keys of the picks that were not committed, last first
-      for (uint32_t t = nt; t > f; --t) {
-        const uint32_t q = sm.list[t - 1];
-        const double oc = s_undo[t - 1];
-        if (sm.cost[q] != oc) {
-          bucket_remove(sm, q);
-          if (!bucket_insert(sm, q, oc, 0)) {
-            bucket_rebuild(sm);
-            bucket_insert(sm, q, oc, 0);
-          }
+      for (uint32_t t = 0; t < nt; ++t) {
+        if (par && !s_ovf[t]) continue;
+        // serial re-insert: tiny partition, or the target bucket was full
+        const uint32_t q = sm.list[t];
+        const double nc = t < f ? s_newcost[t] : sm.cost[q];
+        if (!bucket_insert(sm, q, nc, sm.bkt[q])) {
+          bucket_rebuild(sm);
           first_bucket = 0;
+          bucket_insert(sm, q, nc, 0);
         }
+        if (lane == 0) sm.pend[q] = 0;
+        __syncwarp();
       }
       PROF(11);
       ji += f;
