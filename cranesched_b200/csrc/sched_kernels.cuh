@@ -656,8 +656,11 @@ struct CommitArgs {
 };
 
 constexpr int kRing = 16;            // prefetch ring depth (jobs)
-constexpr int kBatch = 8;            // one-node jobs dispatched together (one helper warp each)
-constexpr int kCommitThreads = 288;  // CTA size of k_commit: driver warp + 8 helpers
+#ifndef CRANE_COMMIT_THREADS
+#define CRANE_COMMIT_THREADS 288
+#endif
+constexpr int kCommitThreads = CRANE_COMMIT_THREADS;  // CTA size of k_commit: driver warp + helpers
+constexpr int kBatch = kCommitThreads / 32 - 1;       // one-node jobs dispatched together (one helper warp each)
 constexpr int kBucket = 64;          // bucket capacity of the cost order
 constexpr int kBucketFill = 32;      // entries per bucket after a (re)build
 
@@ -1122,6 +1125,9 @@ __device__ __forceinline__ bool bucket_insert_t(CommitSmem& sm, uint32_t u, doub
   }
   uint16_t* B = sm.bk + (size_t)tb * kBucket;
   const uint32_t n = sm.bcnt[tb];
+#ifdef CRANE_EMU_DEBUG
+  if (lane == 0) fprintf(stderr, "  insert%s u=%u key=%.6f from=%u -> tb=%u n=%u blast[tb]=%u cost[blast]=%.6f\n", kLocked ? "L" : "", u, new_cost, from_bucket, tb, n, sm.blast[tb], sm.blast[tb] != 0xffff ? sm.cost[sm.blast[tb]] : -1.0);
+#endif
   bool done = false;
   if (n < (uint32_t)kBucket) {
     const uint16_t e0 = lane < n ? B[lane] : (uint16_t)0xffff;
@@ -1209,6 +1215,35 @@ __device__ __noinline__ void bucket_rebuild(CommitSmem& sm) {
   bucket_deal(sm, rank);
 }
 
+#ifdef CRANE_EMU_DEBUG
+// emulation-only invariant check of the bucketed order (driver lane 0)
+inline void bucket_check(const CommitSmem& sm, uint32_t mp, const char* where, uint32_t job) {
+  if (lane_id() != 0) return;
+  std::vector<int> seen(mp, 0);
+  double pc = -1.0; uint32_t pq = 0; bool have = false;
+  for (uint32_t b = 0; b < sm.nb; ++b) {
+    const uint32_t n = sm.bcnt[b];
+    if ((n == 0) != (sm.blast[b] == 0xffff) || (n && sm.blast[b] != sm.bk[(size_t)b * kBucket + n - 1])) {
+      fprintf(stderr, "[%s job %u] blast mismatch bucket %u n=%u blast=%u\n", where, job, b, n, sm.blast[b]); abort();
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint32_t q = sm.bk[(size_t)b * kBucket + i];
+      if (q >= mp || seen[q]++) { fprintf(stderr, "[%s job %u] node %u twice/out of range in bucket %u\n", where, job, q, b); abort(); }
+      if (sm.bkt[q] != b) { fprintf(stderr, "[%s job %u] bkt[%u]=%u but in bucket %u\n", where, job, q, sm.bkt[q], b); abort(); }
+      if (have && !key_lt(pc, pq, sm.cost[q], q)) {
+        fprintf(stderr, "[%s job %u] order violated at bucket %u idx %u: (%g,%u) then (%g,%u)\n", where, job, b, i, pc, pq, sm.cost[q], q); abort();
+      }
+      pc = sm.cost[q]; pq = q; have = true;
+    }
+  }
+  for (uint32_t q = 0; q < mp; ++q)
+    if (!seen[q]) { fprintf(stderr, "[%s job %u] node %u missing (pend=%u)\n", where, job, q, sm.pend[q]); abort(); }
+}
+#define BUCKET_CHECK(where, job) bucket_check(sm, mp, where, job)
+#else
+#define BUCKET_CHECK(where, job)
+#endif
+
 // worker commands (driver -> helpers, through shared memory + the CTA barrier)
 enum : uint32_t {
   OP_NOW_K1 = 0,     // one-node job: test the node now; on success update it
@@ -1220,12 +1255,26 @@ enum : uint32_t {
   OP_NOW_MULTI = 9,  // K <= warps: worker w tests list[w]; if all K pass, each updates its node
   OP_BF_MULTI = 10,  // K <= warps: worker w iterates the common earliest start with the others, then updates
   OP_BATCH_P = 6,    // batch of one-node jobs: worker w evaluates task w (no state change)
+  OP_SELECT = 12,    // helper t < n lists the candidates of batch job t
   OP_REINSERT = 11,  // helper t < n re-inserts list[t] (flagged pend) at s_newcost[t]
   OP_EXIT = 8,
 };
-struct BatchTask {
-  uint32_t slot;   // ring slot of the job
-  uint32_t mode;   // 0 = immediate start on list[w], 1 = backfill on list[w]
+struct BatchTask {   // one (job, node) pair of the batch in flight; its node is sm.list[w]
+  uint32_t slot;     // ring slot of the job
+  uint32_t mode;     // 0 = immediate start, 1 = backfill (one-node jobs only)
+  uint32_t tfirst;   // first task of the same job (its nodes are list[tfirst .. tfirst + node_num))
+  uint32_t pad;
+};
+struct BatchJob {    // one job of the batch being formed
+  uint32_t slot;     // ring slot
+  uint32_t K;        // node_num
+  uint32_t need;     // nodes of this job and of the jobs before it in the batch: candidates worth listing
+  uint32_t n0, n1;   // candidates found: pre-filter (immediate start) / capable (backfill)
+  uint32_t pad;
+};
+struct BatchSel {    // the first `need` candidates of one job in cost order, with the cost each would get
+  double nc0[kBatch], nc1[kBatch];
+  uint16_t c0[kBatch], c1[kBatch];
 };
 struct CommitCmd {
   uint32_t kind, n, slot, first;  // OP_TEST: worker w handles list[first + w]; others: list[w], list[w+nw], ...
@@ -1243,6 +1292,11 @@ struct WorkerCtx {  // lives in shared memory; read-only after set-up
   long long* tbuf;   // [2][32] per-iteration earliest fits of a multi-node job
   int64_t now, max_window;
   uint32_t base, max_jobs;
+  uint32_t words;    // capability bitmap words per job row
+  BatchJob* bj;      // [kBatch]
+  BatchSel* sel;     // [kBatch]
+  const BatchTask* task;         // [kBatch]
+  const uint32_t* first_bucket;  // buckets before it are empty
 };
 
 // barrier protocol of the fused multi-node steps for a warp that holds no node
@@ -1261,6 +1315,128 @@ __device__ __noinline__ void multi_idle(const WorkerCtx* cxp, uint32_t kind, uin
     if (tmax == kInf || tmax == T0) break;
     T0 = tmax;
   }
+}
+
+// Candidate list of batch job t (one helper warp per job, all jobs of the batch
+// at once, the order is not modified meanwhile): the first `need` nodes in cost
+// order that pass capability + pre-filter (JobScheduler.cpp:5224-5266) and — if
+// there are fewer — the first `need` capable nodes, which is where a backfill
+// would go (JobScheduler.cpp:5269-5278). `need` covers the nodes the jobs before
+// it in the batch may take away. Each listed node comes with the cost it gets
+// when the job is placed on it (JobScheduler.h:46-52).
+__device__ __noinline__ void select_step(const WorkerCtx* cxp, uint32_t t) {
+  const WorkerCtx& cx = *cxp;
+  const CommitSmem& sm = cx.sm;
+  const uint32_t lane = lane_id();
+  const BatchJob bj = cx.bj[t];
+  const JobQ& jq = cx.jobs[bj.slot];
+  const uint32_t* bits = sm.bits_ring + (size_t)bj.slot * cx.words;
+  BatchSel& out = cx.sel[t];
+  const uint32_t need = bj.need;
+  const uint32_t jflags = jq.flags;
+  const bool exclusive = jflags & 1u;
+  const int64_t req_cpu = jq.req.cpu_raw;
+  const uint64_t spec8 = jq.spec8;
+  const uint32_t gnames = (jflags >> 8) & 0xffu;
+  const uint32_t fb = *cx.first_bucket;
+  uint32_t c = 0;
+  for (uint32_t b = fb; c < need;) {
+    // next bucket whose bounds admit a candidate (32 buckets per probe)
+    uint32_t nbk = 0xffffffffu;
+    for (uint32_t b0 = b; b0 < sm.nb && nbk == 0xffffffffu; b0 += 32) {
+      const uint32_t bb = b0 + lane;
+      bool prom = false;
+      if (bb < sm.nb && sm.bcnt[bb])
+        prom = exclusive || ((jflags & 2u) ? (sm.bmax_cpug[bb] >= req_cpu && gres_counts_ok(sm.bmax_g[bb], spec8, gnames, jq.name_need))
+                                           : sm.bmax_cpu[bb] >= req_cpu);
+      const unsigned pm = __ballot_sync(kFullMask, prom);
+      if (pm) nbk = b0 + (uint32_t)__ffs((int)pm) - 1u;
+    }
+    if (nbk == 0xffffffffu) break;
+    b = nbk;
+    const uint32_t n = sm.bcnt[b];
+    const uint16_t* B = sm.bk + (size_t)b * kBucket;
+    bool any_cand = false;
+    for (uint32_t h = 0; h < 2 && c < need; ++h) {
+      const uint32_t idx = lane + 32 * h;
+      bool cand = false;
+      uint32_t q = 0;
+      if (idx < n) {
+        q = B[idx];
+        cand = ((bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
+        if (cand && !exclusive)
+          cand = sm.cpu0[q] >= req_cpu && (!(jflags & 2u) || gres_counts_ok(sm.gcnt[q], spec8, gnames, jq.name_need));
+      }
+      const unsigned cm = __ballot_sync(kFullMask, cand);
+      any_cand = any_cand || cm != 0;
+      const uint32_t rank = c + (uint32_t)__popc(cm & ((1u << lane) - 1u));
+      if (cand && rank < need) out.c0[rank] = (uint16_t)q;
+      c += (uint32_t)__popc(cm);
+    }
+    if (!any_cand && !sm.bexact[b]) {
+      // nothing in this bucket passes the pre-filter: tighten its bounds to the
+      // exact maxima (several helpers may do this at once; they write the same values)
+      long long mc = INT64_MIN, mcg = INT64_MIN;
+      unsigned long long mg = 0;
+      for (uint32_t h = 0; h < 2; ++h) {
+        const uint32_t idx = lane + 32 * h;
+        if (idx < n) {
+          const uint32_t q = B[idx];
+          const long long c0 = sm.cpu0[q];
+          const unsigned long long gc = sm.gcnt[q];
+          mc = c0 > mc ? c0 : mc;
+          if (gc && c0 > mcg) mcg = c0;
+          mg = vmax8(mg, gc);
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const long long oc = __shfl_xor_sync(kFullMask, mc, o), ocg = __shfl_xor_sync(kFullMask, mcg, o);
+        mc = oc > mc ? oc : mc;
+        mcg = ocg > mcg ? ocg : mcg;
+        mg = vmax8(mg, __shfl_xor_sync(kFullMask, mg, o));
+      }
+      if (lane == 0) { sm.bmax_cpu[b] = mc; sm.bmax_cpug[b] = mcg; sm.bmax_g[b] = mg; sm.bexact[b] = 1; }
+      __syncwarp();
+    }
+    ++b;
+  }
+  const uint32_t n0 = c < need ? c : need;
+  uint32_t n1 = 0;
+  if (n0 < need) {
+    uint32_t cum = 0;
+    for (uint32_t b = fb; b < sm.nb && cum < need; ++b) {
+      const uint16_t* B = sm.bk + (size_t)b * kBucket;
+      const uint32_t n = sm.bcnt[b];
+      for (uint32_t h = 0; h < 2 && cum < need; ++h) {
+        const uint32_t idx = lane + 32 * h;
+        bool cap = false;
+        uint32_t q = 0;
+        if (idx < n) {
+          q = B[idx];
+          cap = ((bits[q >> 5] >> (q & 31)) & 1u) && !sm.skip[q];
+        }
+        const unsigned m = __ballot_sync(kFullMask, cap);
+        const uint32_t rank = cum + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        if (cap && rank < need) out.c1[rank] = (uint16_t)q;
+        cum += (uint32_t)__popc(m);
+      }
+    }
+    n1 = cum < need ? cum : need;
+  }
+  __syncwarp();
+  // the cost each listed node would get: lanes 0..7 the immediate-start list, 8..15 the backfill list
+  {
+    const bool second = lane >= (uint32_t)kBatch;
+    const uint32_t i = second ? lane - (uint32_t)kBatch : lane;
+    if (lane < 2u * (uint32_t)kBatch && i < (second ? n1 : n0)) {
+      const uint32_t q = second ? out.c1[i] : out.c0[i];
+      const int64_t tot_cpu = sm.cls[q] != 0xff ? cx.classrow[sm.cls[q]].cpu_raw : cx.cl.slot_total[cx.base + q].cpu_raw;
+      const double nc = __dadd_rn(sm.cost[q], cost_delta(jq.time_limit, exclusive ? tot_cpu : req_cpu, tot_cpu));
+      if (second) out.nc1[i] = nc; else out.nc0[i] = nc;
+    }
+  }
+  if (lane == 0) { cx.bj[t].n0 = n0; cx.bj[t].n1 = n1; }
+  __syncwarp();
 }
 
 // The per-node work of one command on this warp's share of sm.list[first, n)
@@ -1362,6 +1538,8 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
       uint32_t f = stride;
       for (uint32_t i = 0; i < stride; ++i)
         if (!cx.ok[i]) { f = i; break; }
+      // a job is placed only if all its nodes pass: cut at the first task of the failing job
+      if (f < stride) f = cx.task[f].tfirst;
       ok = first < f;
       result = (long long)f;
     }
@@ -1373,8 +1551,9 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
       const uint32_t nn = ns <= 64 ? node_update(cx.tl, g, nr, start, end, alloc, seg0)
                                    : node_update_big(cx.tl, g, ns, start, end, alloc, seg0);
       uint32_t rank = 0;  // node-index ascending output slot (deviation D3)
-      if (n > 1 && !batch) {
-        for (uint32_t m = lane; m < K; m += 32) rank += sm.list[m] < q ? 1u : 0u;
+      if ((n > 1 && !batch) || (batch == 2 && K > 1)) {
+        const uint32_t l0 = batch == 2 ? cx.task[first].tfirst : 0u;  // the job's nodes are list[l0 .. l0+K)
+        for (uint32_t m = lane; m < K; m += 32) rank += sm.list[l0 + m] < q ? 1u : 0u;
         for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(kFullMask, rank, o);
       }
       if (lane == 0) {
@@ -1388,10 +1567,10 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
         cx.out.alloc_res[dst] = alloc;
         // pending-reason label for future starts (JobScheduler.cpp:5842-5848)
         const bool short_now = start != now && !row_le(alloc, a0);
-        if (batch) {  // one-node job of a batch: its job-level outputs are written here
+        if (batch) {  // job of a batch: its job-level outputs are written here (by each of its tasks, same values)
           cx.out.start_time[jq.job] = start;
           cx.out.end_time[jq.job] = end;
-          cx.out.n_alloc[jq.job] = 1;
+          cx.out.n_alloc[jq.job] = K;
           cx.out.reason[jq.job] = start == now ? CRANE_REASON_NONE : (short_now ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY);
         } else if (short_now) {
           atomicOr(cx.label, 1u);
@@ -1442,6 +1621,9 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   __shared__ Row s_classrow[kMaxClasses];
   __shared__ CommitCmd s_cmd;
   __shared__ BatchTask s_task[kBatch];
+  __shared__ BatchJob s_bj[kBatch];
+  __shared__ BatchSel s_sel[kBatch];
+  __shared__ uint32_t s_first_bucket;
   __shared__ uint32_t s_ok[32];
   __shared__ long long s_tbuf[2][32];
   __shared__ double s_newcost[kBatch];
@@ -1468,6 +1650,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     s_label = 0;
     s_cx.cl = a.cl; s_cx.tl = a.tl; s_cx.out = a.out; s_cx.sm = sm; s_cx.jobs = s_jobs; s_cx.classrow = s_classrow;
     s_cx.label = &s_label; s_cx.ok = s_ok; s_cx.tbuf = &s_tbuf[0][0]; s_cx.now = a.now; s_cx.max_window = a.max_window; s_cx.base = base; s_cx.max_jobs = a.max_jobs;
+    s_cx.words = words; s_cx.bj = s_bj; s_cx.sel = s_sel; s_cx.task = s_task; s_cx.first_bucket = &s_first_bucket;
     for (int s = 0; s < kRing; ++s) mbar_init(&s_bar[s], 1);
     fence_mbar_init();
   }
@@ -1521,6 +1704,8 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         } else {
           __syncthreads();  // the verdict barrier inside the batch step
         }
+      } else if (c.kind == OP_SELECT) {
+        if (wid - 1 < c.n) select_step(&s_cx, wid - 1);
       } else if (c.kind == OP_REINSERT) {
         const uint32_t t = wid - 1;
         if (t < c.n) {
@@ -1583,6 +1768,20 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       first_bucket = 0;
       bucket_insert(sm, q, nc, 0);
     }
+  };
+
+  // a node the helpers could not put back (tiny partition, or its target bucket
+  // was full): serial insert; once the order was re-dealt the old bucket index
+  // of the remaining nodes means nothing
+  auto leftover_insert = [&](uint32_t q, double nc, bool& rebuilt) {
+    if (!bucket_insert(sm, q, nc, rebuilt ? 0u : (uint32_t)sm.bkt[q])) {
+      bucket_rebuild(sm);
+      first_bucket = 0;
+      rebuilt = true;
+      bucket_insert(sm, q, nc, 0);
+    }
+    if (lane == 0) sm.pend[q] = 0;
+    __syncwarp();
   };
 
   // ---- one job, start to finish (any node_num) ------------------------------
@@ -1884,15 +2083,9 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         if (lane == 0) { s_cmd.kind = OP_REINSERT; s_cmd.n = K; }
         __syncthreads();
         __syncthreads();
-        for (uint32_t t = 0; t < K; ++t) {
-          if (!s_ovf[t]) continue;
-          const uint32_t q = sm.list[t];
-          bucket_rebuild(sm);
-          first_bucket = 0;
-          bucket_insert(sm, q, s_newcost[t], 0);
-          if (lane == 0) sm.pend[q] = 0;
-          __syncwarp();
-        }
+        bool rebuilt = false;
+        for (uint32_t t = 0; t < K; ++t)
+          if (s_ovf[t]) leftover_insert(sm.list[t], s_newcost[t], rebuilt);
       } else {
 #pragma unroll 1
         for (uint32_t k = 0; k < K; ++k) {
@@ -1910,184 +2103,147 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     }
     };
 
-  // ---- dispatcher: runs of one-node jobs go out as batches --------------------
-  // For up to kBatch consecutive one-node jobs the driver picks each job's node
-  // as the reference would (first pre-filter candidate in cost order for an
-  // immediate start, else the first capable node for a backfill), assuming the
-  // jobs before it in the batch get placed. The order itself is not touched
-  // while picking: a picked node is flagged (sm.pend) and skipped by the later
-  // picks, and a later job whose pick would have been an earlier pick at its
-  // new cost ends the batch (it needs that node's updated timeline). Then, in
-  // one step: the driver takes the picked nodes out of the order while the
-  // helpers evaluate all picks in parallel; picks up to the first failure are
-  // committed, and every helper puts its node back — at the new cost if its
-  // pick was committed, where it was otherwise. The failing job takes the
+  // ---- dispatcher: consecutive jobs go out as batches ---------------------------
+  // A batch is a run of jobs with at most kBatch nodes in total (one helper warp
+  // per node). Four steps, each parallel over the helpers:
+  //  select   every job lists its first candidates in cost order, enough of them
+  //           to survive whatever the jobs before it in the batch take away;
+  //  resolve  (driver, a few shared-memory look-ups per job) in job order each job
+  //           takes its first free candidates, exactly the reference's pick if
+  //           the jobs before it get placed; a taken node is flagged (sm.pend);
+  //           a job that could use a taken node at that node's NEW place in the
+  //           order ends the batch — it needs that node's updated timeline;
+  //  evaluate every (job, node) pair is tested exactly, without touching state,
+  //           while the driver takes the picked nodes out of the order; the jobs
+  //           before the first failing one are committed;
+  //  re-key   every helper puts its node back: at the new cost if its job was
+  //           committed, where it was otherwise.
+  // The failing job, multi-node backfills and jobs larger than a batch take the
   // one-job path.
   uint32_t ji = 0;
+  uint32_t single_job = 0xffffffffu;  // a job already known to need the one-job path
   while (ji < njobs) {
     ensure_issued(ji);
-    uint32_t nt = 0;
     PROF(1);
-    while (nt < (uint32_t)kBatch && nt + 1 < nw && ji + nt < njobs) {
-      const uint32_t j = ji + nt;
+    // ---- form the batch ------------------------------------------------------
+    uint32_t nj = 0, need = 0;
+    while (nj < (uint32_t)kBatch && nj + 1 < nw && ji + nj < njobs && ji + nj != single_job) {
+      const uint32_t j = ji + nj;
       const uint32_t slot = j % kRing;
       mbar_wait(&s_bar[slot], (j / kRing) & 1u);
-      const JobQ& jq = s_jobs[slot];
-      if (jq.node_num != 1 || mp == 0) break;
-      const uint32_t* bits = sm.bits_ring + (size_t)slot * words;
-      const uint32_t jflags = jq.flags;
-      const bool exclusive = jflags & 1u;
-      const int64_t req_cpu = jq.req.cpu_raw;
-      const uint64_t spec8 = jq.spec8;
-      const uint32_t gnames = (jflags >> 8) & 0xffu;
-      while (first_bucket + 1 < sm.nb && sm.bcnt[first_bucket] == 0) ++first_bucket;
-      // the earlier picks of this batch, one per lane: can this job use the node?
-      bool p_cap = false, p_cand = false;
-      uint32_t p_node = 0;
-      double p_cost = 0.0;
-      if (lane < nt) {
-        p_node = sm.list[lane];
-        p_cost = s_newcost[lane];
-        p_cap = ((bits[p_node >> 5] >> (p_node & 31)) & 1u) && !sm.skip[p_node];
-        p_cand = p_cap && (exclusive || (sm.cpu0[p_node] >= req_cpu &&
-                                         (!(jflags & 2u) || gres_counts_ok(sm.gcnt[p_node], spec8, gnames, jq.name_need))));
-      }
-      // (1) first node in cost order that passes capability + pre-filter
-      uint32_t q = 0xffffffffu, mode = 0;
-      for (uint32_t b = first_bucket; q == 0xffffffffu;) {
-        uint32_t nbk = 0xffffffffu;
-        for (uint32_t b0 = b; b0 < sm.nb && nbk == 0xffffffffu; b0 += 32) {
-          const uint32_t bb = b0 + lane;
-          bool prom = false;
-          if (bb < sm.nb && sm.bcnt[bb])
-            prom = exclusive || ((jflags & 2u) ? (sm.bmax_cpug[bb] >= req_cpu && gres_counts_ok(sm.bmax_g[bb], spec8, gnames, jq.name_need))
-                                               : sm.bmax_cpu[bb] >= req_cpu);
-          const unsigned pm = __ballot_sync(kFullMask, prom);
-          if (pm) nbk = b0 + (uint32_t)__ffs((int)pm) - 1u;
-        }
-        if (nbk == 0xffffffffu) break;
-        b = nbk;
-        const uint16_t* B = sm.bk + (size_t)b * kBucket;
-        const uint32_t n = sm.bcnt[b];
-        bool any_pend = false;
-        for (uint32_t h = 0; h < 2 && q == 0xffffffffu; ++h) {
-          const uint32_t idx = lane + 32 * h;
-          bool cand = false, pn = false;
-          uint32_t qq = 0;
-          if (idx < n) {
-            qq = B[idx];
-            pn = sm.pend[qq] != 0;
-            cand = !pn && ((bits[qq >> 5] >> (qq & 31)) & 1u) && !sm.skip[qq];
-            if (cand && !exclusive)
-              cand = sm.cpu0[qq] >= req_cpu && (!(jflags & 2u) || gres_counts_ok(sm.gcnt[qq], spec8, gnames, jq.name_need));
-          }
-          const unsigned cm = __ballot_sync(kFullMask, cand);
-          any_pend = any_pend || __any_sync(kFullMask, pn);
-          if (cm) q = __shfl_sync(kFullMask, qq, __ffs((int)cm) - 1);
-        }
-        if (q == 0xffffffffu && !sm.bexact[b] && !any_pend) {
-          long long mc = INT64_MIN, mcg = INT64_MIN;
-          unsigned long long mg = 0;
-          for (uint32_t h = 0; h < 2; ++h) {
-            const uint32_t idx = lane + 32 * h;
-            if (idx < n) {
-              const uint32_t qq = B[idx];
-              const long long c0 = sm.cpu0[qq];
-              const unsigned long long gc = sm.gcnt[qq];
-              mc = c0 > mc ? c0 : mc;
-              if (gc && c0 > mcg) mcg = c0;
-              mg = vmax8(mg, gc);
-            }
-          }
-          for (int o = 16; o > 0; o >>= 1) {
-            const long long oc = __shfl_xor_sync(kFullMask, mc, o), ocg = __shfl_xor_sync(kFullMask, mcg, o);
-            mc = oc > mc ? oc : mc;
-            mcg = ocg > mcg ? ocg : mcg;
-            mg = vmax8(mg, __shfl_xor_sync(kFullMask, mg, o));
-          }
-          if (lane == 0) { sm.bmax_cpu[b] = mc; sm.bmax_cpug[b] = mcg; sm.bmax_g[b] = mg; sm.bexact[b] = 1; }
-          __syncwarp();
-        }
-        ++b;
-      }
-      bool clash = false;
-      if (q != 0xffffffffu) {
-        // an earlier pick that this job could use and that sorts before q at its new cost
-        clash = __any_sync(kFullMask, p_cand && key_lt(p_cost, p_node, sm.cost[q], q));
-      } else if (__any_sync(kFullMask, p_cand)) {
-        clash = true;
-      } else {
-        // (2) else the first capable node (backfill)
-        mode = 1;
-        for (uint32_t b = first_bucket; b < sm.nb && q == 0xffffffffu; ++b) {
-          const uint16_t* B = sm.bk + (size_t)b * kBucket;
-          const uint32_t n = sm.bcnt[b];
-          for (uint32_t h = 0; h < 2 && q == 0xffffffffu; ++h) {
-            const uint32_t idx = lane + 32 * h;
-            bool cap = false;
-            uint32_t qq = 0;
-            if (idx < n) {
-              qq = B[idx];
-              cap = !sm.pend[qq] && ((bits[qq >> 5] >> (qq & 31)) & 1u) && !sm.skip[qq];
-            }
-            const unsigned cm = __ballot_sync(kFullMask, cap);
-            if (cm) q = __shfl_sync(kFullMask, qq, __ffs((int)cm) - 1);
-          }
-        }
-        if (q != 0xffffffffu) clash = __any_sync(kFullMask, p_cap && key_lt(p_cost, p_node, sm.cost[q], q));
-        else clash = __any_sync(kFullMask, p_cap);
-      }
-      PROF(3);
-      if (clash || q == 0xffffffffu) break;  // no capable node at all: the one-job path reports "Resource"
-      // the pick's cost once the job is placed (cost += (end-start) * cpu ratio, JobScheduler.h:46-52)
-      const int64_t tot_cpu = sm.cls[q] != 0xff ? s_classrow[sm.cls[q]].cpu_raw : a.cl.slot_total[base + q].cpu_raw;
-      const double nc = __dadd_rn(sm.cost[q], cost_delta(jq.time_limit, exclusive ? tot_cpu : req_cpu, tot_cpu));
-      if (lane == 0) {
-        s_task[nt].slot = slot;
-        s_task[nt].mode = mode;
-        sm.list[nt] = (uint16_t)q;
-        s_newcost[nt] = nc;
-        sm.pend[q] = 1;
-      }
-      __syncwarp();
-      ++nt;
-      PROF(6);
+      const uint32_t K = s_jobs[slot].node_num;
+      if (K == 0 || K > mp || need + K > (uint32_t)kBatch || need + K + 1 > nw) break;
+      need += K;
+      if (lane == 0) { s_bj[nj].slot = slot; s_bj[nj].K = K; s_bj[nj].need = need; }
+      ++nj;
     }
-
-    bool single = nt == 0;
-    if (nt) {
-      const bool par = mp >= 64;  // the order never runs empty under the parallel inserts
-      if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = nt; s_cmd.first = par ? 1u : 0u; }
-      __syncthreads();                  // the helpers start evaluating
-      bucket_remove_pending(sm, nt);    // meanwhile the picks leave the order
-      __syncthreads();                  // verdicts are in; the order is ready for the inserts
-      uint32_t f = nt;
-      for (uint32_t i = 0; i < nt; ++i)
-        if (!s_ok[i]) { f = i; break; }
-      PROF(9);
-      __syncthreads();                  // commits and re-inserts are done
-      PROF_CNT(13, f);
-      PROF_CNT(14, 1);
-      for (uint32_t t = 0; t < nt; ++t) {
-        if (par && !s_ovf[t]) continue;
-        // serial re-insert: tiny partition, or the target bucket was full
-        const uint32_t q = sm.list[t];
-        const double nc = t < f ? s_newcost[t] : sm.cost[q];
-        if (!bucket_insert(sm, q, nc, sm.bkt[q])) {
-          bucket_rebuild(sm);
-          first_bucket = 0;
-          bucket_insert(sm, q, nc, 0);
+    bool single = nj == 0;
+    if (nj) {
+      while (first_bucket + 1 < sm.nb && sm.bcnt[first_bucket] == 0) ++first_bucket;
+      if (lane == 0) { s_first_bucket = first_bucket; s_cmd.kind = OP_SELECT; s_cmd.n = nj; }
+      __syncthreads();  // helpers list the candidates
+      __syncthreads();  // lists are in
+      PROF(3);
+      // ---- resolve -------------------------------------------------------------
+      uint32_t NT = 0, njr = 0;
+      bool need_single = false;
+      for (uint32_t t = 0; t < nj; ++t) {
+        const BatchJob bj = s_bj[t];
+        const BatchSel& sel = s_sel[t];
+        const uint32_t K = bj.K;
+        // immediate start: the first K free nodes of the pre-filter list
+        uint32_t cq = 0;
+        bool listed = lane < bj.n0, taken = false;
+        if (listed) { cq = sel.c0[lane]; taken = sm.pend[cq] != 0; }
+        unsigned freem = __ballot_sync(kFullMask, listed && !taken), takenm = __ballot_sync(kFullMask, listed && taken);
+        uint32_t mode = 0;
+        bool stop = false;
+        if ((uint32_t)__popc(freem) < K) {
+          if (takenm) {
+            stop = true;  // a taken node may still complete the set once it is updated
+          } else if (K > 1) {
+            stop = true;  // fewer than K candidates in all: a multi-node backfill (one-job path)
+            need_single = t == 0;
+            single_job = ji + t;  // and placing the jobs before it cannot change that
+          } else {
+            // one-node backfill: the first free capable node
+            mode = 1;
+            listed = lane < bj.n1;
+            taken = false;
+            if (listed) { cq = sel.c1[lane]; taken = sm.pend[cq] != 0; }
+            freem = __ballot_sync(kFullMask, listed && !taken);
+            takenm = __ballot_sync(kFullMask, listed && taken);
+            if (!freem) {
+              stop = true;  // taken nodes only: wait for them; none at all: "Resource" on the one-job path
+              need_single = t == 0;
+              if (!takenm) single_job = ji + t;
+            }
+          }
         }
-        if (lane == 0) sm.pend[q] = 0;
+        if (stop) break;
+        // the K chosen: the lowest K bits of freem; `last` = position of the K-th
+        const uint32_t my_rank = (uint32_t)__popc(freem & ((1u << lane) - 1u));
+        const bool chosen = ((freem >> lane) & 1u) && my_rank < K;
+        const unsigned chosenm = __ballot_sync(kFullMask, chosen);
+        const uint32_t last = 31u - (uint32_t)__clz((int)chosenm);
+        const uint32_t q_last = __shfl_sync(kFullMask, cq, (int)last);
+        const double c_last = sm.cost[q_last];
+        // a taken node listed before `last` that sorts before it at its new cost
+        // would be among the first K of the updated order
+        bool clash = false;
+        if (((takenm >> lane) & 1u) && lane < last) clash = key_lt(s_newcost[sm.tmp[cq]], cq, c_last, q_last);
+        if (__any_sync(kFullMask, clash)) break;
+        if (chosen) {
+          const uint32_t w = NT + my_rank;
+          sm.list[w] = (uint16_t)cq;
+          s_newcost[w] = mode ? sel.nc1[lane] : sel.nc0[lane];
+          sm.pend[cq] = 1;
+          sm.tmp[cq] = (uint16_t)w;
+          s_task[w].slot = bj.slot;
+          s_task[w].mode = mode;
+          s_task[w].tfirst = NT;
+        }
         __syncwarp();
+        NT += K;
+        ++njr;
       }
-      PROF(11);
-      ji += f;
-      single = f < nt;
+      PROF(6);
+      if (NT) {
+        const bool par = mp >= 64;  // the order never runs empty under the parallel inserts
+        if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = NT; s_cmd.first = par ? 1u : 0u; }
+        __syncthreads();                  // the helpers start evaluating
+        bucket_remove_pending(sm, NT);    // meanwhile the picks leave the order
+        __syncthreads();                  // verdicts are in; the order is ready for the inserts
+        uint32_t f = NT;
+        for (uint32_t i = 0; i < NT; ++i)
+          if (!s_ok[i]) { f = i; break; }
+        if (f < NT) f = s_task[f].tfirst;
+        PROF(9);
+        __syncthreads();                  // commits and re-inserts are done
+        bool rebuilt = false;
+        for (uint32_t t = 0; t < NT; ++t) {
+          if (par && !s_ovf[t]) continue;
+          // serial re-insert: tiny partition, or the target bucket was full
+          const uint32_t q = sm.list[t];
+          leftover_insert(q, t < f ? s_newcost[t] : sm.cost[q], rebuilt);
+        }
+        // jobs placed = those whose tasks all lie before the cut
+        uint32_t done = 0;
+        for (uint32_t t = 0; t < njr; ++t) done += s_bj[t].need <= f ? 1u : 0u;
+        PROF_CNT(13, done);
+        PROF_CNT(14, 1);
+        PROF(11);
+        BUCKET_CHECK("batch", ji);
+        ji += done;
+        single = f < NT;  // the failing job is next
+      } else {
+        single = need_single || njr == 0;
+      }
     }
     if (single) {
       ensure_issued(ji);
       process_single(ji);
+      BUCKET_CHECK("single", ji);
       ++ji;
     }
   }
