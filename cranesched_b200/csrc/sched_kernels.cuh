@@ -740,6 +740,15 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 
 // ResourceView::GetFeasibleResourceInNode with the concrete pick, one shared
 // out-of-line instance (keeps the per-job instruction footprint small)
+// named barrier among `nthreads` threads (whole warps) of the CTA; id 1..15 (0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+#ifdef CRANE_EMU
+  emu_named_bar((int)id, (int)nthreads, true);
+#else
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
+
 __device__ __noinline__ bool feasible_alloc(const View& req, const Row& avail, Row& alloc) {
   return feasible<true>(req, avail, c_dict, &alloc);
 }
@@ -1166,11 +1175,6 @@ __device__ __forceinline__ bool bucket_insert_t(CommitSmem& sm, uint32_t u, doub
 __device__ __forceinline__ bool bucket_insert(CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
   return bucket_insert_t<false>(sm, u, new_cost, from_bucket);
 }
-// the same, callable by several warps at once for different nodes
-__device__ __noinline__ bool bucket_insert_locked(CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
-  return bucket_insert_t<true>(sm, u, new_cost, from_bucket);
-}
-
 // Deal sm.tmp[0..total) (already in (cost, node) order) out to the buckets,
 // kBucketFill per bucket, and refresh bkt[] and the per-bucket bounds.
 __device__ __noinline__ void bucket_deal(CommitSmem& sm, uint32_t total) {
@@ -1256,14 +1260,13 @@ enum : uint32_t {
   OP_BF_MULTI = 10,  // K <= warps: worker w iterates the common earliest start with the others, then updates
   OP_BATCH_P = 6,    // batch of one-node jobs: worker w evaluates task w (no state change)
   OP_SELECT = 12,    // helper t < n lists the candidates of batch job t
-  OP_REINSERT = 11,  // helper t < n re-inserts list[t] (flagged pend) at s_newcost[t]
   OP_EXIT = 8,
 };
 struct BatchTask {   // one (job, node) pair of the batch in flight; its node is sm.list[w]
   uint32_t slot;     // ring slot of the job
   uint32_t mode;     // 0 = immediate start, 1 = backfill (one-node jobs only)
   uint32_t tfirst;   // first task of the same job (its nodes are list[tfirst .. tfirst + node_num))
-  uint32_t pad;
+  uint32_t job;      // index of the job in the batch
 };
 struct BatchJob {    // one job of the batch being formed
   uint32_t slot;     // ring slot
@@ -1296,6 +1299,7 @@ struct WorkerCtx {  // lives in shared memory; read-only after set-up
   BatchJob* bj;      // [kBatch]
   BatchSel* sel;     // [kBatch]
   const BatchTask* task;         // [kBatch]
+  uint32_t* joblabel;            // [kBatch] "some node is short of resources now" of a multi-node backfill in the batch
   const uint32_t* first_bucket;  // buckets before it are empty
 };
 
@@ -1501,18 +1505,24 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
       start = now;
     }
     if (kind == OP_BF_MULTI) {
-      // common earliest start of the n chosen nodes: every warp keeps its node's
+      // common earliest start of the chosen nodes: every warp keeps its node's
       // timeline in registers and iterates T <- max over nodes of the earliest
-      // fit >= T to the fixed point (JobScheduler.h:806-849), one barrier a round
+      // fit >= T to the fixed point (JobScheduler.h:806-849), one barrier a round.
+      // On the one-job path the nodes are list[0..n) and the barrier is the
+      // CTA's (idle warps follow in multi_idle); inside a batch they are this
+      // job's tasks and the barrier is a named one among just their warps.
+      const uint32_t l0 = batch == 2 ? cx.task[first].tfirst : 0u;
+      const uint32_t cnt = batch == 2 ? K : n;
+      const uint32_t bar_id = batch == 2 ? 1u + cx.task[first].job : 0u;
       int64_t T0 = now;
       ok = false;
       for (uint32_t it = 0;; ++it) {
         const int64_t t = ns <= 64 ? node_earliest(nr, alloc, T0, limit) : node_earliest_big(cx.tl, g, ns, alloc, T0, limit);
         long long* buf = cx.tbuf + (it & 1u) * 32;
         if (lane == 0) buf[first] = t;
-        __syncthreads();
+        if (batch == 2) named_bar_sync(bar_id, cnt * 32u); else __syncthreads();
         int64_t tmax = T0;
-        for (uint32_t i = 0; i < n; ++i) tmax = buf[i] > tmax ? buf[i] : tmax;
+        for (uint32_t i = 0; i < cnt; ++i) tmax = buf[l0 + i] > tmax ? buf[l0 + i] : tmax;
         if (tmax == kInf) break;
         if (tmax == T0) { ok = T0 - now <= cx.max_window; break; }  // JobScheduler.h:809
         T0 = tmax;
@@ -1571,12 +1581,22 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
           cx.out.start_time[jq.job] = start;
           cx.out.end_time[jq.job] = end;
           cx.out.n_alloc[jq.job] = K;
-          cx.out.reason[jq.job] = start == now ? CRANE_REASON_NONE : (short_now ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY);
+          if (K == 1 || start == now)
+            cx.out.reason[jq.job] = start == now ? CRANE_REASON_NONE : (short_now ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY);
+          else if (short_now)
+            atomicOr(&cx.joblabel[cx.task[first].job], 1u);
         } else if (short_now) {
           atomicOr(cx.label, 1u);
         }
       }
       __syncwarp();  // lane 0's shared-memory writes are visible to the whole warp
+      if (batch == 2 && K > 1 && start != now) {
+        // multi-node backfill inside a batch: "Resource" if any of its nodes is
+        // short now, else "Priority" (JobScheduler.cpp:5842-5848)
+        named_bar_sync(1u + cx.task[first].job, K * 32u);
+        if (lane == 0 && first == cx.task[first].tfirst)
+          cx.out.reason[jq.job] = cx.joblabel[cx.task[first].job] ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY;
+      }
     }
   }
   return result;
@@ -1624,10 +1644,10 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   __shared__ BatchJob s_bj[kBatch];
   __shared__ BatchSel s_sel[kBatch];
   __shared__ uint32_t s_first_bucket;
+  __shared__ uint32_t s_joblabel[kBatch];
   __shared__ uint32_t s_ok[32];
   __shared__ long long s_tbuf[2][32];
   __shared__ double s_newcost[kBatch];
-  __shared__ uint32_t s_ovf[kBatch];
   __shared__ WorkerCtx s_cx;
   __shared__ long long s_res[32];   // per-worker result of a multi-warp step
   __shared__ uint32_t s_label;
@@ -1650,7 +1670,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     s_label = 0;
     s_cx.cl = a.cl; s_cx.tl = a.tl; s_cx.out = a.out; s_cx.sm = sm; s_cx.jobs = s_jobs; s_cx.classrow = s_classrow;
     s_cx.label = &s_label; s_cx.ok = s_ok; s_cx.tbuf = &s_tbuf[0][0]; s_cx.now = a.now; s_cx.max_window = a.max_window; s_cx.base = base; s_cx.max_jobs = a.max_jobs;
-    s_cx.words = words; s_cx.bj = s_bj; s_cx.sel = s_sel; s_cx.task = s_task; s_cx.first_bucket = &s_first_bucket;
+    s_cx.words = words; s_cx.bj = s_bj; s_cx.sel = s_sel; s_cx.task = s_task; s_cx.first_bucket = &s_first_bucket; s_cx.joblabel = s_joblabel;
     for (int s = 0; s < kRing; ++s) mbar_init(&s_bar[s], 1);
     fence_mbar_init();
   }
@@ -1690,33 +1710,13 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         const uint32_t t = wid - 1;  // task t of the batch: node sm.list[t], job in ring slot s_task[t].slot
         if (t < c.n) {
           const BatchTask tk = s_task[t];
-          r = worker_step(&s_cx, tk.mode ? OP_BF_K1 : OP_NOW_K1, t + 1, tk.slot, s_cx.now, t, c.n, 2);
-          if (c.first) {
-            // back into the order: at the new cost if the pick was committed
-            const uint32_t q = sm.list[t];
-            const double nc = t < (uint32_t)r ? s_newcost[t] : sm.cost[q];
-            const bool ins = bucket_insert_locked(s_cx.sm, q, nc, sm.bkt[q]);
-            if (lane == 0) {
-              s_ovf[t] = ins ? 0u : 1u;
-              if (ins) sm.pend[q] = 0;
-            }
-          }
+          const uint32_t kind = !tk.mode ? OP_NOW_K1 : (s_jobs[tk.slot].node_num > 1 ? OP_BF_MULTI : OP_BF_K1);
+          r = worker_step(&s_cx, kind, t + 1, tk.slot, s_cx.now, t, c.n, 2);
         } else {
           __syncthreads();  // the verdict barrier inside the batch step
         }
       } else if (c.kind == OP_SELECT) {
         if (wid - 1 < c.n) select_step(&s_cx, wid - 1);
-      } else if (c.kind == OP_REINSERT) {
-        const uint32_t t = wid - 1;
-        if (t < c.n) {
-          const uint32_t q = sm.list[t];
-          bool ins = true;
-          if (sm.pend[q]) ins = bucket_insert_locked(s_cx.sm, q, s_newcost[t], sm.bkt[q]);
-          if (lane == 0) {
-            s_ovf[t] = ins ? 0u : 1u;
-            if (ins) sm.pend[q] = 0;
-          }
-        }
       } else if (c.kind == OP_NOW_MULTI || c.kind == OP_BF_MULTI) {
         if (wid < c.n) r = worker_step(&s_cx, c.kind, c.n, c.slot, c.t0, wid, 1, 0);
         else multi_idle(&s_cx, c.kind, c.n);
@@ -2067,35 +2067,14 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       }
       // cost += (end-start) * cpu ratio (JobScheduler.h:46-52); the allocation's
       // cpu is the job's per-node request, or the node total for exclusive jobs
-      if (K > 1 && K <= (uint32_t)kBatch && K < nw && mp >= 64) {
-        // the K nodes move in parallel: out of the order in one pass per bucket,
-        // back in by one helper each
-        if (lane < K) {
-          const uint32_t q = sm.list[lane];
-          const int64_t tot_cpu = sm.cls[q] != 0xff ? s_classrow[sm.cls[q]].cpu_raw : a.cl.slot_total[base + q].cpu_raw;
-          const double oc = sm.cost[q];
-          const double nc = __dadd_rn(oc, cost_delta(limit, exclusive ? tot_cpu : req_cpu, tot_cpu));
-          s_newcost[lane] = nc;
-          if (nc > oc) sm.pend[q] = 1;
-        }
-        __syncwarp();
-        bucket_remove_pending(sm, K);
-        if (lane == 0) { s_cmd.kind = OP_REINSERT; s_cmd.n = K; }
-        __syncthreads();
-        __syncthreads();
-        bool rebuilt = false;
-        for (uint32_t t = 0; t < K; ++t)
-          if (s_ovf[t]) leftover_insert(sm.list[t], s_newcost[t], rebuilt);
-      } else {
 #pragma unroll 1
-        for (uint32_t k = 0; k < K; ++k) {
-          const uint32_t q = sm.list[k];
-          const int64_t tot_cpu = sm.cls[q] != 0xff ? s_classrow[sm.cls[q]].cpu_raw : a.cl.slot_total[base + q].cpu_raw;
-          const double delta = cost_delta(limit, exclusive ? tot_cpu : req_cpu, tot_cpu);
-          const double oc = sm.cost[q];
-          const double nc = __dadd_rn(oc, delta);
-          if (nc > oc) rekey(q, nc, sm.bkt[q]);
-        }
+      for (uint32_t k = 0; k < K; ++k) {
+        const uint32_t q = sm.list[k];
+        const int64_t tot_cpu = sm.cls[q] != 0xff ? s_classrow[sm.cls[q]].cpu_raw : a.cl.slot_total[base + q].cpu_raw;
+        const double delta = cost_delta(limit, exclusive ? tot_cpu : req_cpu, tot_cpu);
+        const double oc = sm.cost[q];
+        const double nc = __dadd_rn(oc, delta);
+        if (nc > oc) rekey(q, nc, sm.bkt[q]);
       }
       PROF(7);
     } else {
@@ -2161,20 +2140,16 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         if ((uint32_t)__popc(freem) < K) {
           if (takenm) {
             stop = true;  // a taken node may still complete the set once it is updated
-          } else if (K > 1) {
-            stop = true;  // fewer than K candidates in all: a multi-node backfill (one-job path)
-            need_single = t == 0;
-            single_job = ji + t;  // and placing the jobs before it cannot change that
           } else {
-            // one-node backfill: the first free capable node
+            // fewer than K candidates in all: backfill on the first K free capable nodes
             mode = 1;
             listed = lane < bj.n1;
             taken = false;
             if (listed) { cq = sel.c1[lane]; taken = sm.pend[cq] != 0; }
             freem = __ballot_sync(kFullMask, listed && !taken);
             takenm = __ballot_sync(kFullMask, listed && taken);
-            if (!freem) {
-              stop = true;  // taken nodes only: wait for them; none at all: "Resource" on the one-job path
+            if ((uint32_t)__popc(freem) < K) {
+              stop = true;  // taken nodes: wait for them; too few capable nodes at all: "Resource" on the one-job path
               need_single = t == 0;
               if (!takenm) single_job = ji + t;
             }
@@ -2202,31 +2177,35 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
           s_task[w].slot = bj.slot;
           s_task[w].mode = mode;
           s_task[w].tfirst = NT;
+          s_task[w].job = t;
         }
+        if (lane == 0) s_joblabel[t] = 0;
         __syncwarp();
         NT += K;
         ++njr;
       }
       PROF(6);
       if (NT) {
-        const bool par = mp >= 64;  // the order never runs empty under the parallel inserts
-        if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = NT; s_cmd.first = par ? 1u : 0u; }
+        if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = NT; }
         __syncthreads();                  // the helpers start evaluating
         bucket_remove_pending(sm, NT);    // meanwhile the picks leave the order
-        __syncthreads();                  // verdicts are in; the order is ready for the inserts
+        __syncthreads();                  // verdicts are in
         uint32_t f = NT;
         for (uint32_t i = 0; i < NT; ++i)
           if (!s_ok[i]) { f = i; break; }
         if (f < NT) f = s_task[f].tfirst;
         PROF(9);
-        __syncthreads();                  // commits and re-inserts are done
+        // while the helpers commit, every picked node goes back into the order: at
+        // its new cost if its job is placed, where it was otherwise. (The bucket
+        // bounds read cpu0/gcnt while a commit may be lowering them: either value
+        // is a valid upper bound.)
         bool rebuilt = false;
         for (uint32_t t = 0; t < NT; ++t) {
-          if (par && !s_ovf[t]) continue;
-          // serial re-insert: tiny partition, or the target bucket was full
           const uint32_t q = sm.list[t];
           leftover_insert(q, t < f ? s_newcost[t] : sm.cost[q], rebuilt);
         }
+        PROF(10);
+        __syncthreads();                  // commits are done
         // jobs placed = those whose tasks all lie before the cut
         uint32_t done = 0;
         for (uint32_t t = 0; t < njr; ++t) done += s_bj[t].need <= f ? 1u : 0u;
