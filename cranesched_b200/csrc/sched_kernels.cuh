@@ -660,7 +660,8 @@ constexpr int kRing = 16;            // prefetch ring depth (jobs)
 #define CRANE_COMMIT_THREADS 288
 #endif
 constexpr int kCommitThreads = CRANE_COMMIT_THREADS;  // CTA size of k_commit: driver warp + helpers
-constexpr int kBatch = kCommitThreads / 32 - 1;       // one-node jobs dispatched together (one helper warp each)
+constexpr int kBatch = kCommitThreads / 32 - 1;       // nodes of the jobs dispatched together (one helper warp each)
+static_assert(kBatch >= 1 && kBatch <= 8, "the resolve step lays 8 jobs x 4 lanes over one warp");
 constexpr int kBucket = 64;          // bucket capacity of the cost order
 constexpr int kBucketFill = 32;      // entries per bucket after a (re)build
 
@@ -1645,6 +1646,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   __shared__ BatchSel s_sel[kBatch];
   __shared__ uint32_t s_first_bucket;
   __shared__ uint32_t s_joblabel[kBatch];
+  __shared__ __align__(16) uint16_t s_pick[2][8];
   __shared__ uint32_t s_ok[32];
   __shared__ long long s_tbuf[2][32];
   __shared__ double s_newcost[kBatch];
@@ -2104,17 +2106,27 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   while (ji < njobs) {
     ensure_issued(ji);
     PROF(1);
-    // ---- form the batch ------------------------------------------------------
-    uint32_t nj = 0, need = 0;
-    while (nj < (uint32_t)kBatch && nj + 1 < nw && ji + nj < njobs && ji + nj != single_job) {
-      const uint32_t j = ji + nj;
-      const uint32_t slot = j % kRing;
-      mbar_wait(&s_bar[slot], (j / kRing) & 1u);
-      const uint32_t K = s_jobs[slot].node_num;
-      if (K == 0 || K > mp || need + K > (uint32_t)kBatch || need + K + 1 > nw) break;
-      need += K;
-      if (lane == 0) { s_bj[nj].slot = slot; s_bj[nj].K = K; s_bj[nj].need = need; }
-      ++nj;
+    // ---- form the batch: lanes 0..kBatch-1 look at one job each ---------------
+    uint32_t nj = 0;
+    {
+      uint32_t myK = 0, myslot = 0;
+      bool okj = false;
+      if (lane < (uint32_t)kBatch && lane + 1 < nw && ji + lane < njobs && ji + lane != single_job) {
+        const uint32_t j = ji + lane;
+        myslot = j % kRing;
+        mbar_wait(&s_bar[myslot], (j / kRing) & 1u);
+        myK = s_jobs[myslot].node_num;
+        okj = myK >= 1 && myK <= mp && myK <= (uint32_t)kBatch;
+      }
+      uint32_t cum = myK;  // inclusive prefix sum of node_num over the lanes
+      for (int o = 1; o < kBatch; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(kFullMask, cum, o);
+        if ((int)lane >= o) cum += up;
+      }
+      const unsigned good = __ballot_sync(kFullMask, okj && cum <= (uint32_t)kBatch && cum + 1 <= nw);
+      nj = (uint32_t)__ffs((int)~good) - 1u;  // leading run of jobs that fit
+      if (lane < nj) { s_bj[lane].slot = myslot; s_bj[lane].K = myK; s_bj[lane].need = cum; }
+      __syncwarp();
     }
     bool single = nj == 0;
     if (nj) {
@@ -2123,67 +2135,139 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       __syncthreads();  // helpers list the candidates
       __syncthreads();  // lists are in
       PROF(3);
-      // ---- resolve -------------------------------------------------------------
-      uint32_t NT = 0, njr = 0;
-      bool need_single = false;
-      for (uint32_t t = 0; t < nj; ++t) {
-        const BatchJob bj = s_bj[t];
-        const BatchSel& sel = s_sel[t];
-        const uint32_t K = bj.K;
-        // immediate start: the first K free nodes of the pre-filter list
-        uint32_t cq = 0;
-        bool listed = lane < bj.n0, taken = false;
-        if (listed) { cq = sel.c0[lane]; taken = sm.pend[cq] != 0; }
-        unsigned freem = __ballot_sync(kFullMask, listed && !taken), takenm = __ballot_sync(kFullMask, listed && taken);
-        uint32_t mode = 0;
-        bool stop = false;
-        if ((uint32_t)__popc(freem) < K) {
-          if (takenm) {
-            stop = true;  // a taken node may still complete the set once it is updated
-          } else {
-            // fewer than K candidates in all: backfill on the first K free capable nodes
-            mode = 1;
-            listed = lane < bj.n1;
-            taken = false;
-            if (listed) { cq = sel.c1[lane]; taken = sm.pend[cq] != 0; }
-            freem = __ballot_sync(kFullMask, listed && !taken);
-            takenm = __ballot_sync(kFullMask, listed && taken);
-            if ((uint32_t)__popc(freem) < K) {
-              stop = true;  // taken nodes: wait for them; too few capable nodes at all: "Resource" on the one-job path
-              need_single = t == 0;
-              if (!takenm) single_job = ji + t;
-            }
+      // ---- resolve: 4 lanes per job, 2 entries of each list per lane --------------
+      // In job order each job takes its first K free candidates; "free" depends on
+      // what the jobs before it took. Solved as a fixed point over all jobs at once:
+      // every job recomputes its picks against the others' previous picks; job t is
+      // final after round t+1. The first guess — job t skips as many entries as the
+      // jobs before it need — is already the answer when the lists coincide.
+      const uint32_t rt = lane >> 2, rk = lane & 3u, rg = lane & ~3u;
+      const bool ract = rt < nj;
+      uint32_t rK = 0, rfirst = 0, rslot = 0, rn0 = 0, rn1 = 0, rneed = 0;
+      uint32_t c0a = 0xffffu, c0b = 0xffffu, c1a = 0xffffu, c1b = 0xffffu;
+      if (ract) {
+        const BatchJob bj = s_bj[rt];
+        rK = bj.K; rneed = bj.need; rfirst = bj.need - bj.K; rslot = bj.slot; rn0 = bj.n0; rn1 = bj.n1;
+        const BatchSel& sel = s_sel[rt];
+        if (2 * rk < rn0) c0a = sel.c0[2 * rk];
+        if (2 * rk + 1 < rn0) c0b = sel.c0[2 * rk + 1];
+        if (2 * rk < rn1) c1a = sel.c1[2 * rk];
+        if (2 * rk + 1 < rn1) c1b = sel.c1[2 * rk + 1];
+      }
+      if (lane < (uint32_t)kBatch) s_pick[0][lane] = 0xffffu;
+      __syncwarp();
+      if (ract) {
+        // first guess: entries [rfirst, rfirst + K) of the list that is long enough
+        const bool use0 = rn0 >= rneed, use1 = !use0 && rn0 == 0 && rn1 >= rneed;
+        for (uint32_t e = 0; e < 2; ++e) {
+          const uint32_t i = 2 * rk + e;
+          if (i >= rfirst && i < rfirst + rK) {
+            if (use0) s_pick[0][i] = (uint16_t)(e ? c0b : c0a);
+            else if (use1) s_pick[0][i] = (uint16_t)(e ? c1b : c1a);
           }
         }
-        if (stop) break;
-        // the K chosen: the lowest K bits of freem; `last` = position of the K-th
-        const uint32_t my_rank = (uint32_t)__popc(freem & ((1u << lane) - 1u));
-        const bool chosen = ((freem >> lane) & 1u) && my_rank < K;
-        const unsigned chosenm = __ballot_sync(kFullMask, chosen);
-        const uint32_t last = 31u - (uint32_t)__clz((int)chosenm);
-        const uint32_t q_last = __shfl_sync(kFullMask, cq, (int)last);
-        const double c_last = sm.cost[q_last];
-        // a taken node listed before `last` that sorts before it at its new cost
-        // would be among the first K of the updated order
-        bool clash = false;
-        if (((takenm >> lane) & 1u) && lane < last) clash = key_lt(s_newcost[sm.tmp[cq]], cq, c_last, q_last);
-        if (__any_sync(kFullMask, clash)) break;
-        if (chosen) {
-          const uint32_t w = NT + my_rank;
-          sm.list[w] = (uint16_t)cq;
-          s_newcost[w] = mode ? sel.nc1[lane] : sel.nc0[lane];
-          sm.pend[cq] = 1;
-          sm.tmp[cq] = (uint16_t)w;
-          s_task[w].slot = bj.slot;
-          s_task[w].mode = mode;
-          s_task[w].tfirst = NT;
-          s_task[w].job = t;
-        }
-        if (lane == 0) s_joblabel[t] = 0;
-        __syncwarp();
-        NT += K;
-        ++njr;
       }
+      uint32_t cur = 0, rmode = 0, rstop = 0;
+      bool cha = false, chb = false;                   // my entries (of the active list) are chosen
+      uint32_t ranka = 0, rankb = 0;                   // ... as the job's ranka-th / rankb-th node
+      bool ta = false, tb = false;                     // my entries of the active list are taken by an earlier job
+      uint32_t sa = 0, sb = 0;                         // ... as its task sa / sb
+      uint32_t chosen8 = 0;
+      for (uint32_t round = 0; round < (uint32_t)kBatch + 2; ++round) {
+        __syncwarp();
+        const uint4 pk = *reinterpret_cast<const uint4*>(s_pick[cur]);
+        if (lane < (uint32_t)kBatch) s_pick[cur ^ 1u][lane] = 0xffffu;
+        __syncwarp();
+        const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+        bool t0a = false, t0b = false, t1a = false, t1b = false;
+        uint32_t s0a = 0, s0b = 0, s1a = 0, s1b = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < (uint32_t)kBatch; ++w) {
+          const uint32_t v = (pw[w >> 1] >> (16u * (w & 1u))) & 0xffffu;
+          const bool earlier = w < rfirst;  // tasks before mine belong to the jobs before mine
+          if (earlier && v == c0a && c0a != 0xffffu) { t0a = true; s0a = w; }
+          if (earlier && v == c0b && c0b != 0xffffu) { t0b = true; s0b = w; }
+          if (earlier && v == c1a && c1a != 0xffffu) { t1a = true; s1a = w; }
+          if (earlier && v == c1b && c1b != 0xffffu) { t1b = true; s1b = w; }
+        }
+        const unsigned f0a = __ballot_sync(kFullMask, c0a != 0xffffu && !t0a), f0b = __ballot_sync(kFullMask, c0b != 0xffffu && !t0b);
+        const unsigned f1a = __ballot_sync(kFullMask, c1a != 0xffffu && !t1a), f1b = __ballot_sync(kFullMask, c1b != 0xffffu && !t1b);
+        const unsigned tk0 = __ballot_sync(kFullMask, t0a || t0b), tk1 = __ballot_sync(kFullMask, t1a || t1b);
+        // bit i of free8 = entry i of the list is free: entry 2k+e sits in lane rg+k, ballot e
+        auto spread = [](uint32_t x) { return (x & 1u) | ((x & 2u) << 1) | ((x & 4u) << 2) | ((x & 8u) << 3); };
+        const uint32_t free0 = spread((f0a >> rg) & 0xFu) | (spread((f0b >> rg) & 0xFu) << 1);
+        const uint32_t free1 = spread((f1a >> rg) & 0xFu) | (spread((f1b >> rg) & 0xFu) << 1);
+        const bool any_t0 = ((tk0 >> rg) & 0xFu) != 0, any_t1 = ((tk1 >> rg) & 0xFu) != 0;
+        uint32_t fm = 0;
+        rmode = 0; rstop = 0;
+        if ((uint32_t)__popc(free0) >= rK) {
+          fm = free0;                    // immediate start on the first K free pre-filter candidates
+        } else if (any_t0) {
+          rstop = 1;                     // a taken node may still complete the set once it is updated
+        } else {
+          rmode = 1;                     // fewer than K candidates in all: backfill on the first K free capable nodes
+          if ((uint32_t)__popc(free1) >= rK) fm = free1;
+          else rstop = any_t1 ? 1u : 2u; // wait for the taken ones / too few capable nodes at all ("Resource", one-job path)
+        }
+        if (!ract) { rstop = 1; fm = 0; }
+        const uint32_t ia = 2 * rk, ib = 2 * rk + 1;
+        ranka = (uint32_t)__popc(fm & ((1u << ia) - 1u));
+        rankb = (uint32_t)__popc(fm & ((1u << ib) - 1u));
+        cha = !rstop && ((fm >> ia) & 1u) && ranka < rK;
+        chb = !rstop && ((fm >> ib) & 1u) && rankb < rK;
+        chosen8 = 0;
+        if (!rstop) { chosen8 = fm; while ((uint32_t)__popc(chosen8) > rK) chosen8 &= ~(1u << (31 - __clz((int)chosen8))); }
+        ta = rmode ? t1a : t0a; tb = rmode ? t1b : t0b;
+        sa = rmode ? s1a : s0a; sb = rmode ? s1b : s0b;
+        if (cha) s_pick[cur ^ 1u][rfirst + ranka] = (uint16_t)(rmode ? c1a : c0a);
+        if (chb) s_pick[cur ^ 1u][rfirst + rankb] = (uint16_t)(rmode ? c1b : c0b);
+        __syncwarp();
+        bool changed = false;
+        if (lane < (uint32_t)kBatch) changed = s_pick[cur ^ 1u][lane] != ((pw[lane >> 1] >> (16u * (lane & 1u))) & 0xffffu);
+        cur ^= 1u;
+        if (!__any_sync(kFullMask, changed)) break;
+      }
+      // tasks: node, new cost, job
+      const uint32_t na = rmode ? c1a : c0a, nb_ = rmode ? c1b : c0b;
+      if (cha) {
+        const uint32_t w = rfirst + ranka;
+        sm.list[w] = (uint16_t)na;
+        s_newcost[w] = rmode ? s_sel[rt].nc1[2 * rk] : s_sel[rt].nc0[2 * rk];
+        s_task[w].slot = rslot; s_task[w].mode = rmode; s_task[w].tfirst = rfirst; s_task[w].job = rt;
+      }
+      if (chb) {
+        const uint32_t w = rfirst + rankb;
+        sm.list[w] = (uint16_t)nb_;
+        s_newcost[w] = rmode ? s_sel[rt].nc1[2 * rk + 1] : s_sel[rt].nc0[2 * rk + 1];
+        s_task[w].slot = rslot; s_task[w].mode = rmode; s_task[w].tfirst = rfirst; s_task[w].job = rt;
+      }
+      if (lane < (uint32_t)kBatch) s_joblabel[lane] = 0;
+      __syncwarp();
+      // a taken node listed before my job's last pick that sorts before it at its
+      // new cost would be among the first K of the updated order: the job has to
+      // wait for that node's update
+      bool clash = false;
+      if (!rstop && chosen8) {
+        const uint32_t lastbit = 31u - (uint32_t)__clz((int)chosen8);
+        const uint32_t q_last = __shfl_sync(kFullMask, (lastbit & 1u) ? nb_ : na, (int)(rg + (lastbit >> 1)));
+        const double c_last = sm.cost[q_last];
+        if (ta && 2 * rk < lastbit) clash = key_lt(s_newcost[sa], na, c_last, q_last);
+        if (tb && 2 * rk + 1 < lastbit) clash = clash || key_lt(s_newcost[sb], nb_, c_last, q_last);
+      } else {
+        __shfl_sync(kFullMask, 0u, 0);
+      }
+      const unsigned badm = __ballot_sync(kFullMask, rstop != 0 || clash);
+      const uint32_t njr = ((uint32_t)__ffs((int)badm) - 1u) >> 2;  // jobs before the first one that has to wait (lanes of jobs >= nj are "bad")
+      const uint32_t stop_cut = __shfl_sync(kFullMask, rstop, (int)((njr < (uint32_t)kBatch ? njr : 0u) * 4u));
+      bool need_single = false;
+      if (njr < nj && stop_cut == 2u) {
+        single_job = ji + njr;  // placing the jobs before it cannot change that
+        need_single = njr == 0;
+      }
+      const uint32_t NT = njr ? __shfl_sync(kFullMask, rneed, (int)((njr - 1u) * 4u)) : 0u;
+      if (cha && rt < njr) sm.pend[na] = 1;
+      if (chb && rt < njr) sm.pend[nb_] = 1;
+      __syncwarp();
       PROF(6);
       if (NT) {
         if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = NT; }
