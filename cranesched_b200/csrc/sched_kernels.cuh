@@ -2247,17 +2247,19 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       // new cost would be among the first K of the updated order: the job has to
       // wait for that node's update
       bool clash = false;
-      if (!rstop && chosen8) {
-        const uint32_t lastbit = 31u - (uint32_t)__clz((int)chosen8);
+      {
+        const bool live = !rstop && chosen8 != 0;
+        const uint32_t lastbit = live ? 31u - (uint32_t)__clz((int)chosen8) : 0u;
         const uint32_t q_last = __shfl_sync(kFullMask, (lastbit & 1u) ? nb_ : na, (int)(rg + (lastbit >> 1)));
-        const double c_last = sm.cost[q_last];
-        if (ta && 2 * rk < lastbit) clash = key_lt(s_newcost[sa], na, c_last, q_last);
-        if (tb && 2 * rk + 1 < lastbit) clash = clash || key_lt(s_newcost[sb], nb_, c_last, q_last);
-      } else {
-        __shfl_sync(kFullMask, 0u, 0);
+        if (live) {
+          const double c_last = sm.cost[q_last];
+          if (ta && 2 * rk < lastbit) clash = key_lt(s_newcost[sa], na, c_last, q_last);
+          if (tb && 2 * rk + 1 < lastbit) clash = clash || key_lt(s_newcost[sb], nb_, c_last, q_last);
+        }
       }
       const unsigned badm = __ballot_sync(kFullMask, rstop != 0 || clash);
-      const uint32_t njr = ((uint32_t)__ffs((int)badm) - 1u) >> 2;  // jobs before the first one that has to wait (lanes of jobs >= nj are "bad")
+      // jobs before the first one that has to wait (lanes of jobs >= nj are "bad")
+      const uint32_t njr = badm ? ((uint32_t)__ffs((int)badm) - 1u) >> 2 : nj;
       const uint32_t stop_cut = __shfl_sync(kFullMask, rstop, (int)((njr < (uint32_t)kBatch ? njr : 0u) * 4u));
       bool need_single = false;
       if (njr < nj && stop_cut == 2u) {
