@@ -656,8 +656,10 @@ struct CommitArgs {
 };
 
 constexpr int kRing = 16;            // prefetch ring depth (jobs)
+// Registers are handed out per group of 4 warps, so 9 warps cost as much as 12
+// (168 registers per thread, spills); 8 warps leave 255.
 #ifndef CRANE_COMMIT_THREADS
-#define CRANE_COMMIT_THREADS 288
+#define CRANE_COMMIT_THREADS 256
 #endif
 constexpr int kCommitThreads = CRANE_COMMIT_THREADS;  // CTA size of k_commit: driver warp + helpers
 constexpr int kBatch = kCommitThreads / 32 - 1;       // nodes of the jobs dispatched together (one helper warp each)
