@@ -1178,6 +1178,114 @@ __device__ __forceinline__ bool bucket_insert_t(CommitSmem& sm, uint32_t u, doub
 __device__ __forceinline__ bool bucket_insert(CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
   return bucket_insert_t<false>(sm, u, new_cost, from_bucket);
 }
+// Puts the nodes list[0..np) back into the order at the costs key[0..np) — all
+// of them at once: one sweep over the buckets' last keys finds every node's
+// bucket (the first non-empty bucket whose last key is not below the node's
+// key, else the last non-empty one), then every touched bucket is merged with
+// its newcomers in one pass. Returns the mask of nodes whose bucket had no room
+// (the caller re-deals the order and inserts them one by one). Driver warp.
+__device__ __noinline__ uint32_t bucket_insert_batch(CommitSmem& sm, uint32_t np, const double* key, uint32_t fb) {
+  const uint32_t lane = lane_id();
+  uint32_t u[kBatch], tb[kBatch];
+  double k[kBatch];
+#pragma unroll
+  for (int w = 0; w < kBatch; ++w) {
+    u[w] = (uint32_t)w < np ? (uint32_t)sm.list[w] : 0u;
+    k[w] = (uint32_t)w < np ? key[w] : 0.0;
+    tb[w] = 0xffffffffu;
+  }
+  uint32_t last_nonempty = 0xffffffffu;
+  for (uint32_t b0 = fb; b0 < sm.nb; b0 += 32) {
+    const uint32_t b = b0 + lane;
+    const uint32_t o = b < sm.nb ? (uint32_t)sm.blast[b] : 0xffffu;
+    const bool nonempty = o != 0xffffu;
+    const double co = nonempty ? sm.cost[o] : 0.0;
+    const unsigned mn = __ballot_sync(kFullMask, nonempty);
+    if (mn) last_nonempty = b0 + 31u - (uint32_t)__clz((int)mn);
+    bool all = true;
+#pragma unroll
+    for (int w = 0; w < kBatch; ++w) {
+      if ((uint32_t)w < np && tb[w] == 0xffffffffu) {
+        const unsigned mg = __ballot_sync(kFullMask, nonempty && !key_lt(co, o, k[w], u[w]));
+        if (mg) tb[w] = b0 + (uint32_t)__ffs((int)mg) - 1u;
+        else all = false;
+      }
+    }
+    if (all) break;
+  }
+#pragma unroll
+  for (int w = 0; w < kBatch; ++w)
+    if ((uint32_t)w < np && tb[w] == 0xffffffffu) tb[w] = last_nonempty != 0xffffffffu ? last_nonempty : fb;
+  uint32_t todo = np >= 32 ? 0xffffffffu : (1u << np) - 1u, overflow = 0;
+  while (todo) {
+    // the bucket of the lowest pending node, and everybody else going there
+    uint32_t t = 0, members = 0;
+#pragma unroll
+    for (int w = 0; w < kBatch; ++w)
+      if (((todo & (0u - todo)) >> w) & 1u) t = tb[w];
+#pragma unroll
+    for (int w = 0; w < kBatch; ++w)
+      if (((todo >> w) & 1u) && tb[w] == t) members |= 1u << w;
+    todo &= ~members;
+    uint16_t* B = sm.bk + (size_t)t * kBucket;
+    const uint32_t n = sm.bcnt[t], m = (uint32_t)__popc(members);
+    if (n + m > (uint32_t)kBucket) { overflow |= members; continue; }
+    const uint32_t e0 = lane < n ? (uint32_t)B[lane] : 0xffffu, e1 = lane + 32 < n ? (uint32_t)B[lane + 32] : 0xffffu;
+    const double ce0 = lane < n ? sm.cost[e0] : 0.0, ce1 = lane + 32 < n ? sm.cost[e1] : 0.0;
+    uint32_t sh0 = 0, sh1 = 0;      // newcomers that sort before my entries
+    uint32_t mypos = 0;             // lane w: final index of newcomer w
+#pragma unroll
+    for (int w = 0; w < kBatch; ++w) {
+      if ((members >> w) & 1u) {
+        const bool lt0 = lane < n && key_lt(ce0, e0, k[w], u[w]);
+        const bool lt1 = lane + 32 < n && key_lt(ce1, e1, k[w], u[w]);
+        if (lane < n && !lt0) ++sh0;
+        if (lane + 32 < n && !lt1) ++sh1;
+        uint32_t pos = (uint32_t)__popc(__ballot_sync(kFullMask, lt0)) + (uint32_t)__popc(__ballot_sync(kFullMask, lt1));
+#pragma unroll
+        for (int v = 0; v < kBatch; ++v)
+          if (v != w && ((members >> v) & 1u) && key_lt(k[v], u[v], k[w], u[w])) ++pos;
+        if (lane == (uint32_t)w) mypos = pos;
+      }
+    }
+    // every load of the old entries is done (the ballots above depend on them)
+    if (lane < n) B[lane + sh0] = (uint16_t)e0;
+    if (lane + 32 < n) B[lane + 32 + sh1] = (uint16_t)e1;
+    long long mc = INT64_MIN, mcg = INT64_MIN;
+    unsigned long long mg = 0;
+    if (lane < (uint32_t)kBatch && ((members >> lane) & 1u)) {
+      uint32_t uu = 0;
+      double kk = 0.0;
+#pragma unroll
+      for (int w = 0; w < kBatch; ++w)
+        if (lane == (uint32_t)w) { uu = u[w]; kk = k[w]; }
+      B[mypos] = (uint16_t)uu;
+      sm.bkt[uu] = (uint16_t)t;
+      sm.cost[uu] = kk;
+      mc = sm.cpu0[uu];
+      mg = sm.gcnt[uu];
+      if (mg) mcg = mc;
+    }
+    for (int o = 4; o > 0; o >>= 1) {  // newcomers sit in lanes 0..7
+      const long long oc = __shfl_xor_sync(kFullMask, mc, o), ocg = __shfl_xor_sync(kFullMask, mcg, o);
+      mc = oc > mc ? oc : mc;
+      mcg = ocg > mcg ? ocg : mcg;
+      mg = vmax8(mg, __shfl_xor_sync(kFullMask, mg, o));
+    }
+    __syncwarp();
+    if (lane == 0) {
+      sm.bcnt[t] = (uint16_t)(n + m);
+      sm.blast[t] = B[n + m - 1];
+      if (mc > sm.bmax_cpu[t]) sm.bmax_cpu[t] = mc;
+      if (mcg > sm.bmax_cpug[t]) sm.bmax_cpug[t] = mcg;
+      sm.bmax_g[t] = vmax8(sm.bmax_g[t], mg);
+      sm.bexact[t] = 0;
+    }
+    __syncwarp();
+  }
+  return overflow;
+}
+
 // Deal sm.tmp[0..total) (already in (cost, node) order) out to the buckets,
 // kBucketFill per bucket, and refresh bkt[] and the per-bucket bounds.
 __device__ __noinline__ void bucket_deal(CommitSmem& sm, uint32_t total) {
@@ -1696,7 +1804,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   const uint32_t r_begin = a.part_job_off[part], r_end = a.part_job_off[part + 1];
   const uint32_t njobs = r_end - r_begin;
   const uint32_t row_bytes = words * 4;
-  auto issue = [&](uint32_t i) {  // driver lane 0
+  auto issue = [&](uint32_t i) {  // one driver lane per record
     const uint32_t slot = i % kRing;
     mbar_expect_tx(&s_bar[slot], (uint32_t)sizeof(JobQ) + row_bytes);
     tma_load_1d(&s_jobs[slot], &a.jobq[r_begin + i], (uint32_t)sizeof(JobQ), &s_bar[slot]);
@@ -1756,9 +1864,10 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
 
   // ring slot of job i is free once job i-kRing is finished
   auto ensure_issued = [&](uint32_t finished) {
-    while (issued < njobs && issued < finished + (uint32_t)kRing) {
-      if (lane == 0) issue(issued);
-      ++issued;
+    const uint32_t hi = njobs < finished + (uint32_t)kRing ? njobs : finished + (uint32_t)kRing;
+    if (issued < hi) {  // at most kRing <= 32 records: one lane each
+      if (issued + lane < hi) issue(issued + lane);
+      issued = hi;
     }
     __syncwarp();
   };
@@ -2137,100 +2246,81 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       __syncthreads();  // helpers list the candidates
       __syncthreads();  // lists are in
       PROF(3);
-      // ---- resolve: 4 lanes per job, 2 entries of each list per lane --------------
+      // ---- resolve: 4 lanes per job, 2 list entries per lane -----------------------
       // In job order each job takes its first K free candidates; "free" depends on
       // what the jobs before it took. Solved as a fixed point over all jobs at once:
       // every job recomputes its picks against the others' previous picks; job t is
       // final after round t+1. The first guess — job t skips as many entries as the
       // jobs before it need — is already the answer when the lists coincide.
+      // A job with fewer than K pre-filter candidates in all can only be backfilled
+      // (taken nodes lose resources, they do not gain candidates), so its list is the
+      // capable one from the start.
       const uint32_t rt = lane >> 2, rk = lane & 3u, rg = lane & ~3u;
       const bool ract = rt < nj;
-      uint32_t rK = 0, rfirst = 0, rslot = 0, rn0 = 0, rn1 = 0, rneed = 0;
-      uint32_t c0a = 0xffffu, c0b = 0xffffu, c1a = 0xffffu, c1b = 0xffffu;
+      uint32_t rK = 0, rfirst = 0, rslot = 0, rneed = 0, rmode = 0, rnl = 0;
+      uint32_t ca = 0xffffu, cb = 0xffffu;
       if (ract) {
         const BatchJob bj = s_bj[rt];
-        rK = bj.K; rneed = bj.need; rfirst = bj.need - bj.K; rslot = bj.slot; rn0 = bj.n0; rn1 = bj.n1;
-        const BatchSel& sel = s_sel[rt];
-        if (2 * rk < rn0) c0a = sel.c0[2 * rk];
-        if (2 * rk + 1 < rn0) c0b = sel.c0[2 * rk + 1];
-        if (2 * rk < rn1) c1a = sel.c1[2 * rk];
-        if (2 * rk + 1 < rn1) c1b = sel.c1[2 * rk + 1];
+        rK = bj.K; rneed = bj.need; rfirst = bj.need - bj.K; rslot = bj.slot;
+        rmode = bj.n0 < bj.K ? 1u : 0u;
+        rnl = rmode ? bj.n1 : bj.n0;
+        const uint16_t* L = rmode ? s_sel[rt].c1 : s_sel[rt].c0;
+        if (2 * rk < rnl) ca = L[2 * rk];
+        if (2 * rk + 1 < rnl) cb = L[2 * rk + 1];
       }
-      if (lane < (uint32_t)kBatch) s_pick[0][lane] = 0xffffu;
+      if (lane < 8) s_pick[0][lane] = 0xffffu;
       __syncwarp();
-      if (ract) {
-        // first guess: entries [rfirst, rfirst + K) of the list that is long enough
-        const bool use0 = rn0 >= rneed, use1 = !use0 && rn0 == 0 && rn1 >= rneed;
-        for (uint32_t e = 0; e < 2; ++e) {
-          const uint32_t i = 2 * rk + e;
-          if (i >= rfirst && i < rfirst + rK) {
-            if (use0) s_pick[0][i] = (uint16_t)(e ? c0b : c0a);
-            else if (use1) s_pick[0][i] = (uint16_t)(e ? c1b : c1a);
-          }
-        }
+      if (ract && rnl >= rneed) {  // first guess: entries [rfirst, rfirst + K)
+        if (2 * rk >= rfirst && 2 * rk < rneed) s_pick[0][2 * rk] = (uint16_t)ca;
+        if (2 * rk + 1 >= rfirst && 2 * rk + 1 < rneed) s_pick[0][2 * rk + 1] = (uint16_t)cb;
       }
-      uint32_t cur = 0, rmode = 0, rstop = 0;
-      bool cha = false, chb = false;                   // my entries (of the active list) are chosen
-      uint32_t ranka = 0, rankb = 0;                   // ... as the job's ranka-th / rankb-th node
-      bool ta = false, tb = false;                     // my entries of the active list are taken by an earlier job
-      uint32_t sa = 0, sb = 0;                         // ... as its task sa / sb
+      uint32_t cur = 0, rstop = 0;
+      bool cha = false, chb = false;   // my entries are chosen ...
+      uint32_t ranka = 0, rankb = 0;   // ... as the job's ranka-th / rankb-th node
+      bool ta = false, tb = false;     // my entries are taken by an earlier job ...
+      uint32_t sa = 0, sb = 0;         // ... as its task sa / sb
       uint32_t chosen8 = 0;
       for (uint32_t round = 0; round < (uint32_t)kBatch + 2; ++round) {
         __syncwarp();
         const uint4 pk = *reinterpret_cast<const uint4*>(s_pick[cur]);
-        if (lane < (uint32_t)kBatch) s_pick[cur ^ 1u][lane] = 0xffffu;
+        const uint32_t mine_old = lane < 8 ? (uint32_t)s_pick[cur][lane] : 0u;
+        if (lane < 8) s_pick[cur ^ 1u][lane] = 0xffffu;
         __syncwarp();
-        const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
-        bool t0a = false, t0b = false, t1a = false, t1b = false;
-        uint32_t s0a = 0, s0b = 0, s1a = 0, s1b = 0;
+        ta = false; tb = false; sa = 0; sb = 0;
 #pragma unroll
         for (uint32_t w = 0; w < (uint32_t)kBatch; ++w) {
-          const uint32_t v = (pw[w >> 1] >> (16u * (w & 1u))) & 0xffffu;
-          const bool earlier = w < rfirst;  // tasks before mine belong to the jobs before mine
-          if (earlier && v == c0a && c0a != 0xffffu) { t0a = true; s0a = w; }
-          if (earlier && v == c0b && c0b != 0xffffu) { t0b = true; s0b = w; }
-          if (earlier && v == c1a && c1a != 0xffffu) { t1a = true; s1a = w; }
-          if (earlier && v == c1b && c1b != 0xffffu) { t1b = true; s1b = w; }
+          const uint32_t word = (w >> 1) == 0 ? pk.x : (w >> 1) == 1 ? pk.y : (w >> 1) == 2 ? pk.z : pk.w;
+          const uint32_t v = (w & 1u) ? word >> 16 : word & 0xffffu;
+          const bool earlier = w < rfirst && v != 0xffffu;  // tasks before mine belong to the jobs before mine
+          if (earlier && v == ca) { ta = true; sa = w; }
+          if (earlier && v == cb) { tb = true; sb = w; }
         }
-        const unsigned f0a = __ballot_sync(kFullMask, c0a != 0xffffu && !t0a), f0b = __ballot_sync(kFullMask, c0b != 0xffffu && !t0b);
-        const unsigned f1a = __ballot_sync(kFullMask, c1a != 0xffffu && !t1a), f1b = __ballot_sync(kFullMask, c1b != 0xffffu && !t1b);
-        const unsigned tk0 = __ballot_sync(kFullMask, t0a || t0b), tk1 = __ballot_sync(kFullMask, t1a || t1b);
+        const unsigned fa = __ballot_sync(kFullMask, ca != 0xffffu && !ta), fbm = __ballot_sync(kFullMask, cb != 0xffffu && !tb);
+        const unsigned tk = __ballot_sync(kFullMask, ta || tb);
         // bit i of free8 = entry i of the list is free: entry 2k+e sits in lane rg+k, ballot e
-        auto spread = [](uint32_t x) { return (x & 1u) | ((x & 2u) << 1) | ((x & 4u) << 2) | ((x & 8u) << 3); };
-        const uint32_t free0 = spread((f0a >> rg) & 0xFu) | (spread((f0b >> rg) & 0xFu) << 1);
-        const uint32_t free1 = spread((f1a >> rg) & 0xFu) | (spread((f1b >> rg) & 0xFu) << 1);
-        const bool any_t0 = ((tk0 >> rg) & 0xFu) != 0, any_t1 = ((tk1 >> rg) & 0xFu) != 0;
-        uint32_t fm = 0;
-        rmode = 0; rstop = 0;
-        if ((uint32_t)__popc(free0) >= rK) {
-          fm = free0;                    // immediate start on the first K free pre-filter candidates
-        } else if (any_t0) {
-          rstop = 1;                     // a taken node may still complete the set once it is updated
-        } else {
-          rmode = 1;                     // fewer than K candidates in all: backfill on the first K free capable nodes
-          if ((uint32_t)__popc(free1) >= rK) fm = free1;
-          else rstop = any_t1 ? 1u : 2u; // wait for the taken ones / too few capable nodes at all ("Resource", one-job path)
-        }
-        if (!ract) { rstop = 1; fm = 0; }
+        const uint32_t xa = (fa >> rg) & 0xFu, xb = (fbm >> rg) & 0xFu;
+        const uint32_t free8 = ((xa & 1u) | ((xa & 2u) << 1) | ((xa & 4u) << 2) | ((xa & 8u) << 3)) |
+                               (((xb & 1u) | ((xb & 2u) << 1) | ((xb & 4u) << 2) | ((xb & 8u) << 3)) << 1);
+        const bool any_taken = ((tk >> rg) & 0xFu) != 0;
+        rstop = 0;
+        if (!ract) rstop = 1;
+        else if ((uint32_t)__popc(free8) < rK) rstop = (rmode && !any_taken) ? 2u : 1u;  // too few capable nodes at all : wait for the taken ones
         const uint32_t ia = 2 * rk, ib = 2 * rk + 1;
-        ranka = (uint32_t)__popc(fm & ((1u << ia) - 1u));
-        rankb = (uint32_t)__popc(fm & ((1u << ib) - 1u));
-        cha = !rstop && ((fm >> ia) & 1u) && ranka < rK;
-        chb = !rstop && ((fm >> ib) & 1u) && rankb < rK;
+        ranka = (uint32_t)__popc(free8 & ((1u << ia) - 1u));
+        rankb = (uint32_t)__popc(free8 & ((1u << ib) - 1u));
+        cha = !rstop && ((free8 >> ia) & 1u) && ranka < rK;
+        chb = !rstop && ((free8 >> ib) & 1u) && rankb < rK;
         chosen8 = 0;
-        if (!rstop) { chosen8 = fm; while ((uint32_t)__popc(chosen8) > rK) chosen8 &= ~(1u << (31 - __clz((int)chosen8))); }
-        ta = rmode ? t1a : t0a; tb = rmode ? t1b : t0b;
-        sa = rmode ? s1a : s0a; sb = rmode ? s1b : s0b;
-        if (cha) s_pick[cur ^ 1u][rfirst + ranka] = (uint16_t)(rmode ? c1a : c0a);
-        if (chb) s_pick[cur ^ 1u][rfirst + rankb] = (uint16_t)(rmode ? c1b : c0b);
+        if (!rstop) { chosen8 = free8; while ((uint32_t)__popc(chosen8) > rK) chosen8 &= ~(1u << (31 - __clz((int)chosen8))); }
+        if (cha) s_pick[cur ^ 1u][rfirst + ranka] = (uint16_t)ca;
+        if (chb) s_pick[cur ^ 1u][rfirst + rankb] = (uint16_t)cb;
         __syncwarp();
-        bool changed = false;
-        if (lane < (uint32_t)kBatch) changed = s_pick[cur ^ 1u][lane] != ((pw[lane >> 1] >> (16u * (lane & 1u))) & 0xffffu);
+        const bool changed = lane < 8 && (uint32_t)s_pick[cur ^ 1u][lane] != mine_old;
         cur ^= 1u;
         if (!__any_sync(kFullMask, changed)) break;
       }
       // tasks: node, new cost, job
-      const uint32_t na = rmode ? c1a : c0a, nb_ = rmode ? c1b : c0b;
+      const uint32_t na = ca, nb_ = cb;
       if (cha) {
         const uint32_t w = rfirst + ranka;
         sm.list[w] = (uint16_t)na;
@@ -2262,7 +2352,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       const unsigned badm = __ballot_sync(kFullMask, rstop != 0 || clash);
       // jobs before the first one that has to wait (lanes of jobs >= nj are "bad")
       const uint32_t njr = badm ? ((uint32_t)__ffs((int)badm) - 1u) >> 2 : nj;
-      const uint32_t stop_cut = __shfl_sync(kFullMask, rstop, (int)((njr < (uint32_t)kBatch ? njr : 0u) * 4u));
+      const uint32_t stop_cut = __shfl_sync(kFullMask, rstop, (int)((njr < 8u ? njr : 0u) * 4u));
       bool need_single = false;
       if (njr < nj && stop_cut == 2u) {
         single_job = ji + njr;  // placing the jobs before it cannot change that
@@ -2287,10 +2377,15 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         // its new cost if its job is placed, where it was otherwise. (The bucket
         // bounds read cpu0/gcnt while a commit may be lowering them: either value
         // is a valid upper bound.)
+        if (lane < NT && lane >= f) s_newcost[lane] = sm.cost[sm.list[lane]];
+        __syncwarp();
+        uint32_t left = bucket_insert_batch(sm, NT, s_newcost, first_bucket);
+        if (lane < NT && !((left >> lane) & 1u)) sm.pend[sm.list[lane]] = 0;
+        __syncwarp();
         bool rebuilt = false;
-        for (uint32_t t = 0; t < NT; ++t) {
-          const uint32_t q = sm.list[t];
-          leftover_insert(q, t < f ? s_newcost[t] : sm.cost[q], rebuilt);
+        for (; left; left &= left - 1u) {  // no room in the target bucket: re-deal, then one by one
+          const uint32_t t = (uint32_t)__ffs((int)left) - 1u;
+          leftover_insert(sm.list[t], s_newcost[t], rebuilt);
         }
         PROF(10);
         __syncthreads();                  // commits are done
