@@ -1098,14 +1098,12 @@ __device__ __noinline__ void bucket_remove_pending(CommitSmem& sm, uint32_t np) 
   }
 }
 
-template <bool kLocked>
-__device__ __forceinline__ bool bucket_insert_t(CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
+// The bucket a node with key (new_cost, u) belongs into: the first non-empty
+// bucket >= from_bucket whose last key is not below the key; if there is none,
+// the last non-empty bucket. Read-only (blast[] and cost[]), so several warps
+// may search at once, each for its own node.
+__device__ __forceinline__ uint32_t bucket_find(const CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
   const uint32_t lane = lane_id();
-  // first non-empty bucket >= from_bucket whose last key is >= the new key;
-  // if there is none, the last non-empty bucket. The search reads only blast[]
-  // and cost[]: with concurrent (locked) inserts elsewhere a bucket's last node
-  // changes only for the last non-empty bucket, where either view gives the
-  // same target.
   uint32_t tb = 0xffffffffu, last_nonempty = 0xffffffffu;
   for (uint32_t start = from_bucket;; start = 0) {
     for (uint32_t b0 = start; b0 < sm.nb && tb == 0xffffffffu; b0 += 32) {
@@ -1128,164 +1126,45 @@ __device__ __forceinline__ bool bucket_insert_t(CommitSmem& sm, uint32_t u, doub
     // nodes before it are the whole order now
     if (start == 0) { tb = from_bucket; break; }
   }
-  if (kLocked) {
-    if (lane == 0) {
-      while (atomicCAS(&sm.block[tb], 0u, 1u) != 0u) {}
-      __threadfence_block();
-    }
-    __syncwarp();
-  }
+  return tb;
+}
+// Inserts u with key (new_cost, u) into bucket tb at its sorted place; false if
+// the bucket is full (the caller re-deals the order).
+__device__ __forceinline__ bool bucket_place(CommitSmem& sm, uint32_t u, double new_cost, uint32_t tb) {
+  const uint32_t lane = lane_id();
   uint16_t* B = sm.bk + (size_t)tb * kBucket;
   const uint32_t n = sm.bcnt[tb];
 #ifdef CRANE_EMU_DEBUG
-  if (lane == 0) fprintf(stderr, "  insert%s u=%u key=%.6f from=%u -> tb=%u n=%u blast[tb]=%u cost[blast]=%.6f\n", kLocked ? "L" : "", u, new_cost, from_bucket, tb, n, sm.blast[tb], sm.blast[tb] != 0xffff ? sm.cost[sm.blast[tb]] : -1.0);
+  if (lane == 0) fprintf(stderr, "  insert u=%u key=%.6f -> tb=%u n=%u\n", u, new_cost, tb, n);
 #endif
-  bool done = false;
-  if (n < (uint32_t)kBucket) {
-    const uint16_t e0 = lane < n ? B[lane] : (uint16_t)0xffff;
-    const uint16_t e1 = lane + 32 < n ? B[lane + 32] : (uint16_t)0xffff;
-    const bool l0 = lane < n && key_lt(sm.cost[e0], e0, new_cost, u);
-    const bool l1 = lane + 32 < n && key_lt(sm.cost[e1], e1, new_cost, u);
-    const uint32_t pos = (uint32_t)__popc(__ballot_sync(kFullMask, l0)) + (uint32_t)__popc(__ballot_sync(kFullMask, l1));
-    if (lane == 0) sm.cost[u] = new_cost;  // before u becomes visible in the bucket
-    if (lane >= pos && lane < n) B[lane + 1] = e0;
-    if (lane + 32 >= pos && lane + 32 < n) B[lane + 33] = e1;
-    if (kLocked) __threadfence_block();
-    __syncwarp();
-    if (lane == 0) {
-      B[pos] = (uint16_t)u;
-      sm.bcnt[tb] = (uint16_t)(n + 1);
-      if (pos == n) sm.blast[tb] = (uint16_t)u;
-      sm.bkt[u] = (uint16_t)tb;
-      const long long c = sm.cpu0[u];
-      const unsigned long long gc = sm.gcnt[u];
-      if (c > sm.bmax_cpu[tb]) sm.bmax_cpu[tb] = c;
-      if (gc && c > sm.bmax_cpug[tb]) sm.bmax_cpug[tb] = c;
-      sm.bmax_g[tb] = vmax8(sm.bmax_g[tb], gc);
-      sm.bexact[tb] = 0;
-    }
-    done = true;
+  if (n >= (uint32_t)kBucket) return false;
+  const uint16_t e0 = lane < n ? B[lane] : (uint16_t)0xffff;
+  const uint16_t e1 = lane + 32 < n ? B[lane + 32] : (uint16_t)0xffff;
+  const bool l0 = lane < n && key_lt(sm.cost[e0], e0, new_cost, u);
+  const bool l1 = lane + 32 < n && key_lt(sm.cost[e1], e1, new_cost, u);
+  const uint32_t pos = (uint32_t)__popc(__ballot_sync(kFullMask, l0)) + (uint32_t)__popc(__ballot_sync(kFullMask, l1));
+  if (lane >= pos && lane < n) B[lane + 1] = e0;
+  if (lane + 32 >= pos && lane + 32 < n) B[lane + 33] = e1;
+  __syncwarp();
+  if (lane == 0) {
+    sm.cost[u] = new_cost;
+    B[pos] = (uint16_t)u;
+    sm.bcnt[tb] = (uint16_t)(n + 1);
+    if (pos == n) sm.blast[tb] = (uint16_t)u;
+    sm.bkt[u] = (uint16_t)tb;
+    const long long c = sm.cpu0[u];
+    const unsigned long long gc = sm.gcnt[u];
+    if (c > sm.bmax_cpu[tb]) sm.bmax_cpu[tb] = c;
+    if (gc && c > sm.bmax_cpug[tb]) sm.bmax_cpug[tb] = c;
+    sm.bmax_g[tb] = vmax8(sm.bmax_g[tb], gc);
+    sm.bexact[tb] = 0;
   }
   __syncwarp();
-  if (kLocked) {
-    if (lane == 0) {
-      __threadfence_block();
-      atomicExch(&sm.block[tb], 0u);
-    }
-  }
-  return done;
+  return true;
 }
 __device__ __forceinline__ bool bucket_insert(CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
-  return bucket_insert_t<false>(sm, u, new_cost, from_bucket);
+  return bucket_place(sm, u, new_cost, bucket_find(sm, u, new_cost, from_bucket));
 }
-// Puts the nodes list[0..np) back into the order at the costs key[0..np) — all
-// of them at once: one sweep over the buckets' last keys finds every node's
-// bucket (the first non-empty bucket whose last key is not below the node's
-// key, else the last non-empty one), then every touched bucket is merged with
-// its newcomers in one pass. Returns the mask of nodes whose bucket had no room
-// (the caller re-deals the order and inserts them one by one). Driver warp.
-__device__ __noinline__ uint32_t bucket_insert_batch(CommitSmem& sm, uint32_t np, const double* key, uint32_t fb) {
-  const uint32_t lane = lane_id();
-  uint32_t u[kBatch], tb[kBatch];
-  double k[kBatch];
-#pragma unroll
-  for (int w = 0; w < kBatch; ++w) {
-    u[w] = (uint32_t)w < np ? (uint32_t)sm.list[w] : 0u;
-    k[w] = (uint32_t)w < np ? key[w] : 0.0;
-    tb[w] = 0xffffffffu;
-  }
-  uint32_t last_nonempty = 0xffffffffu;
-  for (uint32_t b0 = fb; b0 < sm.nb; b0 += 32) {
-    const uint32_t b = b0 + lane;
-    const uint32_t o = b < sm.nb ? (uint32_t)sm.blast[b] : 0xffffu;
-    const bool nonempty = o != 0xffffu;
-    const double co = nonempty ? sm.cost[o] : 0.0;
-    const unsigned mn = __ballot_sync(kFullMask, nonempty);
-    if (mn) last_nonempty = b0 + 31u - (uint32_t)__clz((int)mn);
-    bool all = true;
-#pragma unroll
-    for (int w = 0; w < kBatch; ++w) {
-      if ((uint32_t)w < np && tb[w] == 0xffffffffu) {
-        const unsigned mg = __ballot_sync(kFullMask, nonempty && !key_lt(co, o, k[w], u[w]));
-        if (mg) tb[w] = b0 + (uint32_t)__ffs((int)mg) - 1u;
-        else all = false;
-      }
-    }
-    if (all) break;
-  }
-#pragma unroll
-  for (int w = 0; w < kBatch; ++w)
-    if ((uint32_t)w < np && tb[w] == 0xffffffffu) tb[w] = last_nonempty != 0xffffffffu ? last_nonempty : fb;
-  uint32_t todo = np >= 32 ? 0xffffffffu : (1u << np) - 1u, overflow = 0;
-  while (todo) {
-    // the bucket of the lowest pending node, and everybody else going there
-    uint32_t t = 0, members = 0;
-#pragma unroll
-    for (int w = 0; w < kBatch; ++w)
-      if (((todo & (0u - todo)) >> w) & 1u) t = tb[w];
-#pragma unroll
-    for (int w = 0; w < kBatch; ++w)
-      if (((todo >> w) & 1u) && tb[w] == t) members |= 1u << w;
-    todo &= ~members;
-    uint16_t* B = sm.bk + (size_t)t * kBucket;
-    const uint32_t n = sm.bcnt[t], m = (uint32_t)__popc(members);
-    if (n + m > (uint32_t)kBucket) { overflow |= members; continue; }
-    const uint32_t e0 = lane < n ? (uint32_t)B[lane] : 0xffffu, e1 = lane + 32 < n ? (uint32_t)B[lane + 32] : 0xffffu;
-    const double ce0 = lane < n ? sm.cost[e0] : 0.0, ce1 = lane + 32 < n ? sm.cost[e1] : 0.0;
-    uint32_t sh0 = 0, sh1 = 0;      // newcomers that sort before my entries
-    uint32_t mypos = 0;             // lane w: final index of newcomer w
-#pragma unroll
-    for (int w = 0; w < kBatch; ++w) {
-      if ((members >> w) & 1u) {
-        const bool lt0 = lane < n && key_lt(ce0, e0, k[w], u[w]);
-        const bool lt1 = lane + 32 < n && key_lt(ce1, e1, k[w], u[w]);
-        if (lane < n && !lt0) ++sh0;
-        if (lane + 32 < n && !lt1) ++sh1;
-        uint32_t pos = (uint32_t)__popc(__ballot_sync(kFullMask, lt0)) + (uint32_t)__popc(__ballot_sync(kFullMask, lt1));
-#pragma unroll
-        for (int v = 0; v < kBatch; ++v)
-          if (v != w && ((members >> v) & 1u) && key_lt(k[v], u[v], k[w], u[w])) ++pos;
-        if (lane == (uint32_t)w) mypos = pos;
-      }
-    }
-    // every load of the old entries is done (the ballots above depend on them)
-    if (lane < n) B[lane + sh0] = (uint16_t)e0;
-    if (lane + 32 < n) B[lane + 32 + sh1] = (uint16_t)e1;
-    long long mc = INT64_MIN, mcg = INT64_MIN;
-    unsigned long long mg = 0;
-    if (lane < (uint32_t)kBatch && ((members >> lane) & 1u)) {
-      uint32_t uu = 0;
-      double kk = 0.0;
-#pragma unroll
-      for (int w = 0; w < kBatch; ++w)
-        if (lane == (uint32_t)w) { uu = u[w]; kk = k[w]; }
-      B[mypos] = (uint16_t)uu;
-      sm.bkt[uu] = (uint16_t)t;
-      sm.cost[uu] = kk;
-      mc = sm.cpu0[uu];
-      mg = sm.gcnt[uu];
-      if (mg) mcg = mc;
-    }
-    for (int o = 4; o > 0; o >>= 1) {  // newcomers sit in lanes 0..7
-      const long long oc = __shfl_xor_sync(kFullMask, mc, o), ocg = __shfl_xor_sync(kFullMask, mcg, o);
-      mc = oc > mc ? oc : mc;
-      mcg = ocg > mcg ? ocg : mcg;
-      mg = vmax8(mg, __shfl_xor_sync(kFullMask, mg, o));
-    }
-    __syncwarp();
-    if (lane == 0) {
-      sm.bcnt[t] = (uint16_t)(n + m);
-      sm.blast[t] = B[n + m - 1];
-      if (mc > sm.bmax_cpu[t]) sm.bmax_cpu[t] = mc;
-      if (mcg > sm.bmax_cpug[t]) sm.bmax_cpug[t] = mcg;
-      sm.bmax_g[t] = vmax8(sm.bmax_g[t], mg);
-      sm.bexact[t] = 0;
-    }
-    __syncwarp();
-  }
-  return overflow;
-}
-
 // Deal sm.tmp[0..total) (already in (cost, node) order) out to the buckets,
 // kBucketFill per bucket, and refresh bkt[] and the per-bucket bounds.
 __device__ __noinline__ void bucket_deal(CommitSmem& sm, uint32_t total) {
@@ -1411,6 +1290,9 @@ struct WorkerCtx {  // lives in shared memory; read-only after set-up
   BatchSel* sel;     // [kBatch]
   const BatchTask* task;         // [kBatch]
   uint32_t* joblabel;            // [kBatch] "some node is short of resources now" of a multi-node backfill in the batch
+  const double* newcost;         // [kBatch] cost of a task's node once its job is placed
+  uint32_t* tbk;                 // [kBatch] bucket the task's node goes back into (found by its helper)
+  uint32_t* found;               // number of helpers that published tbk[] for the batch in flight
   const uint32_t* first_bucket;  // buckets before it are empty
 };
 
@@ -1663,6 +1545,16 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
       if (f < stride) f = cx.task[f].tfirst;
       ok = first < f;
       result = (long long)f;
+      // where the node goes back into the order (the driver has taken all picks
+      // out by now): at its new cost if the job is placed, at the old one otherwise.
+      // Read-only search, published to the driver, which does the inserts while
+      // the timelines are updated below.
+      const uint32_t tbk = bucket_find(sm, q, ok ? cx.newcost[first] : sm.cost[q], *cx.first_bucket);
+      if (lane == 0) {
+        cx.tbk[first] = tbk;
+        __threadfence_block();
+        atomicAdd(cx.found, 1u);
+      }
     }
     const bool do_update = ((kind == OP_NOW_K1 || kind == OP_BF_K1 || kind == OP_NOW_MULTI || kind == OP_BF_MULTI) && ok) ||
                            kind == OP_UPDATE_NOW || kind == OP_UPDATE_BF;
@@ -1756,6 +1648,8 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   __shared__ BatchSel s_sel[kBatch];
   __shared__ uint32_t s_first_bucket;
   __shared__ uint32_t s_joblabel[kBatch];
+  __shared__ uint32_t s_tbk[kBatch];
+  __shared__ uint32_t s_found;
   __shared__ __align__(16) uint16_t s_pick[2][8];
   __shared__ uint32_t s_ok[32];
   __shared__ long long s_tbuf[2][32];
@@ -1782,7 +1676,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     s_label = 0;
     s_cx.cl = a.cl; s_cx.tl = a.tl; s_cx.out = a.out; s_cx.sm = sm; s_cx.jobs = s_jobs; s_cx.classrow = s_classrow;
     s_cx.label = &s_label; s_cx.ok = s_ok; s_cx.tbuf = &s_tbuf[0][0]; s_cx.now = a.now; s_cx.max_window = a.max_window; s_cx.base = base; s_cx.max_jobs = a.max_jobs;
-    s_cx.words = words; s_cx.bj = s_bj; s_cx.sel = s_sel; s_cx.task = s_task; s_cx.first_bucket = &s_first_bucket; s_cx.joblabel = s_joblabel;
+    s_cx.words = words; s_cx.bj = s_bj; s_cx.sel = s_sel; s_cx.task = s_task; s_cx.first_bucket = &s_first_bucket; s_cx.joblabel = s_joblabel; s_cx.newcost = s_newcost; s_cx.tbk = s_tbk; s_cx.found = &s_found;
     for (int s = 0; s < kRing; ++s) mbar_init(&s_bar[s], 1);
     fence_mbar_init();
   }
@@ -2364,7 +2258,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       __syncwarp();
       PROF(6);
       if (NT) {
-        if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = NT; }
+        if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = NT; s_found = 0; }
         __syncthreads();                  // the helpers start evaluating
         bucket_remove_pending(sm, NT);    // meanwhile the picks leave the order
         __syncthreads();                  // verdicts are in
@@ -2377,16 +2271,21 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         // its new cost if its job is placed, where it was otherwise. (The bucket
         // bounds read cpu0/gcnt while a commit may be lowering them: either value
         // is a valid upper bound.)
-        if (lane < NT && lane >= f) s_newcost[lane] = sm.cost[sm.list[lane]];
-        __syncwarp();
-        uint32_t left = bucket_insert_batch(sm, NT, s_newcost, first_bucket);
-        if (lane < NT && !((left >> lane) & 1u)) sm.pend[sm.list[lane]] = 0;
+        // while the helpers commit, every picked node goes back into the order: at
+        // its new cost if its job is placed, where it was otherwise. Each helper has
+        // looked up its node's bucket; the inserts themselves are done here, one
+        // after the other. (The bucket bounds read cpu0/gcnt while a commit may be
+        // lowering them: either value is a valid upper bound.)
+        while (*(volatile uint32_t*)&s_found < NT) {}
         __syncwarp();
         bool rebuilt = false;
-        for (; left; left &= left - 1u) {  // no room in the target bucket: re-deal, then one by one
-          const uint32_t t = (uint32_t)__ffs((int)left) - 1u;
-          leftover_insert(sm.list[t], s_newcost[t], rebuilt);
+        for (uint32_t t = 0; t < NT; ++t) {
+          const uint32_t q = sm.list[t];
+          const double nc = t < f ? s_newcost[t] : sm.cost[q];
+          if (rebuilt || !bucket_place(sm, q, nc, s_tbk[t])) leftover_insert(q, nc, rebuilt);
+          else if (lane == 0) sm.pend[q] = 0;
         }
+        __syncwarp();
         PROF(10);
         __syncthreads();                  // commits are done
         // jobs placed = those whose tasks all lie before the cut
