@@ -689,7 +689,13 @@ struct CommitSmem {
   uint8_t* pend;               // [mp]  picked by the batch in flight: out of the order until re-inserted
   uint32_t nb;
 };
-__host__ __device__ inline uint32_t commit_nbuckets(uint32_t mp) { return (mp + kBucketFill - 1) / kBucketFill + 1; }
+// buckets of a partition: enough for kBucketFill nodes each, plus spare empty ones
+// at the end — re-keyed nodes mostly move to the tail of the order, and a full
+// last bucket overflows into the next empty one instead of forcing a re-deal
+__host__ __device__ inline uint32_t commit_nbuckets(uint32_t mp) {
+  const uint32_t base = (mp + kBucketFill - 1) / kBucketFill;
+  return base + (base / 4 > 4 ? base / 4 : 4);
+}
 __host__ __device__ inline size_t commit_smem_bytes(uint32_t mp, uint32_t words) {
   const size_t nb = commit_nbuckets(mp);
   size_t b = (size_t)kRing * words * 4;
@@ -1137,7 +1143,29 @@ __device__ __forceinline__ bool bucket_place(CommitSmem& sm, uint32_t u, double 
 #ifdef CRANE_EMU_DEBUG
   if (lane == 0) fprintf(stderr, "  insert u=%u key=%.6f -> tb=%u n=%u\n", u, new_cost, tb, n);
 #endif
-  if (n >= (uint32_t)kBucket) return false;
+  if (n >= (uint32_t)kBucket) {
+    // full. A key beyond the bucket's last one was sent here as "last non-empty
+    // bucket": everything after it is empty, so it opens the next bucket.
+    const uint32_t o = sm.blast[tb];
+    if (tb + 1 >= sm.nb || sm.bcnt[tb + 1] != 0 || !key_lt(sm.cost[o], o, new_cost, u)) return false;
+    ++tb;
+    B += kBucket;
+    if (lane == 0) {
+      sm.cost[u] = new_cost;
+      B[0] = (uint16_t)u;
+      sm.bcnt[tb] = 1;
+      sm.blast[tb] = (uint16_t)u;
+      sm.bkt[u] = (uint16_t)tb;
+      const long long c = sm.cpu0[u];
+      const unsigned long long gc = sm.gcnt[u];
+      sm.bmax_cpu[tb] = c;
+      sm.bmax_cpug[tb] = gc ? c : INT64_MIN;
+      sm.bmax_g[tb] = gc;
+      sm.bexact[tb] = 1;
+    }
+    __syncwarp();
+    return true;
+  }
   const uint16_t e0 = lane < n ? B[lane] : (uint16_t)0xffff;
   const uint16_t e1 = lane + 32 < n ? B[lane + 32] : (uint16_t)0xffff;
   const bool l0 = lane < n && key_lt(sm.cost[e0], e0, new_cost, u);
