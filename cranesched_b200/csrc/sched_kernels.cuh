@@ -1134,37 +1134,43 @@ __device__ __forceinline__ uint32_t bucket_find(const CommitSmem& sm, uint32_t u
   }
   return tb;
 }
-// Inserts u with key (new_cost, u) into bucket tb at its sorted place; false if
-// the bucket is full (the caller re-deals the order).
-__device__ __forceinline__ bool bucket_place(CommitSmem& sm, uint32_t u, double new_cost, uint32_t tb) {
+// Inserts u with key (new_cost, u) into bucket tb at its sorted place. Returns 0
+// if the bucket is full (the caller re-deals the order), 1 if placed, 2 if placed
+// by opening the next bucket (bucket look-ups made before that are stale).
+__device__ __forceinline__ int bucket_place(CommitSmem& sm, uint32_t u, double new_cost, uint32_t tb) {
   const uint32_t lane = lane_id();
   uint16_t* B = sm.bk + (size_t)tb * kBucket;
   const uint32_t n = sm.bcnt[tb];
 #ifdef CRANE_EMU_DEBUG
   if (lane == 0) fprintf(stderr, "  insert u=%u key=%.6f -> tb=%u n=%u\n", u, new_cost, tb, n);
 #endif
-  if (n >= (uint32_t)kBucket) {
-    // full. A key beyond the bucket's last one was sent here as "last non-empty
-    // bucket": everything after it is empty, so it opens the next bucket.
+  if (n >= (uint32_t)kBucketFill) {
+    // A key beyond the bucket's last one was sent here as "last non-empty bucket":
+    // everything after it is empty. Such appends open the next bucket once this
+    // one holds kBucketFill nodes, which leaves room for inserts in the middle.
     const uint32_t o = sm.blast[tb];
-    if (tb + 1 >= sm.nb || sm.bcnt[tb + 1] != 0 || !key_lt(sm.cost[o], o, new_cost, u)) return false;
-    ++tb;
-    B += kBucket;
-    if (lane == 0) {
-      sm.cost[u] = new_cost;
-      B[0] = (uint16_t)u;
-      sm.bcnt[tb] = 1;
-      sm.blast[tb] = (uint16_t)u;
-      sm.bkt[u] = (uint16_t)tb;
-      const long long c = sm.cpu0[u];
-      const unsigned long long gc = sm.gcnt[u];
-      sm.bmax_cpu[tb] = c;
-      sm.bmax_cpug[tb] = gc ? c : INT64_MIN;
-      sm.bmax_g[tb] = gc;
-      sm.bexact[tb] = 1;
+    const bool open_next = tb + 1 < sm.nb && sm.bcnt[tb + 1] == 0 && key_lt(sm.cost[o], o, new_cost, u);
+    __syncwarp();  // every lane has read the counts before lane 0 changes them
+    if (!open_next && n >= (uint32_t)kBucket) return 0;
+    if (open_next) {
+      ++tb;
+      B += kBucket;
+      if (lane == 0) {
+        sm.cost[u] = new_cost;
+        B[0] = (uint16_t)u;
+        sm.bcnt[tb] = 1;
+        sm.blast[tb] = (uint16_t)u;
+        sm.bkt[u] = (uint16_t)tb;
+        const long long c = sm.cpu0[u];
+        const unsigned long long gc = sm.gcnt[u];
+        sm.bmax_cpu[tb] = c;
+        sm.bmax_cpug[tb] = gc ? c : INT64_MIN;
+        sm.bmax_g[tb] = gc;
+        sm.bexact[tb] = 1;
+      }
+      __syncwarp();
+      return 2;
     }
-    __syncwarp();
-    return true;
   }
   const uint16_t e0 = lane < n ? B[lane] : (uint16_t)0xffff;
   const uint16_t e1 = lane + 32 < n ? B[lane + 32] : (uint16_t)0xffff;
@@ -1188,10 +1194,10 @@ __device__ __forceinline__ bool bucket_place(CommitSmem& sm, uint32_t u, double 
     sm.bexact[tb] = 0;
   }
   __syncwarp();
-  return true;
+  return 1;
 }
 __device__ __forceinline__ bool bucket_insert(CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
-  return bucket_place(sm, u, new_cost, bucket_find(sm, u, new_cost, from_bucket));
+  return bucket_place(sm, u, new_cost, bucket_find(sm, u, new_cost, from_bucket)) != 0;
 }
 // Deal sm.tmp[0..total) (already in (cost, node) order) out to the buckets,
 // kBucketFill per bucket, and refresh bkt[] and the per-bucket bounds.
@@ -1811,6 +1817,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   auto leftover_insert = [&](uint32_t q, double nc, bool& rebuilt) {
     if (!bucket_insert(sm, q, nc, rebuilt ? 0u : (uint32_t)sm.bkt[q])) {
       bucket_rebuild(sm);
+      PROF_CNT(12, 1);
       first_bucket = 0;
       rebuilt = true;
       bucket_insert(sm, q, nc, 0);
@@ -2064,7 +2071,6 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       __syncwarp();
       PROF(4);
       if (K <= mp && cum >= K) {
-        PROF_CNT(12, 1);
         if (K == 1) {
           const long long t = worker_step(&s_cx, OP_BF_K1, 1, slot, a.now, 0, 1, 0);
           PROF_CNT(11, 1);
@@ -2306,12 +2312,15 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         // lowering them: either value is a valid upper bound.)
         while (*(volatile uint32_t*)&s_found < NT) {}
         __syncwarp();
-        bool rebuilt = false;
+        bool rebuilt = false, stale = false;
         for (uint32_t t = 0; t < NT; ++t) {
           const uint32_t q = sm.list[t];
           const double nc = t < f ? s_newcost[t] : sm.cost[q];
-          if (rebuilt || !bucket_place(sm, q, nc, s_tbk[t])) leftover_insert(q, nc, rebuilt);
+          int r = 0;
+          if (!rebuilt) r = bucket_place(sm, q, nc, stale ? bucket_find(sm, q, nc, first_bucket) : s_tbk[t]);
+          if (r == 0) leftover_insert(q, nc, rebuilt);
           else if (lane == 0) sm.pend[q] = 0;
+          stale = stale || r == 2;
         }
         __syncwarp();
         PROF(10);
