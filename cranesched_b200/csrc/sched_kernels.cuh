@@ -663,7 +663,9 @@ constexpr int kRing = 16;            // prefetch ring depth (jobs)
 #endif
 constexpr int kCommitThreads = CRANE_COMMIT_THREADS;  // CTA size of k_commit: driver warp + helpers
 constexpr int kBatch = kCommitThreads / 32 - 1;       // nodes of the jobs dispatched together (one helper warp each)
-static_assert(kBatch >= 1 && kBatch <= 8, "the resolve step lays 8 jobs x 4 lanes over one warp");
+constexpr int kBatchJobs = kBatch < 8 ? kBatch : 8;   // jobs per batch: the resolve step lays 8 jobs x 4 lanes over one warp
+constexpr int kEnt = (kBatch + 3) / 4;                // list entries per lane in the resolve step
+static_assert(kBatch >= 1 && kBatch <= 12, "the resolve step handles lists of up to 12 entries and 16 picks");
 constexpr int kBucket = 64;          // bucket capacity of the cost order
 constexpr int kBucketFill = 32;      // entries per bucket after a (re)build
 
@@ -689,13 +691,7 @@ struct CommitSmem {
   uint8_t* pend;               // [mp]  picked by the batch in flight: out of the order until re-inserted
   uint32_t nb;
 };
-// buckets of a partition: enough for kBucketFill nodes each, plus spare empty ones
-// at the end — re-keyed nodes mostly move to the tail of the order, and a full
-// last bucket overflows into the next empty one instead of forcing a re-deal
-__host__ __device__ inline uint32_t commit_nbuckets(uint32_t mp) {
-  const uint32_t base = (mp + kBucketFill - 1) / kBucketFill;
-  return base + (base / 4 > 4 ? base / 4 : 4);
-}
+__host__ __device__ inline uint32_t commit_nbuckets(uint32_t mp) { return (mp + kBucketFill - 1) / kBucketFill + 1; }
 __host__ __device__ inline size_t commit_smem_bytes(uint32_t mp, uint32_t words) {
   const size_t nb = commit_nbuckets(mp);
   size_t b = (size_t)kRing * words * 4;
@@ -1134,44 +1130,16 @@ __device__ __forceinline__ uint32_t bucket_find(const CommitSmem& sm, uint32_t u
   }
   return tb;
 }
-// Inserts u with key (new_cost, u) into bucket tb at its sorted place. Returns 0
-// if the bucket is full (the caller re-deals the order), 1 if placed, 2 if placed
-// by opening the next bucket (bucket look-ups made before that are stale).
-__device__ __forceinline__ int bucket_place(CommitSmem& sm, uint32_t u, double new_cost, uint32_t tb) {
+// Inserts u with key (new_cost, u) into bucket tb at its sorted place; false if
+// the bucket is full (the caller re-deals the order).
+__device__ __forceinline__ bool bucket_place(CommitSmem& sm, uint32_t u, double new_cost, uint32_t tb) {
   const uint32_t lane = lane_id();
   uint16_t* B = sm.bk + (size_t)tb * kBucket;
   const uint32_t n = sm.bcnt[tb];
 #ifdef CRANE_EMU_DEBUG
   if (lane == 0) fprintf(stderr, "  insert u=%u key=%.6f -> tb=%u n=%u\n", u, new_cost, tb, n);
 #endif
-  if (n >= (uint32_t)kBucketFill) {
-    // A key beyond the bucket's last one was sent here as "last non-empty bucket":
-    // everything after it is empty. Such appends open the next bucket once this
-    // one holds kBucketFill nodes, which leaves room for inserts in the middle.
-    const uint32_t o = sm.blast[tb];
-    const bool open_next = tb + 1 < sm.nb && sm.bcnt[tb + 1] == 0 && key_lt(sm.cost[o], o, new_cost, u);
-    __syncwarp();  // every lane has read the counts before lane 0 changes them
-    if (!open_next && n >= (uint32_t)kBucket) return 0;
-    if (open_next) {
-      ++tb;
-      B += kBucket;
-      if (lane == 0) {
-        sm.cost[u] = new_cost;
-        B[0] = (uint16_t)u;
-        sm.bcnt[tb] = 1;
-        sm.blast[tb] = (uint16_t)u;
-        sm.bkt[u] = (uint16_t)tb;
-        const long long c = sm.cpu0[u];
-        const unsigned long long gc = sm.gcnt[u];
-        sm.bmax_cpu[tb] = c;
-        sm.bmax_cpug[tb] = gc ? c : INT64_MIN;
-        sm.bmax_g[tb] = gc;
-        sm.bexact[tb] = 1;
-      }
-      __syncwarp();
-      return 2;
-    }
-  }
+  if (n >= (uint32_t)kBucket) return false;
   const uint16_t e0 = lane < n ? B[lane] : (uint16_t)0xffff;
   const uint16_t e1 = lane + 32 < n ? B[lane + 32] : (uint16_t)0xffff;
   const bool l0 = lane < n && key_lt(sm.cost[e0], e0, new_cost, u);
@@ -1194,10 +1162,10 @@ __device__ __forceinline__ int bucket_place(CommitSmem& sm, uint32_t u, double n
     sm.bexact[tb] = 0;
   }
   __syncwarp();
-  return 1;
+  return true;
 }
 __device__ __forceinline__ bool bucket_insert(CommitSmem& sm, uint32_t u, double new_cost, uint32_t from_bucket) {
-  return bucket_place(sm, u, new_cost, bucket_find(sm, u, new_cost, from_bucket)) != 0;
+  return bucket_place(sm, u, new_cost, bucket_find(sm, u, new_cost, from_bucket));
 }
 // Deal sm.tmp[0..total) (already in (cost, node) order) out to the buckets,
 // kBucketFill per bucket, and refresh bkt[] and the per-bucket bounds.
@@ -1684,7 +1652,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
   __shared__ uint32_t s_joblabel[kBatch];
   __shared__ uint32_t s_tbk[kBatch];
   __shared__ uint32_t s_found;
-  __shared__ __align__(16) uint16_t s_pick[2][8];
+  __shared__ __align__(16) uint16_t s_pick[2][16];
   __shared__ uint32_t s_ok[32];
   __shared__ long long s_tbuf[2][32];
   __shared__ double s_newcost[kBatch];
@@ -2150,7 +2118,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     {
       uint32_t myK = 0, myslot = 0;
       bool okj = false;
-      if (lane < (uint32_t)kBatch && lane + 1 < nw && ji + lane < njobs && ji + lane != single_job) {
+      if (lane < (uint32_t)kBatchJobs && lane + 1 < nw && ji + lane < njobs && ji + lane != single_job) {
         const uint32_t j = ji + lane;
         myslot = j % kRing;
         mbar_wait(&s_bar[myslot], (j / kRing) & 1u);
@@ -2158,7 +2126,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         okj = myK >= 1 && myK <= mp && myK <= (uint32_t)kBatch;
       }
       uint32_t cum = myK;  // inclusive prefix sum of node_num over the lanes
-      for (int o = 1; o < kBatch; o <<= 1) {
+      for (int o = 1; o < kBatchJobs; o <<= 1) {
         const uint32_t up = __shfl_up_sync(kFullMask, cum, o);
         if ((int)lane >= o) cum += up;
       }
@@ -2186,80 +2154,95 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       const uint32_t rt = lane >> 2, rk = lane & 3u, rg = lane & ~3u;
       const bool ract = rt < nj;
       uint32_t rK = 0, rfirst = 0, rslot = 0, rneed = 0, rmode = 0, rnl = 0;
-      uint32_t ca = 0xffffu, cb = 0xffffu;
+      uint32_t ce[kEnt];               // my entries of the job's list: entries kEnt*rk + e
+#pragma unroll
+      for (int e = 0; e < kEnt; ++e) ce[e] = 0xffffu;
       if (ract) {
         const BatchJob bj = s_bj[rt];
         rK = bj.K; rneed = bj.need; rfirst = bj.need - bj.K; rslot = bj.slot;
         rmode = bj.n0 < bj.K ? 1u : 0u;
         rnl = rmode ? bj.n1 : bj.n0;
         const uint16_t* L = rmode ? s_sel[rt].c1 : s_sel[rt].c0;
-        if (2 * rk < rnl) ca = L[2 * rk];
-        if (2 * rk + 1 < rnl) cb = L[2 * rk + 1];
+#pragma unroll
+        for (int e = 0; e < kEnt; ++e)
+          if (kEnt * rk + e < rnl) ce[e] = L[kEnt * rk + e];
       }
-      if (lane < 8) s_pick[0][lane] = 0xffffu;
+      if (lane < 16) s_pick[0][lane] = 0xffffu;
       __syncwarp();
       if (ract && rnl >= rneed) {  // first guess: entries [rfirst, rfirst + K)
-        if (2 * rk >= rfirst && 2 * rk < rneed) s_pick[0][2 * rk] = (uint16_t)ca;
-        if (2 * rk + 1 >= rfirst && 2 * rk + 1 < rneed) s_pick[0][2 * rk + 1] = (uint16_t)cb;
+#pragma unroll
+        for (int e = 0; e < kEnt; ++e) {
+          const uint32_t i = kEnt * rk + e;
+          if (i >= rfirst && i < rneed) s_pick[0][i] = (uint16_t)ce[e];
+        }
       }
+      PROF(4);
       uint32_t cur = 0, rstop = 0;
-      bool cha = false, chb = false;   // my entries are chosen ...
-      uint32_t ranka = 0, rankb = 0;   // ... as the job's ranka-th / rankb-th node
-      bool ta = false, tb = false;     // my entries are taken by an earlier job ...
-      uint32_t sa = 0, sb = 0;         // ... as its task sa / sb
-      uint32_t chosen8 = 0;
-      for (uint32_t round = 0; round < (uint32_t)kBatch + 2; ++round) {
+      bool che[kEnt];                  // my entries are chosen ...
+      uint32_t ranke[kEnt];            // ... as the job's ranke-th node
+      bool te[kEnt];                   // my entries are taken by an earlier job ...
+      uint32_t se[kEnt];               // ... as its task se
+      uint32_t chosenm = 0;
+#pragma unroll
+      for (int e = 0; e < kEnt; ++e) { che[e] = false; ranke[e] = 0; te[e] = false; se[e] = 0; }
+      for (uint32_t round = 0; round < (uint32_t)kBatchJobs + 2; ++round) {
         __syncwarp();
-        const uint4 pk = *reinterpret_cast<const uint4*>(s_pick[cur]);
-        const uint32_t mine_old = lane < 8 ? (uint32_t)s_pick[cur][lane] : 0u;
-        if (lane < 8) s_pick[cur ^ 1u][lane] = 0xffffu;
+        const uint4 pk0 = *reinterpret_cast<const uint4*>(&s_pick[cur][0]);
+        const uint4 pk1 = *reinterpret_cast<const uint4*>(&s_pick[cur][8]);
+        const uint32_t mine_old = lane < 16 ? (uint32_t)s_pick[cur][lane] : 0u;
+        if (lane < 16) s_pick[cur ^ 1u][lane] = 0xffffu;
         __syncwarp();
-        ta = false; tb = false; sa = 0; sb = 0;
+#pragma unroll
+        for (int e = 0; e < kEnt; ++e) { te[e] = false; se[e] = 0; }
 #pragma unroll
         for (uint32_t w = 0; w < (uint32_t)kBatch; ++w) {
-          const uint32_t word = (w >> 1) == 0 ? pk.x : (w >> 1) == 1 ? pk.y : (w >> 1) == 2 ? pk.z : pk.w;
+          const uint32_t wi = w >> 1;
+          const uint32_t word = wi == 0 ? pk0.x : wi == 1 ? pk0.y : wi == 2 ? pk0.z : wi == 3 ? pk0.w
+                              : wi == 4 ? pk1.x : wi == 5 ? pk1.y : wi == 6 ? pk1.z : pk1.w;
           const uint32_t v = (w & 1u) ? word >> 16 : word & 0xffffu;
           const bool earlier = w < rfirst && v != 0xffffu;  // tasks before mine belong to the jobs before mine
-          if (earlier && v == ca) { ta = true; sa = w; }
-          if (earlier && v == cb) { tb = true; sb = w; }
+#pragma unroll
+          for (int e = 0; e < kEnt; ++e)
+            if (earlier && v == ce[e]) { te[e] = true; se[e] = w; }
         }
-        const unsigned fa = __ballot_sync(kFullMask, ca != 0xffffu && !ta), fbm = __ballot_sync(kFullMask, cb != 0xffffu && !tb);
-        const unsigned tk = __ballot_sync(kFullMask, ta || tb);
-        // bit i of free8 = entry i of the list is free: entry 2k+e sits in lane rg+k, ballot e
-        const uint32_t xa = (fa >> rg) & 0xFu, xb = (fbm >> rg) & 0xFu;
-        const uint32_t free8 = ((xa & 1u) | ((xa & 2u) << 1) | ((xa & 4u) << 2) | ((xa & 8u) << 3)) |
-                               (((xb & 1u) | ((xb & 2u) << 1) | ((xb & 4u) << 2) | ((xb & 8u) << 3)) << 1);
-        const bool any_taken = ((tk >> rg) & 0xFu) != 0;
+        // bit i of freem = entry i of the list is free: entry kEnt*k+e sits in lane rg+k, ballot e
+        uint32_t freem = 0;
+        bool mine_taken = false;
+#pragma unroll
+        for (int e = 0; e < kEnt; ++e) {
+          const uint32_t x = (__ballot_sync(kFullMask, ce[e] != 0xffffu && !te[e]) >> rg) & 0xFu;
+          freem |= ((x & 1u) | ((x & 2u) << (kEnt - 1)) | ((x & 4u) << (2 * kEnt - 2)) | ((x & 8u) << (3 * kEnt - 3))) << e;
+          mine_taken = mine_taken || te[e];
+        }
+        const bool any_taken = ((__ballot_sync(kFullMask, mine_taken) >> rg) & 0xFu) != 0;
         rstop = 0;
         if (!ract) rstop = 1;
-        else if ((uint32_t)__popc(free8) < rK) rstop = (rmode && !any_taken) ? 2u : 1u;  // too few capable nodes at all : wait for the taken ones
-        const uint32_t ia = 2 * rk, ib = 2 * rk + 1;
-        ranka = (uint32_t)__popc(free8 & ((1u << ia) - 1u));
-        rankb = (uint32_t)__popc(free8 & ((1u << ib) - 1u));
-        cha = !rstop && ((free8 >> ia) & 1u) && ranka < rK;
-        chb = !rstop && ((free8 >> ib) & 1u) && rankb < rK;
-        chosen8 = 0;
-        if (!rstop) { chosen8 = free8; while ((uint32_t)__popc(chosen8) > rK) chosen8 &= ~(1u << (31 - __clz((int)chosen8))); }
-        if (cha) s_pick[cur ^ 1u][rfirst + ranka] = (uint16_t)ca;
-        if (chb) s_pick[cur ^ 1u][rfirst + rankb] = (uint16_t)cb;
+        else if ((uint32_t)__popc(freem) < rK) rstop = (rmode && !any_taken) ? 2u : 1u;  // too few capable nodes at all : wait for the taken ones
+        chosenm = 0;
+        if (!rstop) { chosenm = freem; while ((uint32_t)__popc(chosenm) > rK) chosenm &= ~(1u << (31 - __clz((int)chosenm))); }
+#pragma unroll
+        for (int e = 0; e < kEnt; ++e) {
+          const uint32_t i = kEnt * rk + e;
+          ranke[e] = (uint32_t)__popc(freem & ((1u << i) - 1u));
+          che[e] = (chosenm >> i) & 1u;
+          if (che[e]) s_pick[cur ^ 1u][rfirst + ranke[e]] = (uint16_t)ce[e];
+        }
         __syncwarp();
-        const bool changed = lane < 8 && (uint32_t)s_pick[cur ^ 1u][lane] != mine_old;
+        const bool changed = lane < 16 && (uint32_t)s_pick[cur ^ 1u][lane] != mine_old;
         cur ^= 1u;
+        PROF_CNT(8, 1);
         if (!__any_sync(kFullMask, changed)) break;
       }
+      PROF(5);
       // tasks: node, new cost, job
-      const uint32_t na = ca, nb_ = cb;
-      if (cha) {
-        const uint32_t w = rfirst + ranka;
-        sm.list[w] = (uint16_t)na;
-        s_newcost[w] = rmode ? s_sel[rt].nc1[2 * rk] : s_sel[rt].nc0[2 * rk];
-        s_task[w].slot = rslot; s_task[w].mode = rmode; s_task[w].tfirst = rfirst; s_task[w].job = rt;
-      }
-      if (chb) {
-        const uint32_t w = rfirst + rankb;
-        sm.list[w] = (uint16_t)nb_;
-        s_newcost[w] = rmode ? s_sel[rt].nc1[2 * rk + 1] : s_sel[rt].nc0[2 * rk + 1];
-        s_task[w].slot = rslot; s_task[w].mode = rmode; s_task[w].tfirst = rfirst; s_task[w].job = rt;
+#pragma unroll
+      for (int e = 0; e < kEnt; ++e) {
+        if (che[e]) {
+          const uint32_t w = rfirst + ranke[e];
+          sm.list[w] = (uint16_t)ce[e];
+          s_newcost[w] = rmode ? s_sel[rt].nc1[kEnt * rk + e] : s_sel[rt].nc0[kEnt * rk + e];
+          s_task[w].slot = rslot; s_task[w].mode = rmode; s_task[w].tfirst = rfirst; s_task[w].job = rt;
+        }
       }
       if (lane < (uint32_t)kBatch) s_joblabel[lane] = 0;
       __syncwarp();
@@ -2268,13 +2251,18 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       // wait for that node's update
       bool clash = false;
       {
-        const bool live = !rstop && chosen8 != 0;
-        const uint32_t lastbit = live ? 31u - (uint32_t)__clz((int)chosen8) : 0u;
-        const uint32_t q_last = __shfl_sync(kFullMask, (lastbit & 1u) ? nb_ : na, (int)(rg + (lastbit >> 1)));
+        const bool live = !rstop && chosenm != 0;
+        const uint32_t lastbit = live ? 31u - (uint32_t)__clz((int)chosenm) : 0u;
+        uint32_t mine_sel = ce[0];
+#pragma unroll
+        for (int e = 1; e < kEnt; ++e)
+          if (lastbit % (uint32_t)kEnt == (uint32_t)e) mine_sel = ce[e];
+        const uint32_t q_last = __shfl_sync(kFullMask, mine_sel, (int)(rg + lastbit / (uint32_t)kEnt));
         if (live) {
           const double c_last = sm.cost[q_last];
-          if (ta && 2 * rk < lastbit) clash = key_lt(s_newcost[sa], na, c_last, q_last);
-          if (tb && 2 * rk + 1 < lastbit) clash = clash || key_lt(s_newcost[sb], nb_, c_last, q_last);
+#pragma unroll
+          for (int e = 0; e < kEnt; ++e)
+            if (te[e] && kEnt * rk + e < lastbit) clash = clash || key_lt(s_newcost[se[e]], ce[e], c_last, q_last);
         }
       }
       const unsigned badm = __ballot_sync(kFullMask, rstop != 0 || clash);
@@ -2287,8 +2275,9 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         need_single = njr == 0;
       }
       const uint32_t NT = njr ? __shfl_sync(kFullMask, rneed, (int)((njr - 1u) * 4u)) : 0u;
-      if (cha && rt < njr) sm.pend[na] = 1;
-      if (chb && rt < njr) sm.pend[nb_] = 1;
+#pragma unroll
+      for (int e = 0; e < kEnt; ++e)
+        if (che[e] && rt < njr) sm.pend[ce[e]] = 1;
       __syncwarp();
       PROF(6);
       if (NT) {
@@ -2312,15 +2301,12 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         // lowering them: either value is a valid upper bound.)
         while (*(volatile uint32_t*)&s_found < NT) {}
         __syncwarp();
-        bool rebuilt = false, stale = false;
+        bool rebuilt = false;
         for (uint32_t t = 0; t < NT; ++t) {
           const uint32_t q = sm.list[t];
           const double nc = t < f ? s_newcost[t] : sm.cost[q];
-          int r = 0;
-          if (!rebuilt) r = bucket_place(sm, q, nc, stale ? bucket_find(sm, q, nc, first_bucket) : s_tbk[t]);
-          if (r == 0) leftover_insert(q, nc, rebuilt);
+          if (rebuilt || !bucket_place(sm, q, nc, s_tbk[t])) leftover_insert(q, nc, rebuilt);
           else if (lane == 0) sm.pend[q] = 0;
-          stale = stale || r == 2;
         }
         __syncwarp();
         PROF(10);
