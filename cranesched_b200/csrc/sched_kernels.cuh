@@ -1935,19 +1935,11 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
           any_cand = any_cand || cm != 0;
           PROF_CNT(8, __popc(cm));
           while (cm && nsel < K) {
-            if (K == 1) {
-              // one-node job: the driver tests (and on success updates) the node itself
-              const uint32_t l = (uint32_t)__ffs((int)cm) - 1u;
-              cm &= cm - 1u;
-              const uint32_t qc = __shfl_sync(kFullMask, q, (int)l);
-              if (lane == 0) sm.list[0] = (uint16_t)qc;
-              __syncwarp();
-              PROF_CNT(9, 1);
-              if (worker_step(&s_cx, OP_NOW_K1, 1, slot, a.now, 0, 1, 0)) nsel = 1;
-            } else {
+            {
               // hand the next candidates to the workers, one each, in order
-              uint32_t W = K - nsel;
-              W = W < nw ? W : nw;
+              // (as many as there are workers: tests have no side effects, and the
+              // walk usually has to go past a few candidates that fail the exact test)
+              const uint32_t W = nw;
               uint32_t cnt = 0;
               unsigned taken = 0;
               while (cm && cnt < W) {
@@ -1965,7 +1957,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
               // keep the passing ones, in order, compacted at list[nsel..)
               uint32_t keep = nsel;
               for (uint32_t w = 0; w < cnt; ++w) {
-                if (s_res[w]) {
+                if (s_res[w] && keep < K) {
                   const uint16_t v = sm.list[nsel + w];
                   __syncwarp();
                   if (lane == 0) sm.list[keep] = v;
@@ -2013,7 +2005,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       placed = true;
       start_time = a.now;
       PROF_CNT(10, 1);
-      if (K > 1) multi_step(OP_UPDATE_NOW, K, slot, a.now, 0);
+      multi_step(OP_UPDATE_NOW, K, slot, a.now, 0);
     } else {
       // ---- backfill: the first K capable nodes in cost order, allocation
       // against res_total, earliest common start (JobScheduler.cpp:5269-5278,
