@@ -44,6 +44,24 @@ def test_timeline_cap_and_window(oracle, gpu_lib, seed):
     assert_same(ref, got)
 
 
+@pytest.mark.parametrize("seed", range(100, 124))
+def test_random_sweep(oracle, gpu_lib, seed):
+    """Small clusters of many shapes: partition sizes around the batch width (7
+    nodes), one big partition, caps, short limits — the batch machinery of
+    k_commit (selection lists, resolve, re-keying) under varied contention."""
+    shapes = [dict(n_nodes=7, n_parts=1), dict(n_nodes=8, n_parts=1), dict(n_nodes=20, n_parts=2),
+              dict(n_nodes=70, n_parts=1), dict(n_nodes=130, n_parts=3), dict(n_nodes=33, n_parts=4)]
+    kw = dict(shapes[seed % len(shapes)])
+    kw.update(n_jobs=250 + 37 * (seed % 11), n_running=seed % 40, fifo=bool(seed % 5 == 0), short=bool(seed % 2))
+    if seed % 7 == 0:
+        kw["max_jobs_per_node"] = 9
+    case = synth.random_case(seed, **kw)
+    ref, _, _ = oracle.node_select(*case[:4], case[4])
+    got, _ = run_sched(case, gpu_lib)
+    assert_same(ref, got)
+    check_invariants(case, got)
+
+
 def test_batch_limit(oracle, gpu_lib):
     """ScheduledBatchSize: ranks beyond the limit get "Priority"."""
     case = synth.random_case(50, n_jobs=500, n_nodes=40, n_running=20, limit=137)
