@@ -677,7 +677,6 @@ struct CommitSmem {
   long long* bmax_cpu;         // [nb]  >= cpu0 of every node in the bucket
   long long* bmax_cpug;        // [nb]  >= cpu0 of every node in the bucket that still has a free gres slot
   unsigned long long* bmax_g;  // [nb]  >= gcnt (per byte) of every node in the bucket
-  uint32_t* block;             // [nb]  bucket lock of the parallel inserts
   uint16_t* bk;                // [nb][kBucket] node ids, ascending (cost, node); buckets ascending
   uint16_t* bcnt;              // [nb]
   uint16_t* blast;             // [nb]  last (largest-key) node of the bucket, 0xffff = empty
@@ -695,7 +694,7 @@ __host__ __device__ inline uint32_t commit_nbuckets(uint32_t mp) { return (mp + 
 __host__ __device__ inline size_t commit_smem_bytes(uint32_t mp, uint32_t words) {
   const size_t nb = commit_nbuckets(mp);
   size_t b = (size_t)kRing * words * 4;
-  b += (size_t)mp * 8 * 3 + nb * 8 * 3 + nb * 4 + nb;
+  b += (size_t)mp * 8 * 3 + nb * 8 * 3 + nb;
   b += nb * kBucket * 2 + nb * 2 * 2;
   b += (size_t)mp * 2 * 4;
   b += (size_t)mp * 3;
@@ -1553,9 +1552,8 @@ __device__ __noinline__ long long worker_step(const WorkerCtx* cxp, uint32_t kin
       // the timelines are updated below.
       const uint32_t tbk = bucket_find(sm, q, ok ? cx.newcost[first] : sm.cost[q], *cx.first_bucket);
       if (lane == 0) {
-        cx.tbk[first] = tbk;
         __threadfence_block();
-        atomicAdd(cx.found, 1u);
+        *(volatile uint32_t*)&cx.tbk[first] = tbk;  // the driver polls this word
       }
     }
     const bool do_update = ((kind == OP_NOW_K1 || kind == OP_BF_K1 || kind == OP_NOW_MULTI || kind == OP_BF_MULTI) && ok) ||
@@ -1628,7 +1626,6 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     sm.bmax_cpu = reinterpret_cast<long long*>(ptr); ptr += (size_t)sm.nb * 8;
     sm.bmax_cpug = reinterpret_cast<long long*>(ptr); ptr += (size_t)sm.nb * 8;
     sm.bmax_g = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)sm.nb * 8;
-    sm.block = reinterpret_cast<uint32_t*>(ptr); ptr += (size_t)sm.nb * 4;
     sm.bk = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)sm.nb * kBucket * 2;
     sm.bcnt = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)sm.nb * 2;
     sm.blast = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)sm.nb * 2;
@@ -1673,7 +1670,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     sm.pend[q] = 0;
   }
   if (threadIdx.x < kMaxClasses) s_classrow[threadIdx.x] = a.cl.class_rows[(size_t)part * kMaxClasses + threadIdx.x];
-  for (uint32_t b = threadIdx.x; b < sm.nb; b += blockDim.x) { sm.bcnt[b] = 0; sm.block[b] = 0; }
+  for (uint32_t b = threadIdx.x; b < sm.nb; b += blockDim.x) sm.bcnt[b] = 0;
   if (threadIdx.x == 0) {
     s_label = 0;
     s_cx.cl = a.cl; s_cx.tl = a.tl; s_cx.out = a.out; s_cx.sm = sm; s_cx.jobs = s_jobs; s_cx.classrow = s_classrow;
@@ -1724,7 +1721,14 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
           __syncthreads();  // the verdict barrier inside the batch step
         }
       } else if (c.kind == OP_SELECT) {
-        if (wid - 1 < c.n) select_step(&s_cx, wid - 1);
+        if (wid - 1 < c.n) {
+          select_step(&s_cx, wid - 1);
+          if (lane == 0) {
+            __threadfence_block();
+            atomicAdd(&s_found, 1u);  // the driver polls this count instead of a CTA barrier
+          }
+        }
+        continue;
       } else if (c.kind == OP_NOW_MULTI || c.kind == OP_BF_MULTI) {
         if (wid < c.n) r = worker_step(&s_cx, c.kind, c.n, c.slot, c.t0, wid, 1, 0);
         else multi_idle(&s_cx, c.kind, c.n);
@@ -2130,9 +2134,10 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
     bool single = nj == 0;
     if (nj) {
       while (first_bucket + 1 < sm.nb && sm.bcnt[first_bucket] == 0) ++first_bucket;
-      if (lane == 0) { s_first_bucket = first_bucket; s_cmd.kind = OP_SELECT; s_cmd.n = nj; }
+      if (lane == 0) { s_first_bucket = first_bucket; s_cmd.kind = OP_SELECT; s_cmd.n = nj; s_found = 0; }
       __syncthreads();  // helpers list the candidates
-      __syncthreads();  // lists are in
+      while (*(volatile uint32_t*)&s_found < nj) {}
+      __syncwarp();     // lists are in
       PROF(3);
       // ---- resolve: 4 lanes per job, 2 list entries per lane -----------------------
       // In job order each job takes its first K free candidates; "free" depends on
@@ -2273,7 +2278,8 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       __syncwarp();
       PROF(6);
       if (NT) {
-        if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = NT; s_found = 0; }
+        if (lane == 0) { s_cmd.kind = OP_BATCH_P; s_cmd.n = NT; }
+        if (lane < NT) s_tbk[lane] = 0xffffffffu;
         __syncthreads();                  // the helpers start evaluating
         bucket_remove_pending(sm, NT);    // meanwhile the picks leave the order
         __syncthreads();                  // verdicts are in
@@ -2291,13 +2297,14 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         // looked up its node's bucket; the inserts themselves are done here, one
         // after the other. (The bucket bounds read cpu0/gcnt while a commit may be
         // lowering them: either value is a valid upper bound.)
-        while (*(volatile uint32_t*)&s_found < NT) {}
-        __syncwarp();
         bool rebuilt = false;
         for (uint32_t t = 0; t < NT; ++t) {
           const uint32_t q = sm.list[t];
           const double nc = t < f ? s_newcost[t] : sm.cost[q];
-          if (rebuilt || !bucket_place(sm, q, nc, s_tbk[t])) leftover_insert(q, nc, rebuilt);
+          uint32_t tbt;
+          while ((tbt = *(volatile uint32_t*)&s_tbk[t]) == 0xffffffffu) {}  // its helper is still searching
+          __syncwarp();
+          if (rebuilt || !bucket_place(sm, q, nc, tbt)) leftover_insert(q, nc, rebuilt);
           else if (lane == 0) sm.pend[q] = 0;
         }
         __syncwarp();
