@@ -744,6 +744,13 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 
 // ResourceView::GetFeasibleResourceInNode with the concrete pick, one shared
 // out-of-line instance (keeps the per-job instruction footprint small)
+// body of a polling loop on a shared-memory word
+__device__ __forceinline__ void spin_pause() {
+#ifdef CRANE_EMU
+  sched_yield();  // the emulation runs more host threads than cores
+#endif
+}
+
 // named barrier among `nthreads` threads (whole warps) of the CTA; id 1..15 (0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 #ifdef CRANE_EMU
@@ -2136,7 +2143,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
       while (first_bucket + 1 < sm.nb && sm.bcnt[first_bucket] == 0) ++first_bucket;
       if (lane == 0) { s_first_bucket = first_bucket; s_cmd.kind = OP_SELECT; s_cmd.n = nj; s_found = 0; }
       __syncthreads();  // helpers list the candidates
-      while (*(volatile uint32_t*)&s_found < nj) {}
+      while (*(volatile uint32_t*)&s_found < nj) spin_pause();
       __syncwarp();     // lists are in
       PROF(3);
       // ---- resolve: 4 lanes per job, 2 list entries per lane -----------------------
@@ -2302,7 +2309,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
           const uint32_t q = sm.list[t];
           const double nc = t < f ? s_newcost[t] : sm.cost[q];
           uint32_t tbt;
-          while ((tbt = *(volatile uint32_t*)&s_tbk[t]) == 0xffffffffu) {}  // its helper is still searching
+          while ((tbt = *(volatile uint32_t*)&s_tbk[t]) == 0xffffffffu) spin_pause();  // its helper is still searching
           __syncwarp();
           if (rebuilt || !bucket_place(sm, q, nc, tbt)) leftover_insert(q, nc, rebuilt);
           else if (lane == 0) sm.pend[q] = 0;

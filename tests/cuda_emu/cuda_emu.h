@@ -16,6 +16,7 @@
 #pragma once
 
 #include <atomic>
+#include <sched.h>
 #include <barrier>
 #include <condition_variable>
 #include <mutex>

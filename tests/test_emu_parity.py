@@ -12,8 +12,9 @@ CASES = {
     "config2_tiny_no_running": lambda: synth.config2(n_jobs=160, n_nodes=20),
     "random_multifactor": lambda: synth.random_case(11, n_jobs=100, n_nodes=20, n_running=12),
     # one partition above the 64-node threshold of the parallel (locked) re-inserts
-    "big_partition": lambda: synth.random_case(13, n_jobs=260, n_nodes=80, n_parts=1, n_running=10, short=True),
-    "big_partition_cfg2": lambda: synth.config2(n_jobs=300, n_nodes=200),
+    # partitions larger than a batch: selection lists, resolve, re-keying
+    "big_partition": lambda: synth.random_case(13, n_jobs=200, n_nodes=80, n_parts=1, n_running=10, short=True),
+    "big_partition_cfg2": lambda: synth.config2(n_jobs=240, n_nodes=200),
     "random_fifo_cap": lambda: synth.random_case(12, n_jobs=90, n_nodes=10, n_parts=2, n_running=6, fifo=True,
                                                  max_jobs_per_node=12, short=True),
 }
