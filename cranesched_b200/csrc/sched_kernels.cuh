@@ -1256,13 +1256,13 @@ enum : uint32_t {
   OP_UPDATE_BF = 5,  // workers: allocate against res_total and update their share
   OP_NOW_MULTI = 9,  // K <= warps: worker w tests list[w]; if all K pass, each updates its node
   OP_BF_MULTI = 10,  // K <= warps: worker w iterates the common earliest start with the others, then updates
-  OP_BATCH_P = 6,    // batch of one-node jobs: worker w evaluates task w (no state change)
+  OP_BATCH_P = 6,    // batch: helper w+1 evaluates task w, and after the verdict commits it if its job is placed
   OP_SELECT = 12,    // helper t < n lists the candidates of batch job t
   OP_EXIT = 8,
 };
 struct BatchTask {   // one (job, node) pair of the batch in flight; its node is sm.list[w]
   uint32_t slot;     // ring slot of the job
-  uint32_t mode;     // 0 = immediate start, 1 = backfill (one-node jobs only)
+  uint32_t mode;     // 0 = immediate start, 1 = backfill
   uint32_t tfirst;   // first task of the same job (its nodes are list[tfirst .. tfirst + node_num))
   uint32_t job;      // index of the job in the batch
 };

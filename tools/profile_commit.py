@@ -6,9 +6,9 @@ from cranesched_b200 import synth, abi
 from cranesched_b200.scheduler import GpuScheduler
 from cranesched_b200.build import CSRC
 
-NAMES = ["0 single: job load", "1 batch: loop top", "2 single: scan+test(+update)", "3 batch: select node", "4 resolve: load lists",
-         "5 resolve: fixed point", "6 batch: bookkeeping+rekey", "7 single: outputs+rekey", "8 #resolve rounds", "9 batch: P phase (eval)", "10 batch: C phase (commit)",
-         "11 batch: rollback", "12 #re-deals of the order", "13 #committed in batches", "14 #batches", "15 single: entry"]
+NAMES = ["0 single: job load", "1 batch: loop top", "2 single: scan+test(+update)", "3 batch: form + select", "4 resolve: load lists",
+         "5 resolve: fixed point", "6 batch: tasks + clash check", "7 single: outputs+rekey", "8 #resolve rounds", "9 batch: evaluate", "10 batch: re-key (driver)",
+         "11 batch: wait for commits", "12 #re-deals of the order", "13 #committed in batches", "14 #batches", "15 single: entry"]
 TIMED = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 15}
 cfg_id = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 kw = {}
