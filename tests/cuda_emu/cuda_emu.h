@@ -92,7 +92,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes,
     abort();
   }
   BlockCtx bc(nt);
-  bc.dyn_smem.assign(smem_bytes + 16, 0);
+  bc.dyn_smem.assign(smem_bytes + 16, (unsigned char)(getenv("CRANE_EMU_SMEM_FILL") ? atoi(getenv("CRANE_EMU_SMEM_FILL")) : 0));
   auto worker = [&](int t) {
     tctx.bdim = block;
     tctx.gdim = grid;
