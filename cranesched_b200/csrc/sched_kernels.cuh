@@ -1771,6 +1771,7 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
 
   // ring slot of job i is free once job i-kRing is finished
   auto ensure_issued = [&](uint32_t finished) {
+    __syncwarp();  // no lane is still reading the ring slots of finished jobs
     const uint32_t hi = njobs < finished + (uint32_t)kRing ? njobs : finished + (uint32_t)kRing;
     if (issued < hi) {  // at most kRing <= 32 records: one lane each
       if (issued + lane < hi) issue(issued + lane);
@@ -2320,12 +2321,21 @@ __global__ void __launch_bounds__(kCommitThreads, 1) k_commit(CommitArgs a) {
         // jobs placed = those whose tasks all lie before the cut
         uint32_t done = 0;
         for (uint32_t t = 0; t < njr; ++t) done += s_bj[t].need <= f ? 1u : 0u;
+        // A failed backfill is final: the reference takes exactly these nodes (the
+        // first K capable ones) and gives up when they have no common start inside
+        // the window (JobScheduler.cpp:5371-5404, 5802). Only a failed immediate
+        // start has to continue its walk on the one-job path.
+        const bool final_fail = f < NT && s_task[f].mode == 1u;
+        if (final_fail) {
+          if (lane == 0) a.out.reason[s_jobs[s_task[f].slot].job] = CRANE_REASON_RESOURCE;
+          ++done;
+        }
         PROF_CNT(13, done);
         PROF_CNT(14, 1);
         PROF(11);
         BUCKET_CHECK("batch", ji);
         ji += done;
-        single = f < NT;  // the failing job is next
+        single = f < NT && !final_fail;  // the failing job is next
       } else {
         single = need_single || njr == 0;
       }
