@@ -14,6 +14,8 @@ cfg_id = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 kw = {}
 if len(sys.argv) > 3:
     kw = dict(n_jobs=int(sys.argv[2]), n_nodes=int(sys.argv[3]))
+if os.environ.get("SEED_ID"):
+    kw["seed_id"] = int(os.environ["SEED_ID"])
 cfg, cl, rn, pd, now = synth.CONFIGS[cfg_id](**kw)
 s = GpuScheduler(cfg, 0, os.path.join(CSRC, "libcrane_sched_prof.so"))
 s.set_cluster(cl)
