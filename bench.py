@@ -268,7 +268,7 @@ def main():
             "scaling": "weak", "vs_baseline": None,
             "dtype": "int64 cpu / u64 mem + bit masks; f64 cost and priority", "data": "synthetic",
             "config": {"workload": workload_name(args), "per_gpu_jobs": pd.n, "per_gpu_nodes": cl.n_nodes,
-                       "partitions_per_gpu": cl.n_partitions, "sharding": "by partition (independent LocalSchedulers)",
+                       "partitions_per_gpu": cl.n_partitions, "sharding": "by partition (independent LocalSchedulers); every rank schedules its own copy of the same synthetic draw (equal per-GPU work)",
                        "l2": "256 MiB flush write between timed iterations",
                        "started_now": placed_now, "backfill_reserved": reserved},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

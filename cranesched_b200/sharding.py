@@ -16,8 +16,12 @@ from . import abi, synth
 
 
 def shard_workload(config_id: int, rank: int, world: int, n_jobs: int = 0, n_nodes: int = 0):
-    """Weak-scaling shard: rank r gets its own config-shaped set of partitions
-    (a disjoint slice of a `world`-times larger cluster), seeded per rank."""
+    """Weak-scaling shard: rank r gets its own config-shaped set of partitions (a
+    disjoint slice of a `world`-times larger cluster). Every rank's slice is
+    generated from the same seed, so the per-GPU work is the same for every N —
+    the definition of weak scaling; with per-rank seeds the max over ranks
+    measures the spread of the synthetic workloads instead (one of eight
+    config-2 draws takes 1.8x the cycles of the others)."""
     gen = synth.CONFIGS[config_id]
     kw = {}
     if n_jobs:
@@ -25,7 +29,7 @@ def shard_workload(config_id: int, rank: int, world: int, n_jobs: int = 0, n_nod
     if n_nodes:
         kw["n_nodes"] = n_nodes
     if config_id != 1:
-        kw["seed_id"] = config_id + 1000 * rank
+        kw["seed_id"] = config_id
     return gen(**kw)
 
 

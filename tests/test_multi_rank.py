@@ -65,4 +65,4 @@ def test_two_ranks_gloo(oracle, emu_lib):
         assert ok_weak, f"rank {rank}: shard result differs from the oracle"
         assert ok_split, f"rank {rank}: partition split does not reproduce the unsplit answer"
         assert total == 180.0 and tmax == 20.0  # sum of decisions, max of times
-        assert seeds[0] != seeds[1]  # ranks schedule different queues
+        assert seeds[0] == seeds[1]  # weak scaling: every rank gets the same draw (equal per-GPU work)
