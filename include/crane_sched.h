@@ -290,7 +290,11 @@ typedef struct crane_qos_table {
  * job that NodeSelect starts now is checked against its (user,qos), account
  * chain and qos limits and, if it passes, added to the usage; a job that fails
  * gets the QoS reason code (it keeps the timeline reservation it made, as in
- * the reference). `reason` ([n_pending], host) receives the updated reasons. */
+ * the reference). `reason` ([n_pending], host) receives the updated reasons.
+ * Needs pending.qos and pending.user at upload. CRANE_ENOSYS for an account
+ * chain longer than 30, CRANE_EINVAL for an account repeated inside a chain or
+ * ids outside the tables. Usage maps are dense here, so the reference's
+ * "QosResourceLimit" (entry missing from a map) cannot occur. */
 int crane_sched_qos_filter(crane_sched_t* h, const crane_qos_table_t* qos, uint8_t* reason);
 
 /* Capability bitmap of the last run (the jobs x nodes feasibility bitmap):
