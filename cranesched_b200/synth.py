@@ -267,11 +267,16 @@ def config5(n_jobs=200_000, n_nodes=5_000, seed_id=5):
 # ---------------------------------------------------------------------------
 def random_case(seed, n_jobs=300, n_nodes=48, n_parts=3, n_running=40, fifo=False,
                 frac_cpu=True, lists=True, exclusive=True, limit=None,
-                max_jobs_per_node=1000, short=False):
+                max_jobs_per_node=1000, short=False, one_type_per_name=False, ntpn_range=False):
+    """one_type_per_name: no node carries two types of the same gres name, so the
+    reference's unordered_map walk over a node's types (PublicHeader.cpp:564,583)
+    has a single possible order — the cases oracle/_ref can pin (tests/test_ref_pin.py)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     names = (0, 0, 1)  # gpu:a, gpu:b, npu:x
     kinds = [node_row(16, 64 * GiB), node_row(32, 128 * GiB, {0: 4, 1: 4}),
              node_row(24, 96 * GiB, {0: 2, 2: 8}), node_row(8, 32 * GiB, {1: 8})]
+    if one_type_per_name:
+        kinds[1] = node_row(32, 128 * GiB, {0: 4, 2: 4})
     sizes = rng.multinomial(n_nodes - n_parts, np.ones(n_parts) / n_parts) + 1
     rows, off, base = [], [0], 0
     for p in range(n_parts):
@@ -377,6 +382,11 @@ def random_case(seed, n_jobs=300, n_nodes=48, n_parts=3, n_running=40, fifo=Fals
     multi = rng.random(n_jobs) < 0.2
     tpn[multi] = rng.integers(2, 4, int(multi.sum()))
     ntasks = node_num * tpn
+    tpn_max = tpn.copy()
+    if ntpn_range:  # general task distribution: ntasks anywhere in [node_num*min, node_num*max]
+        wide = rng.random(n_jobs) < 0.5
+        tpn_max[wide] = tpn[wide] + rng.integers(1, 4, int(wide.sum()))
+        ntasks = (node_num * tpn + rng.integers(0, 1 << 30, n_jobs) % (node_num * (tpn_max - tpn) + 1)).astype(np.uint32)
     gt, gs = gres_req(n_jobs, part)
     mem_task = rng.integers(1, 9, n_jobs).astype(np.uint64) * GiB // 2
     mem_node = np.where(rng.random(n_jobs) < 0.2, rng.integers(0, 4, n_jobs), 0).astype(np.uint64) * GiB
@@ -406,7 +416,7 @@ def random_case(seed, n_jobs=300, n_nodes=48, n_parts=3, n_running=40, fifo=Fals
                     account=rng.integers(0, 6, n_jobs).astype(np.uint32),
                     qos=rng.integers(0, 3, n_jobs).astype(np.uint32),
                     user=rng.integers(0, 20, n_jobs).astype(np.uint32),
-                    exclusive=excl_flag, ntpn=(tpn, tpn.copy()), mandated=mand,
+                    exclusive=excl_flag, ntpn=(tpn, tpn_max), mandated=mand,
                     incl=incl, excl=excl)
     cfg = Config(priority_type=0 if fifo else 1, scheduled_batch_size=limit or n_jobs,
                  max_jobs_per_node=max_jobs_per_node,

@@ -158,6 +158,8 @@ enum {
   CRANE_REASON_RESOURCE = 2,       /* "Resource"                              */
   CRANE_REASON_RESERVED = 3,       /* "Resource Reserved"                     */
   CRANE_REASON_PART_NOT_FOUND = 4, /* "Partition Not Found"                   */
+  CRANE_REASON_RESV_NOT_FOUND = 5, /* "Reservation Not Found" (JS.cpp:5793)   */
+  CRANE_REASON_PREEMPTED = 6,      /* "Preempted" (JS.cpp:5815)               */
   /* written by crane_sched_qos_filter (Accounting/AccountMetaContainer.cpp:382-531) */
   CRANE_REASON_QOS_CPU = 16,       /* "QosCpuResourceLimit"                   */
   CRANE_REASON_QOS_JOBS = 17,      /* "QosJobsResourceLimit"                  */
