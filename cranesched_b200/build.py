@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "cranesched_b200", "csrc")
 SO = os.path.join(CSRC, "libcrane_sched.so")
 EMU_SO = os.path.join(ROOT, "tests", "_emu", "libcrane_sched_emu.so")
-_SOURCES = ["sched_api.cu", "sched_kernels.cuh", "qos_kernels.cuh", "algebra.cuh"]
+_SOURCES = ["sched_api.cu", "sched_kernels.cuh", "commit_v2.cuh", "qos_kernels.cuh", "algebra.cuh"]
 
 
 def _stale(target: str, extra=()) -> bool:

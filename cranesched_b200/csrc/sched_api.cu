@@ -25,6 +25,7 @@
 
 #include "../../include/crane_sched.h"
 #include "sched_kernels.cuh"
+#include "commit_v2.cuh"
 #include "qos_kernels.cuh"
 
 using namespace crane;
@@ -64,6 +65,9 @@ struct crane_sched {
   std::string err;
   crane_sched_timing_t timing{};
   int commit_threads = kCommitThreads;
+  bool use_v1 = false;        // CRANE_COMMIT_V1=1: the round-1 kernel (A/B runs only)
+  size_t v2_budget = 0;       // dynamic shared memory k_commit2 may use
+  uint32_t v2_ring = 0;
 
   // cluster (host copies)
   bool have_cluster = false;
@@ -206,6 +210,18 @@ int crane_sched_create(const crane_sched_config_t* cfg, int device, crane_sched_
   if (!getenv("CRANE_COMMIT_THREADS")) h->commit_threads = 128;
 #endif
   cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  if (const char* s = getenv("CRANE_COMMIT_V1")) h->use_v1 = atoi(s) != 0;
+  {
+    // k_commit2: everything the SM has beyond the kernel's static tables
+    size_t stat = 20 * 1024;
+#ifndef CRANE_EMU
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k_commit2) == cudaSuccess) stat = fa.sharedSizeBytes;
+#endif
+    const size_t sm_total = 227 * 1024;
+    h->v2_budget = sm_total > stat + 1024 ? sm_total - stat - 1024 : 0;
+    cudaFuncSetAttribute(k_commit2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->v2_budget);
+  }
   h->tl_cap = cfg->max_jobs_per_node + 1;
   *out = h;
   return CRANE_OK;
@@ -291,8 +307,14 @@ int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
   h->n_slots = (uint32_t)h->h_slot_node.size();
   h->max_part_slots = max_mp;
   h->words_per_row = std::max<uint32_t>(4, ((max_mp + 31) / 32 + 3) / 4 * 4);  // 16-byte rows for the bulk copies
-  if (max_mp > 65535 || commit_smem_bytes(max_mp, h->words_per_row) > kMaxDynSmem || max_mp > 32u * (uint32_t)h->commit_threads)
-    return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
+  if (h->use_v1) {
+    if (max_mp > 65535 || commit_smem_bytes(max_mp, h->words_per_row) > kMaxDynSmem || max_mp > 32u * (uint32_t)h->commit_threads)
+      return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
+  } else {
+    h->v2_ring = commit2_ring_slots(max_mp, h->words_per_row, h->v2_budget);
+    if (max_mp > 65000 || h->v2_ring == 0)
+      return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
+  }
   // res_total classes per partition (distinct rows), cached in shared memory by the commit kernel
   std::vector<uint8_t> slot_class(std::max<size_t>(slot_total.size(), 1), 0xff);
   std::vector<Row> class_rows((size_t)std::max<uint32_t>(c->n_partitions, 1) * kMaxClasses);
@@ -671,8 +693,17 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
     ca.max_jobs = h->cfg.max_jobs_per_node;
     CU(h->d_prof.ensure((size_t)h->n_parts * 16));
     ca.prof = h->d_prof.p;
-    size_t smem = commit_smem_bytes(h->max_part_slots, h->words_per_row);
-    CRANE_LAUNCH(k_commit, h->n_parts, h->commit_threads, smem, st, ca);
+    if (h->use_v1) {
+      size_t smem = commit_smem_bytes(h->max_part_slots, h->words_per_row);
+      CRANE_LAUNCH(k_commit, h->n_parts, h->commit_threads, smem, st, ca);
+    } else {
+      Commit2Args c2{};
+      c2.cl = cl; c2.tl = tl; c2.jobq = ca.jobq; c2.part_job_off = ca.part_job_off; c2.bitmap = ca.bitmap;
+      c2.words_per_row = ca.words_per_row; c2.ring = h->v2_ring; c2.out = out; c2.now = now;
+      c2.max_window = ca.max_window; c2.max_jobs = ca.max_jobs; c2.cost_policy = h->cfg.cost_policy; c2.prof = ca.prof;
+      size_t smem = commit2_smem_bytes(h->max_part_slots, h->words_per_row, h->v2_ring);
+      CRANE_LAUNCH(k_commit2, h->n_parts, kT2, smem, st, c2);
+    }
     h->timing.kernel_launches++;
   }
   CU(cudaEventRecord(h->ev[6], st));
