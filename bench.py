@@ -2,21 +2,29 @@
 """bench.py — placement decisions / second of the NodeSelect hot path.
 
 A "step" is one full scheduling tick (SchedulerAlgo::NodeSelect,
-JobScheduler.cpp:5543-5868) over one synthetic pending queue. At N=1 the
-workload is BASELINE.json configs[1]: 100k pending jobs x 10k nodes, cpu+mem+
-gres(GPU), 4 partitions, multifactor priority + backfill. At N>1 the queue
-shards by partition: rank r schedules its own config-2-shaped
-set of partitions (a disjoint slice of an N-times larger cluster; weak scaling,
-no data-path collective inside the tick; NCCL is used for the barrier and the
-max-over-ranks timing reduction).
+JobScheduler.cpp:5543-5868) over one synthetic pending queue: BASELINE.json
+configs[1], 100k pending jobs x 10k nodes, cpu+mem+gres(GPU), 4 partitions,
+multifactor priority + backfill.
 
-  value   decisions/s, tables resident in HBM when the timed region starts
-          (device time of crane_sched_run, CUDA events on the launching stream)
-  e2e     same metric through crane_sched_node_select with HOST buffers
-          (H2D of the pending table + D2H of the placements inside the region)
-  --impl reference   the CPU oracle (oracle/, a restatement of the reference's
-          single-threaded NodeSelect; the reference itself cannot be built in
-          this image) on a bounded sample of the same workload.
+  N = 1   value = decisions/s with the tables resident in HBM when the timed
+          region starts (device time of crane_sched_run, CUDA events on the
+          launching stream); e2e = the same metric through
+          crane_sched_node_select with HOST buffers (H2D of the pending table
+          + D2H of the placements inside the region).
+  N > 1   ONE queue — the same 100k x 10k queue — over N GPUs (strong scaling):
+          partitions are dealt to the ranks (cranesched_b200/sharding.py), every
+          rank commits its own partitions and the placement columns are
+          all-reduced over NCCL; the gathered result is compared with the
+          unsplit single-GPU answer inside the bench ("sharded_equals_unsplit").
+          The job loop of a partition is a dependency chain that one GPU already
+          runs concurrently with the other partitions, so more GPUs shorten the
+          tick only as far as the largest partition allows — the line reports
+          that honestly. "weak" in the same line: N independent clusters, one
+          per rank, each its own draw (seed 1000*rank + 2).
+  --impl reference   the reference's CPU NodeSelect on a bounded sample of the
+          same queue: oracle/_ref (the reference's own source compiled against
+          shim headers, kind "reference") when it was built, else the oracle
+          port (kind "port"); single thread, as the reference is.
 """
 from __future__ import annotations
 
@@ -87,8 +95,8 @@ class ClockSampler:
 
 def measured_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of k_commit from the committed
-    `ncu --set full` capture (profiles/r01_ncu_k_commit_summary.csv), per launch."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_k_commit_summary.csv")
+    `ncu --set full` capture (profiles/r02_ncu_k_commit2_summary.csv: captured on the shipped build), per launch."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_k_commit2_summary.csv")
     if not os.path.exists(p):
         return None
     tot = 0.0
@@ -113,12 +121,28 @@ def algorithmic_bytes(cluster, pending, n_decided):
     return int(b.sum()), node_row
 
 
-def workload(args, rank):
-    """Rank r's shard: its own config-shaped set of partitions (weak scaling)."""
+def workload(args, rank=0):
+    """The bench queue. rank > 0: that rank's own draw of the same shape (weak line)."""
     from cranesched_b200 import sharding
     if args.config not in (1, 2, 5):
         raise SystemExit("bench.py --config must be 1, 2 or 5")
-    return sharding.shard_workload(args.config, rank, int(os.environ.get("WORLD_SIZE", "1")), args.jobs, args.nodes)
+    return sharding.shard_workload(args.config, rank, 1, args.jobs, args.nodes)
+
+
+def cpu_reference(cfg, cl, rn, pd, now, sample):
+    """The reference's CPU NodeSelect on the first `sample` jobs of the priority
+    order (ScheduledBatchSize = sample: the rest of the queue only gets its
+    priority computed and the reason "Priority"). Returns (ms, jobs, kind)."""
+    import copy
+    from oracle import pyoracle, pyref
+    if pyref.available():
+        c2 = copy.copy(cfg)
+        c2.scheduled_batch_size = min(sample, pd.n)
+        _, ms = pyref.node_select(c2, cl, rn, pd, now)
+        return ms, int(min(sample, pd.n)), "reference"
+    pyoracle.build()
+    _, ms, done = pyoracle.node_select(cfg, cl, rn, pd, now, max_jobs=sample)
+    return ms, done, "port"
 
 
 def workload_name(args):
@@ -130,31 +154,38 @@ def workload_name(args):
 
 
 def run_reference(args, rank, world):
-    """CPU arm: the oracle, single thread like the reference's NodeSelect
-    ("TODO: do it in parallel", JobScheduler.cpp:5756,5776)."""
+    """CPU arm: the reference's NodeSelect, single thread as upstream ("TODO: do it
+    in parallel", JobScheduler.cpp:5756,5776), on a bounded sample of the queue."""
     if rank != 0:
         return
-    from oracle import pyoracle
-    pyoracle.build()
     cfg, cl, rn, pd, now = workload(args, 0)
-    sample = args.ref_sample
-    times, done = [], 0
+    times, done, kind = [], 0, "port"
     for i in range(args.warmup + args.steps):
-        _, ms, done = pyoracle.node_select(cfg, cl, rn, pd, now, max_jobs=sample)
+        ms, done, kind = cpu_reference(cfg, cl, rn, pd, now, args.ref_sample)
         if i >= args.warmup:
             times.append(ms)
     ms = float(np.mean(times))
     v = done / (ms / 1e3)
+    what = ("oracle/_ref: the reference's own JobScheduler/PublicHeader source compiled against shim headers"
+            if kind == "reference" else "oracle/: CPU restatement of NodeSelect")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int64+u64 masks, f64 cost/priority",
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "int64+u64 masks, f64 cost/priority",
             "data": "synthetic", "config": {"workload": workload_name(args)},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": "first %d jobs of the priority order of the same queue (cost per job grows as "
-                                       "the cluster fills, so this flatters the CPU)" % done},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+                             "sample": "%s, 1 thread, first %d jobs of the priority order of the same queue (cost per job "
+                                       "grows as the cluster fills, so this flatters the CPU)" % (what, done)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def digest(out):
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("reason", "priority", "start_time", "end_time", "n_alloc", "alloc_node", "alloc_ntasks", "alloc_res"):
+        h.update(np.ascontiguousarray(getattr(out, f)).tobytes())
+    return h.hexdigest()
 
 
 def main():
@@ -182,7 +213,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from cranesched_b200 import abi
+    from cranesched_b200 import abi, sharding
     from cranesched_b200.scheduler import GpuScheduler
 
     if not torch.cuda.is_available():
@@ -192,11 +223,6 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    cfg, cl, rn, pd, now = workload(args, rank)
-    sched = GpuScheduler(cfg, local_rank)
-    sched.set_cluster(cl)
-    out = abi.Placements.for_pending(pd, pinned=True)
-    # pinned copies of the pending table for the e2e leg
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def barrier():
@@ -205,96 +231,173 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sched.upload(rn, pd)
-    sched.sync()
-    dev_ms = []
-    timing_last = None
+    def reduce_max(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
 
-    def step(record):
-        flush.fill_(1)  # L2 flush between timed iterations
-        torch.cuda.synchronize()
-        sched.run(now)
-        ms = sched.sync()
-        if record:
-            dev_ms.append(ms)
+    def one_gpu_line(case):
+        """K ticks of one whole queue on this rank's GPU: (device ms total, e2e ms total,
+        wall ms, timing of the last tick, placements, clocks)."""
+        cfg, cl, rn, pd, now = case
+        sched = GpuScheduler(cfg, local_rank)
+        sched.set_cluster(cl)
+        out = abi.Placements.for_pending(pd, pinned=True)
+        sched.upload(rn, pd)
+        sched.sync()
+        dev_ms = []
 
-    for _ in range(args.warmup):
-        step(False)
-    barrier()
-    with ClockSampler(local_rank) as clocks:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step(True)
+        def step(record):
+            flush.fill_(1)  # L2 flush between timed iterations
+            torch.cuda.synchronize()
+            sched.run(now)
+            ms = sched.sync()
+            if record:
+                dev_ms.append(ms)
+
+        for _ in range(args.warmup):
+            step(False)
         barrier()
-        wall = time.perf_counter() - t0
-    timing_last = sched.timing()
-    sched.fetch(out)
+        with ClockSampler(local_rank) as clocks:
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step(True)
+            barrier()
+            wall = time.perf_counter() - t0
+        timing_last = sched.timing()
+        sched.fetch(out)
+        # e2e: host buffers through crane_sched_node_select
+        e2e_ms = []
+        for i in range(2 + args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            sched.node_select(now, rn, pd, out)
+            dt = (time.perf_counter() - t1) * 1e3
+            if i >= 2:
+                e2e_ms.append(dt)
+        barrier()
+        sched.close()
+        return float(np.sum(dev_ms)), float(np.sum(e2e_ms)), wall * 1e3, timing_last, out, clocks.summary()
+
+    case0 = workload(args, 0)
+    cfg, cl, rn, pd, now = case0
     n_decided = int(min(pd.n, cfg.scheduled_batch_size))
-    dev_total_ms = float(np.sum(dev_ms))
-
-    # ---- e2e: host buffers through crane_sched_node_select --------------------
-    e2e_ms = []
-    for i in range(2 + args.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        sched.node_select(now, rn, pd, out)
-        dt = (time.perf_counter() - t1) * 1e3
-        if i >= 2:
-            e2e_ms.append(dt)
-    barrier()
     h2d = sum(getattr(pd, f).nbytes for f in pd.__dataclass_fields__ if getattr(pd, f) is not None)
-    d2h = out.nbytes()
+    line = {"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "vs_baseline": None,
+            "dtype": "int64 cpu / u64 mem + bit masks; f64 cost and priority", "data": "synthetic"}
 
-    # max over ranks
-    t_dev = torch.tensor([dev_total_ms, float(np.sum(e2e_ms)), wall * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_total_ms, e2e_total_ms, wall_ms = [float(x) for x in t_dev.tolist()]
-    total_decided = n_decided * world
-    value = total_decided * args.steps / (dev_total_ms / 1e3)
-    e2e_value = total_decided * args.steps / (e2e_total_ms / 1e3)
+    if world == 1:
+        dev_total_ms, e2e_total_ms, wall_ms, timing_last, out, clk = one_gpu_line(case0)
+        value = n_decided * args.steps / (dev_total_ms / 1e3)
+        e2e_value = n_decided * args.steps / (e2e_total_ms / 1e3)
+        line.update({"value": value, "ms_per_step": dev_total_ms / args.steps, "scaling": "weak",
+                     "config": {"workload": workload_name(args), "jobs": pd.n, "nodes": cl.n_nodes,
+                                "partitions": cl.n_partitions, "l2": "256 MiB flush write between timed iterations",
+                                "started_now": int((out.reason == 0).sum()),
+                                "backfill_reserved": int(((out.reason != 0) & (out.n_alloc > 0)).sum())},
+                     "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                             "d2h_bytes_per_step": int(out.nbytes()), "ms_per_step": e2e_total_ms / args.steps},
+                     "gpu_launches": int(timing_last["kernel_launches"]) * args.steps,
+                     "wall_ms_per_step_incl_flush": wall_ms / args.steps, "clocks": clk})
+    else:
+        # ---- ONE queue over `world` GPUs: partitions dealt to the ranks ------------
+        owner = sharding.deal_partitions(pd, cl.n_partitions, world)
+        sched = GpuScheduler(cfg, local_rank)
+        sched.set_cluster(cl)
+        out = abi.Placements.for_pending(pd, pinned=True)
+        sched.upload(rn, pd)
+        sched.sync()
+        step_ms, e2e_ms = [], []
+        for i in range(args.warmup + args.steps):
+            flush.fill_(1)
+            barrier()
+            t1 = time.perf_counter()
+            sharding.sharded_tick(sched, now, rn, pd, owner, dist, out=out, upload=False)  # run + all-reduce + fetch
+            torch.cuda.synchronize()
+            if i >= args.warmup:
+                step_ms.append((time.perf_counter() - t1) * 1e3)
+        own_commit_ms = float(sched.timing()["commit_ms"])
+        launches = int(sched.timing()["kernel_launches"])
+        barrier()
+        with ClockSampler(local_rank) as clocks:
+            for i in range(2 + args.steps):
+                flush.fill_(1)
+                barrier()
+                t1 = time.perf_counter()
+                sharding.sharded_tick(sched, now, rn, pd, owner, dist, out=out, upload=True)  # + H2D of the whole table
+                torch.cuda.synchronize()
+                if i >= 2:
+                    e2e_ms.append((time.perf_counter() - t1) * 1e3)
+            barrier()
+        sched.close()
+        got = digest(out)
+        # the unsplit answer, on rank 0's GPU, outside the timed region
+        same = True
+        if rank == 0:
+            s1 = GpuScheduler(cfg, local_rank)
+            s1.set_cluster(cl)
+            ref_out = s1.node_select(now, rn, pd)
+            s1.close()
+            same = digest(ref_out) == got
+        tot_ms, e2e_total_ms, commit_max = reduce_max([float(np.sum(step_ms)), float(np.sum(e2e_ms)), own_commit_ms])
+        value = n_decided * args.steps / (tot_ms / 1e3)
+        jobs_per_rank = np.bincount(owner[pd.partition[pd.partition < cl.n_partitions]], minlength=world).tolist()
+        # ---- weak line: `world` independent clusters, one per rank, each its own draw --
+        wcase = workload(args, rank)
+        w_dev, w_e2e, _, w_timing, w_out, _ = one_gpu_line(wcase)
+        w_dev, w_e2e = reduce_max([w_dev, w_e2e])
+        w_dec = int(min(wcase[3].n, wcase[0].scheduled_batch_size)) * world
+        timing_last = w_timing
+        d2h = out.nbytes()
+        line.update({"value": value, "ms_per_step": tot_ms / args.steps, "scaling": "strong",
+                     "config": {"workload": workload_name(args) + " — ONE queue split over %d GPUs by partition" % world,
+                                "jobs": pd.n, "nodes": cl.n_nodes, "partitions": cl.n_partitions,
+                                "partition_owner": owner.tolist(), "jobs_per_rank": jobs_per_rank,
+                                "timed": "run of the own partitions + NCCL all-reduce(sum) of the 7 placement columns "
+                                         "+ D2H on every rank; wall clock between barriers, max over ranks",
+                                "collective_bytes_per_step": int(d2h - out.priority.nbytes - out.alloc_off.nbytes),
+                                "l2": "256 MiB flush write between timed iterations"},
+                     "sharded_equals_unsplit": bool(same),
+                     "slowest_rank_commit_ms": commit_max,
+                     "e2e": {"value": n_decided * args.steps / (e2e_total_ms / 1e3), "unit": UNIT,
+                             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                             "ms_per_step": e2e_total_ms / args.steps},
+                     "gpu_launches": launches * args.steps,
+                     "weak": {"value": w_dec * args.steps / (w_dev / 1e3), "unit": UNIT, "scaling": "weak",
+                              "workload": "%d independent clusters of the config's shape, one per GPU, each its own draw "
+                                          "(seed 1000*rank + config)" % world,
+                              "e2e_value": w_dec * args.steps / (w_e2e / 1e3), "ms_per_step": w_dev / args.steps},
+                     "clocks": clocks.summary()})
+        out = w_out if False else out
 
     if rank == 0:
         peak, peak_src = load_peaks()
         alg_bytes, node_row = algorithmic_bytes(cl, pd, n_decided)
-        commit_ms = timing_last["commit_ms"]
+        if world == 1:
+            commit_ms = timing_last["commit_ms"]
+            line["phases_ms"] = {k: round(float(v), 4) for k, v in timing_last.items() if k.endswith("_ms")}
+        else:
+            commit_ms = line["slowest_rank_commit_ms"]
         achieved = alg_bytes / (commit_ms / 1e3) / 1e9
-        placed_now = int((out.reason == 0).sum())
-        reserved = int(((out.reason != 0) & (out.n_alloc > 0)).sum())
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
-            "dtype": "int64 cpu / u64 mem + bit masks; f64 cost and priority", "data": "synthetic",
-            "config": {"workload": workload_name(args), "per_gpu_jobs": pd.n, "per_gpu_nodes": cl.n_nodes,
-                       "partitions_per_gpu": cl.n_partitions, "sharding": "by partition (independent LocalSchedulers); every rank schedules its own copy of the same synthetic draw (equal per-GPU work)",
-                       "l2": "256 MiB flush write between timed iterations",
-                       "started_now": placed_now, "backfill_reserved": reserved},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_total_ms / args.steps},
-            "gpu_launches": int(timing_last["kernel_launches"]) * args.steps,
-            "phases_ms": {k: round(float(v), 4) for k, v in timing_last.items() if k.endswith("_ms")},
-            "wall_ms_per_step_incl_flush": wall_ms / args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_commit", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic() if args.config == 2 and not args.jobs else None,
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "per decision 64 B job row + M_part x %d B node row + 16 B + 32 B x node_num "
-                                 "(SURVEY.md 8d); the job loop is a dependency chain, so the binding limit is "
-                                 "per-job latency, not DRAM" % node_row},
-            "clocks": clocks.summary(),
-        }
+        line["roofline"] = {"bound": "hbm", "kernel": "k_commit2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak,
+                            "traffic": measured_traffic() if args.config == 2 and not args.jobs and world == 1 else None,
+                            "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                            "kernel_ms": commit_ms,
+                            "note": "per decision 64 B job row + M_part x %d B node row + 16 B + 32 B x node_num "
+                                    "(SURVEY.md 8d); the job loop is a dependency chain, so the binding limit is "
+                                    "per-batch latency, not DRAM" % node_row}
         if not args.no_cpu_baseline and world == 1:
-            from oracle import pyoracle
-            pyoracle.build()
-            _, ms, done = pyoracle.node_select(cfg, cl, rn, pd, now, max_jobs=args.cpu_sample)
+            ms, done, kind = cpu_reference(cfg, cl, rn, pd, now, args.cpu_sample)
             line["cpu_baseline"] = {
-                "value": done / (ms / 1e3), "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": "oracle (CPU restatement of NodeSelect, 1 thread like the reference) on the first %d jobs "
-                          "of the priority order of the same queue, %.1f s" % (done, ms / 1e3)}
+                "value": done / (ms / 1e3), "unit": UNIT, "cores": 1, "kind": kind,
+                "sample": "%s, 1 thread like the reference, on the first %d jobs of the priority order of the same queue, %.1f s"
+                          % ("oracle/_ref (the reference's own NodeSelect source compiled against shim headers)"
+                             if kind == "reference" else "oracle (CPU restatement of NodeSelect)", done, ms / 1e3)}
         print(json.dumps(line))
-    sched.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -549,3 +549,10 @@ def _pinned_empty(shape, dt):
         pass
     a = t.numpy()[: n * dt.itemsize].view(dt)
     return a.reshape(shape)  # the ndarray keeps `t` alive through .base
+
+
+class DevicePlacementsC(C.Structure):
+    """crane_device_placements_t: device pointers of the placement columns."""
+    _fields_ = [("reason", C.c_void_p), ("start_time", C.c_void_p), ("end_time", C.c_void_p), ("n_alloc", C.c_void_p),
+                ("alloc_node", C.c_void_p), ("alloc_ntasks", C.c_void_p), ("alloc_res", C.c_void_p),
+                ("n_jobs", C.c_uint64), ("n_rows", C.c_uint64)]

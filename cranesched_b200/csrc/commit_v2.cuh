@@ -55,7 +55,11 @@ constexpr int kMaxJ = 32;          // jobs per batch
 constexpr int kMaxT = kNG;         // (job, node) tasks per batch: one group each
 constexpr int kBlk = 32;           // order positions per bounds block
 constexpr int kRingMax = 64;       // prefetch ring depth (jobs)
-constexpr int kRK = 64;            // nodes re-keyed by one event-based rebuild
+constexpr int kRK = 64;
+constexpr int kDeltaClasses = 4;
+#ifndef CRANE_SPEC_EVAL
+#define CRANE_SPEC_EVAL 1          // warps 1-7 test each slot's first guess while warp 0 resolves (A/B on config 2:
+#endif                             // 961k vs 918k decisions/s with the speculation off)   // res_total classes with a pre-computed cost delta per batch job            // nodes re-keyed by one event-based rebuild
 static_assert(kMaxT <= 32 && kMaxJ <= 32, "resolve lays a batch over one warp's ballots");
 
 struct Smem2 {
@@ -71,25 +75,25 @@ struct Smem2 {
   uint16_t* tmp;                // [mp]  re-key scratch
   uint16_t* posn;               // [mp]  position of a node
   uint16_t* nseg;               // [mp]  timeline entry count
-  uint16_t* list;               // [mp]  picks of the one-job path
+  uint16_t* list;               // = tmp: picks of the one-job path
   uint8_t* skip;                // [mp]  timeline at the size cap (JobScheduler.cpp:5230)
   uint8_t* cls;                 // [mp]  res_total class
   uint32_t nblk, ring;
 };
-__host__ __device__ inline size_t commit2_fixed_bytes(uint32_t mp) {
+__host__ __device__ inline size_t commit2_fixed_bytes(uint32_t mp, bool gres) {
   const size_t nblk = (mp + kBlk - 1) / kBlk;
-  return (size_t)mp * 8 * 3 + nblk * 8 * 3 + ((size_t)mp + 4) * 4 + (size_t)mp * 2 * 5 + (size_t)mp * 2 + 256;
+  return (size_t)mp * 8 * (gres ? 3 : 2) + nblk * 8 * 3 + ((size_t)mp + 4) * 4 + (size_t)mp * 2 * 4 + (size_t)mp * 2 + 256;
 }
 // ring slots that fit next to a partition of mp nodes (0 = the partition does not fit)
-__host__ __device__ inline uint32_t commit2_ring_slots(uint32_t mp, uint32_t words, size_t budget) {
-  const size_t fixed = commit2_fixed_bytes(mp);
+__host__ __device__ inline uint32_t commit2_ring_slots(uint32_t mp, uint32_t words, bool gres, size_t budget) {
+  const size_t fixed = commit2_fixed_bytes(mp, gres);
   if (fixed >= budget) return 0;
   size_t r = (budget - fixed) / ((size_t)words * 4);
   if (r > (size_t)kRingMax) r = kRingMax;
   return r >= (size_t)kMaxJ + 4 ? (uint32_t)r : 0u;
 }
-__host__ __device__ inline size_t commit2_smem_bytes(uint32_t mp, uint32_t words, uint32_t ring) {
-  return commit2_fixed_bytes(mp) + (size_t)ring * words * 4;
+__host__ __device__ inline size_t commit2_smem_bytes(uint32_t mp, uint32_t words, bool gres, uint32_t ring) {
+  return commit2_fixed_bytes(mp, gres) + (size_t)ring * words * 4;
 }
 
 // ---- groups of 8 lanes ---------------------------------------------------------
@@ -286,25 +290,26 @@ __device__ __forceinline__ uint32_t g_update(TlEntry* E, uint32_t n, int64_t sta
 extern __shared__ __align__(16) unsigned char crane_dyn_smem2[];
 #define CRANE_DYN_BASE() (crane_dyn_smem2)
 #endif
-__device__ __forceinline__ Smem2 smem2_layout(uint32_t mp, uint32_t words, uint32_t ring) {
+__device__ __forceinline__ Smem2 smem2_layout(uint32_t mp, uint32_t words, uint32_t ring, bool gres) {
   Smem2 sm;
   sm.nblk = (mp + kBlk - 1) / kBlk;
   sm.ring = ring;
   unsigned char* ptr = CRANE_DYN_BASE();  // 16-byte aligned; widest element types first
   sm.cost = reinterpret_cast<double*>(ptr); ptr += (size_t)mp * 8;
   sm.cpu0 = reinterpret_cast<long long*>(ptr); ptr += (size_t)mp * 8;
-  sm.gcnt = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)mp * 8;
+  sm.gcnt = gres ? reinterpret_cast<unsigned long long*>(ptr) : nullptr;  // a cluster without gres keeps no slot counts
+  if (gres) ptr += (size_t)mp * 8;
   sm.bmax_cpu = reinterpret_cast<long long*>(ptr); ptr += (size_t)sm.nblk * 8;
   sm.bmax_cpug = reinterpret_cast<long long*>(ptr); ptr += (size_t)sm.nblk * 8;
   sm.bmax_g = reinterpret_cast<unsigned long long*>(ptr); ptr += (size_t)sm.nblk * 8;
-  ptr += (16u - (uint32_t)(((size_t)mp * 24 + (size_t)sm.nblk * 24) & 15u)) & 15u;
+  ptr += (16u - (uint32_t)(((size_t)mp * (gres ? 24 : 16) + (size_t)sm.nblk * 24) & 15u)) & 15u;
   sm.bits_ring = reinterpret_cast<uint32_t*>(ptr); ptr += (size_t)ring * words * 4;
   sm.scratch = reinterpret_cast<uint32_t*>(ptr); ptr += ((size_t)mp + 4) * 4;
   sm.ord = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
   sm.tmp = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
   sm.posn = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
   sm.nseg = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
-  sm.list = reinterpret_cast<uint16_t*>(ptr); ptr += (size_t)mp * 2;
+  sm.list = sm.tmp;  // the one-job path's picks: consumed before the re-key writes tmp
   sm.skip = ptr; ptr += mp;
   sm.cls = ptr; ptr += mp;
   return sm;
@@ -340,6 +345,8 @@ struct Commit2Args {
   int64_t max_window;
   uint32_t max_jobs;
   uint32_t cost_policy;
+  uint32_t gres;              // the cluster has gres entries
+  const uint32_t* part_list;  // partitions this launch commits (one CTA each), or null = all
   unsigned long long* prof;
 };
 
@@ -348,9 +355,9 @@ struct Ctx2 {           // per-CTA constants
   TimelineDev tl;
   PlaceDev out;
   int64_t now, max_window;
-  uint32_t base, mp, words, max_jobs, ring;
+  uint32_t base, mp, words, max_jobs, ring, gres;
 };
-#define SM2() smem2_layout(s2_cx.mp, s2_cx.words, s2_cx.ring)
+#define SM2() smem2_layout(s2_cx.mp, s2_cx.words, s2_cx.ring, s2_cx.gres != 0)
 
 __shared__ Ctx2 s2_cx;
 __shared__ JobQ s2_jobs[kRingMax];
@@ -372,7 +379,8 @@ __shared__ uint32_t s2_ok[kNG];
 __shared__ uint32_t s2_joblabel[kMaxJ];
 __shared__ uint16_t s2_chunk[kNG];
 __shared__ uint32_t s2_jw[kMaxJ];       // K | tfirst << 8 | mode << 16 | state << 17 | list length << 24
-__shared__ double s2_jdelta[kMaxJ][kMaxClasses];  // cost a node of class c gains when the job is placed on it
+__shared__ double s2_jdelta[kMaxJ][kDeltaClasses];  // cost a node of class c gains when the job is placed on it
+__shared__ unsigned long long s2_prof_windows, s2_prof_tests, s2_prof_singles;  // one-job path statistics (profiling builds)
 __shared__ uint32_t s2_nj, s2_njr, s2_nbf, s2_cut, s2_pmin, s2_pmax, s2_cutpos, s2_nsel, s2_label;
 __shared__ long long s2_gmax_cpu, s2_gmax_cpug;  // maxima over all blocks
 __shared__ unsigned long long s2_gmax_g;
@@ -413,7 +421,7 @@ __device__ __forceinline__ bool capable2(const Smem2& sm, const JSel2& js, uint3
 __device__ __forceinline__ bool prefilter2(const Smem2& sm, const JSel2& js, uint32_t q) {
   if (js.exclusive) return true;
   if (sm.cpu0[q] < js.req_cpu) return false;
-  return !js.has_gres || gres_counts_ok(sm.gcnt[q], js.spec8, js.gnames, js.name_need);
+  return !js.has_gres || (sm.gcnt && gres_counts_ok(sm.gcnt[q], js.spec8, js.gnames, js.name_need));
 }
 __device__ __forceinline__ bool bounds_admit2(const JSel2& js, long long mcpu, long long mcpug, unsigned long long mg) {
   if (js.exclusive) return true;
@@ -535,7 +543,7 @@ __device__ __noinline__ void bounds_recompute2(uint32_t b_first, uint32_t b_last
         if (p < mp) {
           const uint32_t q = sm.ord[p];
           const long long c = sm.cpu0[q];
-          const unsigned long long g = sm.gcnt[q];
+          const unsigned long long g = sm.gcnt ? sm.gcnt[q] : 0ull;
           mc = c > mc ? c : mc;
           if (g && c > mcg) mcg = c;
           mg = vmax8(mg, g);
@@ -736,7 +744,7 @@ __device__ __forceinline__ void write_node2(const JobQ& jq, uint32_t q, uint32_t
   sm.nseg[q] = (uint16_t)nn;
   if (nn >= s2_cx.max_jobs) sm.skip[q] = 1;
   sm.cpu0[q] = seg0.cpu_raw;
-  sm.gcnt[q] = (seg0.g[0] | seg0.g[1]) ? pack_gres_counts(seg0) : 0ull;
+  if (sm.gcnt) sm.gcnt[q] = (seg0.g[0] | seg0.g[1]) ? pack_gres_counts(seg0) : 0ull;
   const uint32_t dst = jq.alloc_off + rank;
   s2_cx.out.alloc_node[dst] = s2_cx.cl.slot_node[s2_cx.base + q];
   s2_cx.out.alloc_ntasks[dst] = jq.ntasks_per_node;
@@ -771,6 +779,9 @@ __device__ __noinline__ void single2(uint32_t ji) {
   }
   uint32_t nsel = 0, ntot = 0, pos = 0;
   if (tid == 0) s2_label = 0;
+#ifdef CRANE_PROFILE
+  if (tid == 0) s2_prof_singles += 1;
+#endif
   while (pos < mp && nsel < K) {
     // skip a window none of whose blocks can hold a candidate (once the first K
     // capable nodes are known)
@@ -791,6 +802,9 @@ __device__ __noinline__ void single2(uint32_t ji) {
     uint32_t totc;
     const uint32_t rank_c = block_excl_scan(cand ? 1u : 0u, totc);
     const uint32_t ncand = totc < (uint32_t)kNG ? totc : (uint32_t)kNG;
+#ifdef CRANE_PROFILE
+    if (tid == 0) { s2_prof_windows += 1; s2_prof_tests += ncand; }
+#endif
     if (cand && rank_c < (uint32_t)kNG) s2_chunk[rank_c] = (uint16_t)q;
     if (cand && rank_c == (uint32_t)kNG - 1u && totc > (uint32_t)kNG) s2_cutpos = p + 1;  // the rest of the window comes back
     __syncthreads();
@@ -990,7 +1004,7 @@ __device__ __noinline__ void single2(uint32_t ji) {
 }
 
 __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
-  const uint32_t part = blockIdx.x;
+  const uint32_t part = a.part_list ? a.part_list[blockIdx.x] : blockIdx.x;
   const uint32_t base = a.cl.part_base[part];
   const uint32_t mp = a.cl.part_base[part + 1] - base;
   const uint32_t words = a.words_per_row;
@@ -998,7 +1012,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
   const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
   const uint32_t gl = g_lane(), gi = g_index();
 
-  const Smem2 sm = smem2_layout(mp, words, ring);
+  const Smem2 sm = smem2_layout(mp, words, ring, a.gres != 0);
 
   // ---- load node state -------------------------------------------------------
   for (uint32_t q = tid; q < mp; q += kT2) {
@@ -1006,7 +1020,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
     sm.cost[q] = a.tl.cost0[g];
     const Row s0 = a.tl.ent[(size_t)g * a.tl.cap].seg;
     sm.cpu0[q] = s0.cpu_raw;
-    sm.gcnt[q] = pack_gres_counts(s0);
+    if (sm.gcnt) sm.gcnt[q] = pack_gres_counts(s0);
     sm.skip[q] = a.tl.skip[g];
     sm.nseg[q] = (uint16_t)a.tl.n[g];
     sm.cls[q] = a.cl.slot_class[g];
@@ -1016,7 +1030,8 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
   if (tid == 0) {
     s2_cx.cl = a.cl; s2_cx.tl = a.tl; s2_cx.out = a.out;
     s2_cx.now = a.now; s2_cx.max_window = a.max_window; s2_cx.base = base; s2_cx.mp = mp; s2_cx.words = words;
-    s2_cx.max_jobs = a.max_jobs; s2_cx.ring = ring;
+    s2_cx.max_jobs = a.max_jobs; s2_cx.ring = ring; s2_cx.gres = a.gres;
+    s2_prof_windows = 0; s2_prof_tests = 0; s2_prof_singles = 0;
     for (uint32_t s = 0; s < ring; ++s) mbar_init(&s2_bar[s], 1);
     fence_mbar_init();
   }
@@ -1048,6 +1063,8 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
 
   // =============================== dispatcher =====================================
   uint32_t ji = 0;
+  uint32_t jcap = kMaxJ;     // jobs offered to the next batch: twice what the last one placed (a batch that is cut
+                             // early wastes the selection of the jobs behind the cut)
   bool want_single = false;  // the job at ji goes down the one-job path
   while (ji < njobs) {
     ensure_issued(ji);
@@ -1065,7 +1082,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
       uint32_t myK = 0, myslot = 0;
       bool okj = false;
       const uint32_t j = ji + lane;
-      if (lane < (uint32_t)kMaxJ && j < njobs) {
+      if (lane < jcap && j < njobs) {
         myslot = j % ring;
         mbar_wait(&s2_bar[myslot], (j / ring) & 1u);
         myK = s2_jobs[myslot].node_num;
@@ -1112,7 +1129,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
       if (jact) {
         // cost a node of class c gets when this job is placed on it (JobScheduler.h:46-52)
         const JobQ& jq = s2_jobs[bj.slot];
-        for (uint32_t c = gl; c < (uint32_t)kMaxClasses; c += kGL) {
+        for (uint32_t c = gl; c < (uint32_t)kDeltaClasses; c += kGL) {
           const int64_t tot_cpu = s2_classrow[c].cpu_raw;
           s2_jdelta[gi][c] = tot_cpu > 0 ? cost_delta(jq.time_limit, js.exclusive ? tot_cpu : jq.req.cpu_raw, tot_cpu) : 0.0;
         }
@@ -1219,7 +1236,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
             if ((cm >> lane) & 1u) {
               sm.scratch[lq] = 1;
               const uint8_t c = sm.cls[lq];
-              nc = c != 0xff ? __dadd_rn(cq, s2_jdelta[t][c]) : new_cost2(s2_jobs[s2_bj[t].slot], lq);
+              nc = c < kDeltaClasses ? __dadd_rn(cq, s2_jdelta[t][c]) : new_cost2(s2_jobs[s2_bj[t].slot], lq);
             }
             // pick number i of the job goes to task slot tf + i
             const uint32_t src = mine ? (K == 1 ? kth : nth_set_bit(cm, lane - tf + 1u)) : 0u;
@@ -1236,7 +1253,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
           }
           if (tv != 0xffffu) sm.scratch[tv] = 0;  // the marks go back to zero
           if (lane == 0) { s2_njr = njr_l; s2_cut = NTl; }
-        } else if (myslot < nslots && tstate == 0) {
+        } else if (CRANE_SPEC_EVAL && myslot < nslots && tstate == 0) {
           // first guess of my slot: entry `myslot` of the job's list if the list is
           // long enough for all the jobs before it to be served, else its own i-th entry
           const uint32_t jw = s2_jw[tjob];
@@ -1284,7 +1301,6 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
       __syncthreads();
       if (pass == 0) PROF(3);
     }
-    PROF_CNT(15, nj);
     if (njr < nj) PROF_CNT(s2_bj[njr].state == 1u ? 9 : 10, 1);
     if (njr == 0) { want_single = true; continue; }  // (nothing is taken before the first job: cannot happen)
 
@@ -1418,7 +1434,14 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
     PROF_CNT(13, done);
     PROF_CNT(14, 1);
     ji += done;
+    jcap = 2u * done + 4u < (uint32_t)kMaxJ ? 2u * done + 4u : (uint32_t)kMaxJ;
   }
+  PROF_CNT(8, s2_prof_windows);
+  PROF_CNT(15, s2_prof_tests);
+  PROF_CNT(9, 0);
+#ifdef CRANE_PROFILE
+  if (threadIdx.x == 0) prof_acc[12] = prof_acc[12] | (s2_prof_singles << 32);
+#endif
   PROF_FLUSH(a.prof);
 }
 

@@ -119,6 +119,10 @@ struct crane_sched {
   DBuf<uint32_t> d_out_nalloc, d_out_node, d_out_ntasks;
   DBuf<Row> d_out_res;
   bool uploaded = false, ran = false;
+  // one queue over several GPUs
+  uint32_t shard_rank = 0, shard_n = 1;
+  std::vector<uint32_t> h_part_owner, h_part_list;
+  DBuf<uint32_t> d_part_owner, d_part_list;
   // QoS post-filter (R12)
   bool have_qos_cols = false;
   DBuf<uint32_t> d_qos, d_user, d_q_u32, d_q_chain_off, d_q_chain;
@@ -243,7 +247,7 @@ void crane_sched_destroy(crane_sched_t* h) {
   REL(d_vals_b); REL(d_hist); REL(d_part_count); REL(d_part_job_off); REL(d_bitmap); REL(d_jobq); REL(d_reason);
   REL(d_out_prio); REL(d_out_start); REL(d_out_end); REL(d_out_nalloc); REL(d_out_node); REL(d_out_ntasks);
   REL(d_out_res); REL(d_prof); REL(d_qos); REL(d_user); REL(d_q_u32); REL(d_q_chain_off); REL(d_q_chain);
-  REL(d_q_i64); REL(d_q_valid); REL(d_q_tres); REL(d_q_user_usage); REL(d_q_acct_usage); REL(d_q_qos_usage);
+  REL(d_q_i64); REL(d_q_valid); REL(d_part_owner); REL(d_part_list); REL(d_q_tres); REL(d_q_user_usage); REL(d_q_acct_usage); REL(d_q_qos_usage);
 #undef REL
   for (auto& e : h->ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -311,7 +315,7 @@ int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
     if (max_mp > 65535 || commit_smem_bytes(max_mp, h->words_per_row) > kMaxDynSmem || max_mp > 32u * (uint32_t)h->commit_threads)
       return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
   } else {
-    h->v2_ring = commit2_ring_slots(max_mp, h->words_per_row, h->v2_budget);
+    h->v2_ring = commit2_ring_slots(max_mp, h->words_per_row, c->n_gres_entries > 0, h->v2_budget);
     if (max_mp > 65000 || h->v2_ring == 0)
       return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
   }
@@ -351,6 +355,47 @@ int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
   CU(cudaStreamSynchronize(h->stream));
   h->have_cluster = true;
   h->uploaded = false;
+  h->shard_rank = 0;
+  h->shard_n = 1;  // a new cluster: the partition -> rank table has to be set again
+  return CRANE_OK;
+}
+
+int crane_sched_set_shard(crane_sched_t* h, uint32_t rank, uint32_t n_ranks, const uint32_t* part_owner) {
+  if (!h) return CRANE_EINVAL;
+  if (!h->have_cluster) return fail(h, CRANE_EINVAL, "set_shard: set_cluster first");
+  if (n_ranks == 0 || rank >= n_ranks) return fail(h, CRANE_EINVAL, "set_shard: rank %u of %u", rank, n_ranks);
+  if (h->use_v1 && n_ranks > 1) return fail(h, CRANE_ENOSYS, "set_shard: not built for the round-1 commit kernel");
+  CU(cudaSetDevice(h->device));
+  h->shard_rank = rank;
+  h->shard_n = n_ranks;
+  h->h_part_owner.clear();
+  h->h_part_list.clear();
+  if (n_ranks > 1) {
+    if (!part_owner && h->n_parts) return fail(h, CRANE_EINVAL, "set_shard: null owner table");
+    for (uint32_t p = 0; p < h->n_parts; ++p) {
+      if (part_owner[p] >= n_ranks) return fail(h, CRANE_EINVAL, "set_shard: partition %u owned by rank %u of %u", p, part_owner[p], n_ranks);
+      h->h_part_owner.push_back(part_owner[p]);
+      if (part_owner[p] == rank) h->h_part_list.push_back(p);
+    }
+    H2D(h->d_part_owner, h->h_part_owner.data(), h->h_part_owner.size());
+    H2D(h->d_part_list, h->h_part_list.data(), h->h_part_list.size());
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return CRANE_OK;
+}
+
+int crane_sched_device_placements(crane_sched_t* h, crane_device_placements_t* out) {
+  if (!h || !out) return CRANE_EINVAL;
+  if (!h->ran) return fail(h, CRANE_EINVAL, "device_placements: run first");
+  out->reason = h->d_reason.p;
+  out->start_time = h->d_out_start.p;
+  out->end_time = h->d_out_end.p;
+  out->n_alloc = h->d_out_nalloc.p;
+  out->alloc_node = h->d_out_node.p;
+  out->alloc_ntasks = h->d_out_ntasks.p;
+  out->alloc_res = h->d_out_res.p;
+  out->n_jobs = h->n_pending;
+  out->n_rows = h->total_alloc;
   return CRANE_OK;
 }
 
@@ -673,7 +718,8 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
   if (nq_cap && h->n_parts) {
     uint32_t wpb = 8;
     uint32_t nb = std::min<uint32_t>((nq_cap + wpb - 1) / wpb, 148 * 8);
-    CRANE_LAUNCH(k_feas_bitmap, nb, wpb * 32, 0, st, cl, pd, h->d_jobq.p, h->d_part_job_off.p + h->n_parts, h->words_per_row, h->d_bitmap.p);
+    CRANE_LAUNCH(k_feas_bitmap, nb, wpb * 32, 0, st, cl, pd, h->d_jobq.p, h->d_part_job_off.p + h->n_parts, h->words_per_row, h->d_bitmap.p,
+                 h->shard_n > 1 ? h->d_part_owner.p : nullptr, h->shard_rank);
     h->timing.kernel_launches++;
   }
   CU(cudaEventRecord(h->ev[5], st));
@@ -701,10 +747,20 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
       c2.cl = cl; c2.tl = tl; c2.jobq = ca.jobq; c2.part_job_off = ca.part_job_off; c2.bitmap = ca.bitmap;
       c2.words_per_row = ca.words_per_row; c2.ring = h->v2_ring; c2.out = out; c2.now = now;
       c2.max_window = ca.max_window; c2.max_jobs = ca.max_jobs; c2.cost_policy = h->cfg.cost_policy; c2.prof = ca.prof;
-      size_t smem = commit2_smem_bytes(h->max_part_slots, h->words_per_row, h->v2_ring);
-      CRANE_LAUNCH(k_commit2, h->n_parts, kT2, smem, st, c2);
+      c2.gres = h->dict.n_entries > 0 ? 1u : 0u;
+      size_t smem = commit2_smem_bytes(h->max_part_slots, h->words_per_row, c2.gres != 0, h->v2_ring);
+      uint32_t grid = h->n_parts;
+      if (h->shard_n > 1) {
+        c2.part_list = h->d_part_list.p;
+        grid = (uint32_t)h->h_part_list.size();
+      }
+      if (grid) CRANE_LAUNCH(k_commit2, grid, kT2, smem, st, c2);
     }
     h->timing.kernel_launches++;
+    if (h->shard_n > 1 && N) {
+      CRANE_LAUNCH(k_shard_mask, (N + 255) / 256, 256, 0, st, pd, out, h->d_part_owner.p, h->n_parts, h->shard_rank);
+      h->timing.kernel_launches++;
+    }
   }
   CU(cudaEventRecord(h->ev[6], st));
   CU(cudaGetLastError());

@@ -573,18 +573,20 @@ __global__ void k_node_init(ClusterDev cl, RunningDev rn, TimelineDev tl, int64_
 // the commit kernel can fetch a row with one 16-byte-aligned bulk copy.
 // ------------------------------------------------------------------------
 __global__ void k_feas_bitmap(ClusterDev cl, PendingDev pd, const JobQ* jobq, const uint32_t* n_queued_ptr,
-                              uint32_t words_per_row, uint32_t* bitmap) {
+                              uint32_t words_per_row, uint32_t* bitmap, const uint32_t* part_owner, uint32_t rank) {
   const int lane = lane_id();
   const uint32_t n_queued = *n_queued_ptr;
   uint32_t warps_per_block = blockDim.x >> 5;
   for (uint32_t r = blockIdx.x * warps_per_block + warp_id(); r < n_queued; r += gridDim.x * warps_per_block) {
     JobQ jq = jobq[r];
     uint32_t p = pd.partition[jq.job];
+    if (part_owner && part_owner[p] != rank) continue;  // another GPU commits this partition
     uint32_t base = cl.part_base[p], mp = cl.part_base[p + 1] - base;
+    const uint32_t row_words = (mp + 31) / 32;          // words beyond the job's own partition are never read
     uint32_t il = 0, ih = 0, el = 0, eh = 0;
     if (pd.incl_off) { il = pd.incl_off[jq.job]; ih = pd.incl_off[jq.job + 1]; }
     if (pd.excl_off) { el = pd.excl_off[jq.job]; eh = pd.excl_off[jq.job + 1]; }
-    for (uint32_t w = 0; w < words_per_row; ++w) {
+    for (uint32_t w = 0; w < row_words; ++w) {
       uint32_t q = w * 32 + lane;
       bool ok = false;
       if (q < mp) {
@@ -600,6 +602,21 @@ __global__ void k_feas_bitmap(ClusterDev cl, PendingDev pd, const JobQ* jobq, co
       unsigned word = __ballot_sync(kFullMask, ok);
       if (lane == 0) bitmap[(size_t)r * words_per_row + w] = word;
     }
+  }
+}
+
+// One queue over several GPUs: the placement columns of jobs another rank owns
+// go to zero, so the union over ranks is a sum (crane_sched_set_shard).
+__global__ void k_shard_mask(PendingDev pd, PlaceDev out, const uint32_t* part_owner, uint32_t n_parts, uint32_t rank) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= pd.n) return;
+  const uint32_t p = pd.partition[j];
+  const uint32_t owner = p < n_parts ? part_owner[p] : 0u;
+  if (owner != rank) {
+    out.reason[j] = 0;
+    out.start_time[j] = 0;
+    out.end_time[j] = 0;
+    out.n_alloc[j] = 0;
   }
 }
 

@@ -14,6 +14,8 @@ from __future__ import annotations
 import ctypes as C
 import os
 
+import numpy as np
+
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -59,6 +61,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.crane_sched_get_timing.argtypes = [C.c_void_p, P(abi.TimingC)]
     lib.crane_sched_qos_filter.restype = C.c_int
     lib.crane_sched_qos_filter.argtypes = [C.c_void_p, P(abi.QosTableC), C.c_void_p]
+    lib.crane_sched_set_shard.restype = C.c_int
+    lib.crane_sched_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.crane_sched_device_placements.restype = C.c_int
+    lib.crane_sched_device_placements.argtypes = [C.c_void_p, P(abi.DevicePlacementsC)]
     lib.crane_sched_debug_bitmap.restype = C.c_int
     lib.crane_sched_debug_bitmap.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_uint32), P(C.c_uint32)]
     lib.crane_sched_debug_profile.restype = C.c_int
@@ -70,7 +76,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 EXPORTS = ("crane_sched_create", "crane_sched_destroy", "crane_sched_last_error",
            "crane_sched_set_cluster", "crane_sched_node_select", "crane_sched_upload",
            "crane_sched_run", "crane_sched_fetch", "crane_sched_sync", "crane_sched_get_timing",
-           "crane_sched_qos_filter",
+           "crane_sched_qos_filter", "crane_sched_set_shard", "crane_sched_device_placements",
            "crane_sched_debug_bitmap", "crane_sched_debug_profile")
 
 
@@ -134,6 +140,17 @@ class GpuScheduler:
         c_out = out.as_c()
         self._check(self._lib.crane_sched_fetch(self._h, C.byref(c_out)))
         return out
+
+    # --- one queue over several GPUs (include/crane_sched.h: crane_sched_set_shard) ---
+    def set_shard(self, rank: int, n_ranks: int, part_owner):
+        import numpy as np
+        owner = np.ascontiguousarray(part_owner, np.uint32) if part_owner is not None else None
+        self._check(self._lib.crane_sched_set_shard(self._h, rank, n_ranks, owner.ctypes.data if owner is not None else None))
+
+    def device_placements(self) -> "abi.DevicePlacementsC":
+        d = abi.DevicePlacementsC()
+        self._check(self._lib.crane_sched_device_placements(self._h, C.byref(d)))
+        return d
 
     def qos_filter(self, qos: abi.QosTable, reason: np.ndarray) -> np.ndarray:
         """CheckAndMallocQosResource pass of the commit loop (JobScheduler.cpp:1262)

@@ -1,14 +1,24 @@
-"""Multi-GPU layout of the scheduling tick.
+"""One scheduling tick over several GPUs.
 
-The path shards by partition: every partition has its own LocalScheduler and
-its own node set (JobScheduler.cpp:5757-5766), so disjoint partitions never
-interact inside a tick. Rank r of N therefore owns a disjoint slice of the
-cluster's partitions together with the pending jobs of those partitions and
-runs the unmodified single-GPU tick on it; there is no data-path collective.
-`torch.distributed` (nccl on GPUs, gloo in the CPU tests) carries the barrier,
-the max-over-ranks timing and the gather of per-rank summaries only.
+The job loop of NodeSelect is independent per partition — one LocalScheduler
+each, with its own node set (JobScheduler.cpp:5757-5766; "TODO: do it in
+parallel", :5756) — so ONE queue is split by dealing its partitions to the
+ranks (largest job count first). Every rank uploads the whole pending table
+(priority, batch limit and queue order are global: JobScheduler.cpp:6545-6671),
+commits only its own partitions, zeroes the placement columns of the jobs it
+does not own, and the union over ranks is one all-reduce(sum) per column —
+NCCL over NVLink on GPUs, gloo in the CPU tests. The result on every rank is
+bit-identical to the single-GPU tick.
+
+Inside one partition the loop is a dependency chain of ~20 microsecond batches
+(DESIGN.md §5): there is nothing left to hand to another GPU at NVLink latency,
+so partitions are the unit and a queue with fewer partitions than ranks leaves
+ranks idle. `shard_workload` is the other line of the bench: independent
+clusters, one per rank (weak scaling).
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 
@@ -16,12 +26,8 @@ from . import abi, synth
 
 
 def shard_workload(config_id: int, rank: int, world: int, n_jobs: int = 0, n_nodes: int = 0):
-    """Weak-scaling shard: rank r gets its own config-shaped set of partitions (a
-    disjoint slice of a `world`-times larger cluster). Every rank's slice is
-    generated from the same seed, so the per-GPU work is the same for every N —
-    the definition of weak scaling; with per-rank seeds the max over ranks
-    measures the spread of the synthetic workloads instead (one of eight
-    config-2 draws takes 1.8x the cycles of the others)."""
+    """Weak scaling: rank r schedules its own cluster (config-shaped, its own
+    draw: seed = 1000 * rank + config) — `world` independent clusters."""
     gen = synth.CONFIGS[config_id]
     kw = {}
     if n_jobs:
@@ -29,60 +35,73 @@ def shard_workload(config_id: int, rank: int, world: int, n_jobs: int = 0, n_nod
     if n_nodes:
         kw["n_nodes"] = n_nodes
     if config_id != 1:
-        kw["seed_id"] = config_id
+        kw["seed_id"] = config_id + 1000 * rank
     return gen(**kw)
 
 
-def split_by_partition(case, world: int):
-    """Strong split of ONE cluster: partitions are dealt to ranks (largest job
-    count first, LPT), each rank keeps the nodes and jobs of its partitions.
-    Returns per-rank (case, job_index) so results can be scattered back."""
-    cfg, cl, rn, pd, now = case
-    njobs = np.bincount(pd.partition[pd.partition < cl.n_partitions], minlength=cl.n_partitions)
+def deal_partitions(pending: abi.Pending, n_partitions: int, world: int) -> np.ndarray:
+    """partition -> rank, longest processing time first on the job counts (the
+    tick of a rank is the longest job loop among its partitions, and one GPU
+    runs its partitions concurrently, so what matters is to spread the big ones)."""
+    njobs = np.bincount(pending.partition[pending.partition < n_partitions], minlength=n_partitions)
     load = np.zeros(world, np.int64)
-    owner = np.zeros(cl.n_partitions, np.int64)
+    owner = np.zeros(n_partitions, np.uint32)
     for p in np.argsort(-njobs, kind="stable"):
         r = int(np.argmin(load))
         owner[p] = r
         load[r] += njobs[p]
+    return owner
+
+
+class _DevArray:
+    """Zero-copy view of a device buffer of the C-ABI library for torch
+    (`__cuda_array_interface__`)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _columns(sched, on_gpu: bool):
+    """The placement columns of the last run as torch tensors aliasing the
+    library's buffers (device memory on a GPU, host memory under the CPU
+    kernel-emulation harness of the tests)."""
+    import torch
+    d = sched.device_placements()
+    nj, nr = int(d.n_jobs), int(d.n_rows)
+    spec = [(d.reason, nj, "|u1", np.uint8), (d.start_time, nj, "<i8", np.int64), (d.end_time, nj, "<i8", np.int64),
+            (d.n_alloc, nj, "<i4", np.int32), (d.alloc_node, nr, "<i4", np.int32), (d.alloc_ntasks, nr, "<i4", np.int32),
+            (d.alloc_res, nr * 9, "<i8", np.int64)]
     out = []
-    for r in range(world):
-        parts = np.flatnonzero(owner == r)
-        node_sel = np.concatenate([cl.part_nodes[cl.part_off[p]:cl.part_off[p + 1]] for p in parts]) if len(parts) else np.zeros(0, np.uint32)
-        remap = np.full(cl.n_nodes, -1, np.int64)
-        remap[node_sel] = np.arange(len(node_sel))
-        off = [0]
-        for p in parts:
-            off.append(off[-1] + int(cl.part_off[p + 1] - cl.part_off[p]))
-        sub_cl = abi.Cluster(cl.res_total[node_sel], cl.alive[node_sel], cl.drain[node_sel],
-                             np.array(off, np.uint32), np.arange(len(node_sel), dtype=np.uint32),
-                             cl.n_gres_entries, cl.gres_entry_name)
-        pmap = np.full(cl.n_partitions + 1, len(parts), np.int64)  # unknown partitions stay unknown
-        pmap[parts] = np.arange(len(parts))
-        jsel = np.flatnonzero(np.isin(pd.partition, parts) | ((pd.partition >= cl.n_partitions) & (r == 0)))
-        cols = {}
-        for f in pd.__dataclass_fields__:
-            v = getattr(pd, f)
-            if f in ("incl_off", "incl_nodes", "excl_off", "excl_nodes") or v is None:
-                continue
-            cols[f] = v[jsel]
-        cols["partition"] = pmap[np.minimum(cols["partition"], cl.n_partitions)].astype(np.uint32)
-        for k in ("incl", "excl"):
-            o = getattr(pd, k + "_off")
-            if o is not None:
-                nodes = getattr(pd, k + "_nodes")
-                new_off, new_nodes = [0], []
-                for j in jsel:
-                    lst = remap[nodes[o[j]:o[j + 1]]]
-                    new_nodes += lst[lst >= 0].tolist()
-                    new_off.append(len(new_nodes))
-                cols[k + "_off"] = np.array(new_off, np.uint32)
-                cols[k + "_nodes"] = np.array(new_nodes, np.uint32)
-        sub_pd = abi.Pending(**cols)
-        if rn.n:
-            raise NotImplementedError("split_by_partition: running jobs are not split yet")
-        out.append(((cfg, sub_cl, rn, sub_pd, now), jsel, node_sel))
+    for ptr, n, ts, dt in spec:
+        if n == 0 or not ptr:
+            continue
+        if on_gpu:
+            out.append(torch.as_tensor(_DevArray(ptr, n, ts), device="cuda"))
+        else:
+            buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr)
+            out.append(torch.from_numpy(np.frombuffer(buf, dtype=dt)))
     return out
+
+
+def sharded_tick(sched, now: int, running: abi.Running, pending: abi.Pending, owner: np.ndarray, dist,
+                 out: abi.Placements | None = None, on_gpu: bool = True, upload: bool = True) -> abi.Placements:
+    """One NodeSelect over dist.get_world_size() GPUs: upload (whole tables), run
+    (own partitions), all-reduce of the placement columns, fetch. Every rank
+    returns the whole tick."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sched.set_shard(rank, world, owner)
+    if upload:
+        sched.upload(running, pending)
+    sched.run(now)
+    sched.sync()  # the library's stream is not torch's: the columns are complete before the collective reads them
+    cols = _columns(sched, on_gpu)
+    for t in cols:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if on_gpu:
+        import torch
+        torch.cuda.synchronize()
+    out = out if out is not None else abi.Placements.for_pending(pending)
+    return sched.fetch(out)
 
 
 def reduce_metric(decided_local: int, device_ms_local: float, dist=None, device="cpu"):

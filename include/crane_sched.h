@@ -239,6 +239,37 @@ int crane_sched_sync(crane_sched_t* h, float* run_ms);
 
 int crane_sched_get_timing(const crane_sched_t* h, crane_sched_timing_t* t);
 
+/* ---- one queue over several GPUs ----------------------------- */
+/* The job loop is independent per partition (one LocalScheduler each,
+ * JobScheduler.cpp:5757-5766; the reference's "TODO: do it in parallel", :5756):
+ * with part_owner[p] == rank this handle commits partition p and leaves every
+ * other partition to the handle (GPU) that owns it. Priority, batch limit and
+ * queue order are computed from the WHOLE pending table on every rank (upload
+ * the same tables everywhere), so they are identical on all ranks. After
+ * crane_sched_run the device-side placement columns hold zeros for the jobs this
+ * rank does not own (a job without a valid partition belongs to rank 0), which
+ * makes the union over ranks a plain sum: one all-reduce(sum) per column of
+ * crane_sched_device_placements(), then crane_sched_fetch on any rank returns the
+ * whole tick. n_ranks == 1 (the default) switches sharding off. */
+int crane_sched_set_shard(crane_sched_t* h, uint32_t rank, uint32_t n_ranks,
+                          const uint32_t* part_owner /* [n_partitions] */);
+
+/* Device pointers of the placement columns of the last crane_sched_run, for the
+ * all-reduce above (NCCL through the caller's communicator). `priority` is
+ * identical on all ranks and is not part of the exchange. */
+typedef struct crane_device_placements {
+  void* reason;       /* uint8  [n_jobs]                                      */
+  void* start_time;   /* int64  [n_jobs]                                      */
+  void* end_time;     /* int64  [n_jobs]                                      */
+  void* n_alloc;      /* uint32 [n_jobs]                                      */
+  void* alloc_node;   /* uint32 [n_rows]                                      */
+  void* alloc_ntasks; /* uint32 [n_rows]                                      */
+  void* alloc_res;    /* crane_res_in_node_t [n_rows] = 9 x uint64 per row    */
+  uint64_t n_jobs;
+  uint64_t n_rows;
+} crane_device_placements_t;
+int crane_sched_device_placements(crane_sched_t* h, crane_device_placements_t* out);
+
 /* ---- QoS post-filter (R12) ------------------------------------------------ */
 /* A ResourceView limit of struct Qos (Account/AccountDefs.h:27-50): max_tres,
  * max_tres_per_user, max_tres_per_account. A gres name / type that is absent
