@@ -346,6 +346,7 @@ struct Commit2Args {
   uint32_t max_jobs;
   uint32_t cost_policy;
   uint32_t gres;              // the cluster has gres entries
+  uint32_t dslot;             // the handle's gres dictionary: c_dicts[dslot]
   const uint32_t* part_list;  // partitions this launch commits (one CTA each), or null = all
   unsigned long long* prof;
 };
@@ -355,8 +356,9 @@ struct Ctx2 {           // per-CTA constants
   TimelineDev tl;
   PlaceDev out;
   int64_t now, max_window;
-  uint32_t base, mp, words, max_jobs, ring, gres;
+  uint32_t base, mp, words, max_jobs, ring, gres, dslot;
 };
+#define C_DICT2 (c_dicts[s2_cx.dslot])
 #define SM2() smem2_layout(s2_cx.mp, s2_cx.words, s2_cx.ring, s2_cx.gres != 0)
 
 __shared__ Ctx2 s2_cx;
@@ -421,11 +423,11 @@ __device__ __forceinline__ bool capable2(const Smem2& sm, const JSel2& js, uint3
 __device__ __forceinline__ bool prefilter2(const Smem2& sm, const JSel2& js, uint32_t q) {
   if (js.exclusive) return true;
   if (sm.cpu0[q] < js.req_cpu) return false;
-  return !js.has_gres || (sm.gcnt && gres_counts_ok(sm.gcnt[q], js.spec8, js.gnames, js.name_need));
+  return !js.has_gres || (sm.gcnt && gres_counts_ok(sm.gcnt[q], js.spec8, js.gnames, js.name_need, C_DICT2));
 }
 __device__ __forceinline__ bool bounds_admit2(const JSel2& js, long long mcpu, long long mcpug, unsigned long long mg) {
   if (js.exclusive) return true;
-  if (js.has_gres) return mcpug >= js.req_cpu && gres_counts_ok(mg, js.spec8, js.gnames, js.name_need);
+  if (js.has_gres) return mcpug >= js.req_cpu && gres_counts_ok(mg, js.spec8, js.gnames, js.name_need, C_DICT2);
   return mcpu >= js.req_cpu;
 }
 __device__ __forceinline__ bool block_promising2(const Smem2& sm, const JSel2& js, uint32_t b) {
@@ -837,7 +839,7 @@ __device__ __noinline__ void single2(uint32_t ji) {
         if (ok) {
           Row wr;
           win_row(w, a0, req, wr);
-          ok = feasible<false>(req, wr, c_dict, nullptr);
+          ok = feasible<false>(req, wr, C_DICT2, nullptr);
         }
       }
       if (gl == 0) s2_ok[gi] = ok ? 1u : 0u;
@@ -885,7 +887,7 @@ __device__ __noinline__ void single2(uint32_t ji) {
         else {
           Row wr;
           win_row(w, a0, req, wr);
-          feasible_alloc(req, wr, alloc);
+          feasible_alloc(req, wr, alloc, s2_cx.dslot);
         }
       }
       Row seg0;
@@ -917,7 +919,7 @@ __device__ __noinline__ void single2(uint32_t ji) {
           g = base + q;
           ns = sm.nseg[q];
           const Row tot = node_total2(q);
-          if (exclusive) alloc = tot; else feasible_alloc(req, tot, alloc);
+          if (exclusive) alloc = tot; else feasible_alloc(req, tot, alloc, s2_cx.dslot);
         }
         const int64_t e = g_earliest(tl.ent + (size_t)g * tl.cap, ns, alloc, T0, limit, act);
         if (act) { emax = e > emax ? e : emax; emin = e < emin ? e : emin; }
@@ -951,7 +953,7 @@ __device__ __noinline__ void single2(uint32_t ji) {
           ns = sm.nseg[q];
           a0 = tl.avail0[g];
           const Row tot = node_total2(q);
-          if (exclusive) alloc = tot; else feasible_alloc(req, tot, alloc);
+          if (exclusive) alloc = tot; else feasible_alloc(req, tot, alloc, s2_cx.dslot);
         }
         Row seg0;
         row_zero(seg0);
@@ -1030,7 +1032,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
   if (tid == 0) {
     s2_cx.cl = a.cl; s2_cx.tl = a.tl; s2_cx.out = a.out;
     s2_cx.now = a.now; s2_cx.max_window = a.max_window; s2_cx.base = base; s2_cx.mp = mp; s2_cx.words = words;
-    s2_cx.max_jobs = a.max_jobs; s2_cx.ring = ring; s2_cx.gres = a.gres;
+    s2_cx.max_jobs = a.max_jobs; s2_cx.ring = ring; s2_cx.gres = a.gres; s2_cx.dslot = a.dslot;
     s2_prof_windows = 0; s2_prof_tests = 0; s2_prof_singles = 0;
     for (uint32_t s = 0; s < ring; ++s) mbar_init(&s2_bar[s], 1);
     fence_mbar_init();
@@ -1289,11 +1291,11 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
             if (tok) {
               Row wr;
               win_row(w, ta0, tjq->req, wr);
-              tok = feasible<false>(tjq->req, wr, c_dict, nullptr);
+              tok = feasible<false>(tjq->req, wr, C_DICT2, nullptr);
             }
           }
         } else if (do_eval) {
-          if (texcl) talloc = ttot; else feasible<true>(tjq->req, ttot, c_dict, &talloc);
+          if (texcl) talloc = ttot; else feasible<true>(tjq->req, ttot, C_DICT2, &talloc);
         }
         const int64_t e = g_earliest(E, ns, talloc, now, tlimit, do_eval && tmode);
         if (do_eval && tmode) te0 = e;
@@ -1374,7 +1376,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
         else {
           Row wr;
           win_row(tw, ta0, tjq->req, wr);
-          feasible<true>(tjq->req, wr, c_dict, &talloc);
+          feasible<true>(tjq->req, wr, C_DICT2, &talloc);
         }
       }
       Row seg0;

@@ -17,6 +17,7 @@
 #endif
 
 #include <algorithm>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -53,7 +54,6 @@ struct DBuf {
   }
 };
 
-constexpr size_t kMaxDynSmem = 220 * 1024;
 
 }  // namespace
 
@@ -64,8 +64,6 @@ struct crane_sched {
   cudaEvent_t ev[8]{};
   std::string err;
   crane_sched_timing_t timing{};
-  int commit_threads = kCommitThreads;
-  bool use_v1 = false;        // CRANE_COMMIT_V1=1: the round-1 kernel (A/B runs only)
   size_t v2_budget = 0;       // dynamic shared memory k_commit2 may use
   uint32_t v2_ring = 0;
 
@@ -119,6 +117,7 @@ struct crane_sched {
   DBuf<uint32_t> d_out_nalloc, d_out_node, d_out_ntasks;
   DBuf<Row> d_out_res;
   bool uploaded = false, ran = false;
+  int dict_slot = -1;  // this handle's entry of c_dicts[] on its device
   // one queue over several GPUs
   uint32_t shard_rank = 0, shard_n = 1;
   std::vector<uint32_t> h_part_owner, h_part_list;
@@ -133,6 +132,10 @@ struct crane_sched {
 };
 
 namespace {
+
+// c_dicts[] slots in use, per device
+std::mutex g_slot_mu;
+uint32_t g_slots_used[64] = {0};
 
 int fail(crane_sched* h, int code, const char* fmt, ...) {
   char buf[512];
@@ -198,23 +201,24 @@ int crane_sched_create(const crane_sched_config_t* cfg, int device, crane_sched_
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return CRANE_ENODEV;
   if (cfg->max_jobs_per_node < 2 || cfg->max_jobs_per_node > 65000) return CRANE_EINVAL;
   if (cfg->cost_policy != 0) return CRANE_ENOSYS;
+  if (device >= 64) return CRANE_EINVAL;
+  int slot = -1;
+  {
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    for (int k = 0; k < kDictSlots; ++k)
+      if (!(g_slots_used[device] >> k & 1u)) { slot = k; g_slots_used[device] |= 1u << k; break; }
+  }
+  if (slot < 0) return CRANE_ENOSYS;  // more than kDictSlots live handles on one device
   crane_sched* h = new crane_sched();
   h->cfg = *cfg;
   h->device = device;
+  h->dict_slot = slot;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    { std::lock_guard<std::mutex> lk(g_slot_mu); g_slots_used[device] &= ~(1u << slot); }
     delete h;
     return CRANE_ENODEV;
   }
   for (auto& e : h->ev) cudaEventCreate(&e);
-  if (const char* s = getenv("CRANE_COMMIT_THREADS")) {
-    int t = atoi(s);
-    if (t >= 64 && t <= kCommitThreads && t % 32 == 0) h->commit_threads = t;
-  }
-#ifdef CRANE_EMU
-  if (!getenv("CRANE_COMMIT_THREADS")) h->commit_threads = 128;
-#endif
-  cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-  if (const char* s = getenv("CRANE_COMMIT_V1")) h->use_v1 = atoi(s) != 0;
   {
     // k_commit2: everything the SM has beyond the kernel's static tables
     size_t stat = 20 * 1024;
@@ -251,6 +255,7 @@ void crane_sched_destroy(crane_sched_t* h) {
 #undef REL
   for (auto& e : h->ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
+  { std::lock_guard<std::mutex> lk(g_slot_mu); g_slots_used[h->device] &= ~(1u << h->dict_slot); }
   delete h;
 }
 
@@ -265,7 +270,12 @@ int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
       return fail(h, CRANE_EINVAL, "cluster: gres entries must be grouped by ascending name id");
   }
   CU(cudaSetDevice(h->device));
-  h->have_cluster = false;
+  h->have_cluster = false;  // state of the previous cluster / tick is void from here on
+  h->uploaded = false;
+  h->ran = false;
+  if (c->n_partitions && c->part_off[0] != 0) return fail(h, CRANE_EINVAL, "cluster: part_off[0] != 0");
+  for (uint32_t p = 0; p < c->n_partitions; ++p)
+    if (c->part_off[p + 1] < c->part_off[p]) return fail(h, CRANE_EINVAL, "cluster: part_off is not monotonic");
   h->n_nodes = c->n_nodes;
   h->n_parts = c->n_partitions;
   memset(&h->dict, 0, sizeof h->dict);
@@ -311,14 +321,9 @@ int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
   h->n_slots = (uint32_t)h->h_slot_node.size();
   h->max_part_slots = max_mp;
   h->words_per_row = std::max<uint32_t>(4, ((max_mp + 31) / 32 + 3) / 4 * 4);  // 16-byte rows for the bulk copies
-  if (h->use_v1) {
-    if (max_mp > 65535 || commit_smem_bytes(max_mp, h->words_per_row) > kMaxDynSmem || max_mp > 32u * (uint32_t)h->commit_threads)
-      return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
-  } else {
-    h->v2_ring = commit2_ring_slots(max_mp, h->words_per_row, c->n_gres_entries > 0, h->v2_budget);
-    if (max_mp > 65000 || h->v2_ring == 0)
-      return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
-  }
+  h->v2_ring = commit2_ring_slots(max_mp, h->words_per_row, c->n_gres_entries > 0, h->v2_budget);
+  if (max_mp > 65000 || h->v2_ring == 0)
+    return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
   // res_total classes per partition (distinct rows), cached in shared memory by the commit kernel
   std::vector<uint8_t> slot_class(std::max<size_t>(slot_total.size(), 1), 0xff);
   std::vector<Row> class_rows((size_t)std::max<uint32_t>(c->n_partitions, 1) * kMaxClasses);
@@ -343,7 +348,7 @@ int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
   H2D(h->d_slot_total, slot_total.data(), slot_total.size());
   H2D(h->d_slot_class, slot_class.data(), slot_class.size());
   H2D(h->d_class_rows, class_rows.data(), class_rows.size());
-  CU(cudaMemcpyToSymbolAsync(c_dict, &h->dict, sizeof(GresDict), 0, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyToSymbolAsync(c_dicts, &h->dict, sizeof(GresDict), (size_t)h->dict_slot * sizeof(GresDict), cudaMemcpyHostToDevice, h->stream));
   size_t ns = std::max<uint32_t>(h->n_slots, 1);
   CU(h->d_tl_n.ensure(ns));
   CU(h->d_tl_ent.ensure(ns * h->tl_cap));
@@ -364,7 +369,6 @@ int crane_sched_set_shard(crane_sched_t* h, uint32_t rank, uint32_t n_ranks, con
   if (!h) return CRANE_EINVAL;
   if (!h->have_cluster) return fail(h, CRANE_EINVAL, "set_shard: set_cluster first");
   if (n_ranks == 0 || rank >= n_ranks) return fail(h, CRANE_EINVAL, "set_shard: rank %u of %u", rank, n_ranks);
-  if (h->use_v1 && n_ranks > 1) return fail(h, CRANE_ENOSYS, "set_shard: not built for the round-1 commit kernel");
   CU(cudaSetDevice(h->device));
   h->shard_rank = rank;
   h->shard_n = n_ranks;
@@ -403,9 +407,16 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
   if (!h || !pd) return CRANE_EINVAL;
   if (!h->have_cluster) return fail(h, CRANE_EINVAL, "upload: set_cluster first");
   CU(cudaSetDevice(h->device));
+  h->uploaded = false;  // a failed upload leaves nothing runnable behind
+  h->ran = false;
   CU(cudaEventRecord(h->ev[0], h->stream));
   const uint32_t N = pd->n;
   const uint32_t R = rn ? rn->n : 0;
+  if (R && (!rn->start_time || !rn->end_time || !rn->node_num || !rn->partition_priority || !rn->qos_priority ||
+            !rn->account || !rn->view_cpu_raw || !rn->view_mem || !rn->alloc_off))
+    return fail(h, CRANE_EINVAL, "running: null column");
+  for (uint32_t j = 0; j < R; ++j)
+    if (rn->alloc_off[j + 1] < rn->alloc_off[j]) return fail(h, CRANE_EINVAL, "running: alloc_off is not monotonic");
   if (N && (!pd->partition || !pd->time_limit || !pd->submit_time || !pd->node_num || !pd->ntasks ||
             !pd->ntasks_per_node_min || !pd->ntasks_per_node_max || !pd->exclusive || !pd->partition_priority ||
             !pd->qos_priority || !pd->account || !pd->req_node || !pd->req_task || !pd->req_total))
@@ -433,6 +444,9 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
   h->total_alloc = acc;
   if ((pd->incl_off && !pd->incl_nodes && pd->incl_off[N]) || (pd->excl_off && !pd->excl_nodes && pd->excl_off[N]))
     return fail(h, CRANE_EINVAL, "pending: node list CSR without node array");
+  for (uint32_t i = 0; i < N; ++i)
+    if ((pd->incl_off && pd->incl_off[i + 1] < pd->incl_off[i]) || (pd->excl_off && pd->excl_off[i + 1] < pd->excl_off[i]))
+      return fail(h, CRANE_EINVAL, "pending[%u]: node list offsets are not monotonic", i);
   for (uint32_t k = 0; k < R; ++k) max_account = std::max(max_account, rn->account[k]);
   if (max_account > (1u << 24)) return fail(h, CRANE_EINVAL, "account ids must be dense (< 2^24)");
   const uint32_t A = (N + R) ? max_account + 1 : 0;
@@ -705,7 +719,7 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
     if (nq_cap) {
       // n_queued <= nq_cap lives on the device (part_job_off[n_parts]); the
       // kernels below bound themselves with it.
-      CRANE_LAUNCH(k_build_jobq, (nq_cap + 127) / 128, 128, 0, st, pd, queue, h->d_part_job_off.p + h->n_parts, h->d_jobq.p);
+      CRANE_LAUNCH(k_build_jobq, (nq_cap + 127) / 128, 128, 0, st, pd, queue, h->d_part_job_off.p + h->n_parts, h->d_jobq.p, (uint32_t)h->dict_slot);
       h->timing.kernel_launches++;
     }
   } else {
@@ -719,43 +733,28 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
     uint32_t wpb = 8;
     uint32_t nb = std::min<uint32_t>((nq_cap + wpb - 1) / wpb, 148 * 8);
     CRANE_LAUNCH(k_feas_bitmap, nb, wpb * 32, 0, st, cl, pd, h->d_jobq.p, h->d_part_job_off.p + h->n_parts, h->words_per_row, h->d_bitmap.p,
-                 h->shard_n > 1 ? h->d_part_owner.p : nullptr, h->shard_rank);
+                 h->shard_n > 1 ? h->d_part_owner.p : nullptr, h->shard_rank, (uint32_t)h->dict_slot);
     h->timing.kernel_launches++;
   }
   CU(cudaEventRecord(h->ev[5], st));
 
   // ---- sequential commit (R7,R9,R10,R11) -----------------------------------
   if (nq_cap && h->n_parts) {
-    CommitArgs ca{};
-    ca.cl = cl;
-    ca.tl = tl;
-    ca.jobq = h->d_jobq.p;
-    ca.part_job_off = h->d_part_job_off.p;
-    ca.bitmap = h->d_bitmap.p;
-    ca.words_per_row = h->words_per_row;
-    ca.out = out;
-    ca.now = now;
-    ca.max_window = h->cfg.max_time_window_s;
-    ca.max_jobs = h->cfg.max_jobs_per_node;
+    Commit2Args c2{};
+    c2.cl = cl; c2.tl = tl; c2.jobq = h->d_jobq.p; c2.part_job_off = h->d_part_job_off.p; c2.bitmap = h->d_bitmap.p;
+    c2.words_per_row = h->words_per_row; c2.ring = h->v2_ring; c2.out = out; c2.now = now;
+    c2.max_window = h->cfg.max_time_window_s; c2.max_jobs = h->cfg.max_jobs_per_node; c2.cost_policy = h->cfg.cost_policy;
     CU(h->d_prof.ensure((size_t)h->n_parts * 16));
-    ca.prof = h->d_prof.p;
-    if (h->use_v1) {
-      size_t smem = commit_smem_bytes(h->max_part_slots, h->words_per_row);
-      CRANE_LAUNCH(k_commit, h->n_parts, h->commit_threads, smem, st, ca);
-    } else {
-      Commit2Args c2{};
-      c2.cl = cl; c2.tl = tl; c2.jobq = ca.jobq; c2.part_job_off = ca.part_job_off; c2.bitmap = ca.bitmap;
-      c2.words_per_row = ca.words_per_row; c2.ring = h->v2_ring; c2.out = out; c2.now = now;
-      c2.max_window = ca.max_window; c2.max_jobs = ca.max_jobs; c2.cost_policy = h->cfg.cost_policy; c2.prof = ca.prof;
-      c2.gres = h->dict.n_entries > 0 ? 1u : 0u;
-      size_t smem = commit2_smem_bytes(h->max_part_slots, h->words_per_row, c2.gres != 0, h->v2_ring);
-      uint32_t grid = h->n_parts;
-      if (h->shard_n > 1) {
-        c2.part_list = h->d_part_list.p;
-        grid = (uint32_t)h->h_part_list.size();
-      }
-      if (grid) CRANE_LAUNCH(k_commit2, grid, kT2, smem, st, c2);
+    c2.prof = h->d_prof.p;
+    c2.gres = h->dict.n_entries > 0 ? 1u : 0u;
+    c2.dslot = (uint32_t)h->dict_slot;
+    size_t smem = commit2_smem_bytes(h->max_part_slots, h->words_per_row, c2.gres != 0, h->v2_ring);
+    uint32_t grid = h->n_parts;
+    if (h->shard_n > 1) {
+      c2.part_list = h->d_part_list.p;
+      grid = (uint32_t)h->h_part_list.size();
     }
+    if (grid) CRANE_LAUNCH(k_commit2, grid, kT2, smem, st, c2);
     h->timing.kernel_launches++;
     if (h->shard_n > 1 && N) {
       CRANE_LAUNCH(k_shard_mask, (N + 255) / 256, 256, 0, st, pd, out, h->d_part_owner.p, h->n_parts, h->shard_rank);

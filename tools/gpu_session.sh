@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 tail -5 gpurun_out/gputests.log
 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1
 tail -2 gpurun_out/bench.log
-CRANE_COMMIT_V1=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v1.log 2>&1
-tail -1 gpurun_out/bench_v1.log
+
+
 for c in 2 5; do timeout 300 python tools/profile_commit.py $c > gpurun_out/prof_config$c.log 2>&1; done
 SEED_ID=3002 timeout 300 python tools/profile_commit.py 2 > gpurun_out/prof_config2_s3002.log 2>&1
 head -3 gpurun_out/prof_config2.log gpurun_out/prof_config5.log gpurun_out/prof_config2_s3002.log

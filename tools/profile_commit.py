@@ -1,4 +1,4 @@
-"""Phase breakdown of k_commit (needs the -DCRANE_PROFILE build)."""
+"""Phase breakdown of k_commit2 (needs the -DCRANE_PROFILE build)."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -6,16 +6,10 @@ from cranesched_b200 import synth, abi
 from cranesched_b200.scheduler import GpuScheduler
 from cranesched_b200.build import CSRC
 
-NAMES_V1 = ["0 single: job load", "1 batch: loop top", "2 single: scan+test(+update)", "3 batch: form + select", "4 resolve: load lists",
-         "5 resolve: fixed point", "6 batch: tasks + clash check", "7 single: outputs+rekey", "8 #windows of the one-job path", "9 batch: evaluate", "10 batch: re-key (driver)",
-         "11 batch: wait for commits", "12 #re-deals of the order", "13 #committed in batches", "14 #batches", "15 single: entry"]
-TIMED_V1 = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 15}
-NAMES_V2 = ["0 loop top + ring issue", "1 form batch", "2 select", "3 resolve", "4 evaluate", "5 commit", "6 re-key", "7 one-job path",
+NAMES = ["0 loop top + ring issue", "1 form batch", "2 select", "3 resolve", "4 evaluate", "5 commit", "6 re-key", "7 one-job path",
             "8 #windows of the one-job path", "9 #batches cut: candidates taken (wait)", "10 #batches cut: clash with a re-keyed node", "11 #batches cut: pick failed the exact test",
             "12 #batches cut: backfill without a start", "13 #jobs finished in batches", "14 #batches", "15 #exact tests of the one-job path"]
-TIMED_V2 = {0, 1, 2, 3, 4, 5, 6, 7}
-V1 = bool(os.environ.get("CRANE_COMMIT_V1"))
-NAMES, TIMED = (NAMES_V1, TIMED_V1) if V1 else (NAMES_V2, TIMED_V2)
+TIMED = {0, 1, 2, 3, 4, 5, 6, 7}
 cfg_id = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 kw = {}
 if len(sys.argv) > 3:
