@@ -254,4 +254,16 @@ CRANE_HD double cost_delta(int64_t seconds, int64_t res_cpu_raw, int64_t total_c
 #endif
 }
 
+// IUpdateNodeCostPolicy::UpdateCost as a cost step: policy 0 MinCpuTimeRatioFirst
+// (JobScheduler.h:40-54), policy 1 BestFit (ours, BASELINE config 4: the node's
+// cost is its free cpu count over all allocations; integers as doubles, exact).
+CRANE_HD double cost_step(uint32_t policy, int64_t seconds, int64_t res_cpu_raw, int64_t total_cpu_raw) {
+#if defined(__CUDA_ARCH__) || defined(CRANE_EMU)
+  if (policy == 1) return -__ll2double_rn(res_cpu_raw);
+#else
+  if (policy == 1) return -(double)res_cpu_raw;
+#endif
+  return cost_delta(seconds, res_cpu_raw, total_cpu_raw);
+}
+
 }  // namespace crane

@@ -56,6 +56,7 @@ constexpr int kMaxT = kNG;         // (job, node) tasks per batch: one group eac
 constexpr int kBlk = 32;           // order positions per bounds block
 constexpr int kRingMax = 64;       // prefetch ring depth (jobs)
 constexpr int kRK = 64;
+constexpr int kHeapMax = 128;      // general task distribution: top-K heaps of up to 127 nodes
 constexpr int kDeltaClasses = 4;
 #ifndef CRANE_SPEC_EVAL
 #define CRANE_SPEC_EVAL 1          // warps 1-7 test each slot's first guess while warp 0 resolves (A/B on config 2:
@@ -347,6 +348,8 @@ struct Commit2Args {
   uint32_t cost_policy;
   uint32_t gres;              // the cluster has gres entries
   uint32_t dslot;             // the handle's gres dictionary: c_dicts[dslot]
+  const View* req_node;       // pending.req_node / req_task (general task distribution only)
+  const View* req_task;
   const uint32_t* part_list;  // partitions this launch commits (one CTA each), or null = all
   unsigned long long* prof;
 };
@@ -356,7 +359,9 @@ struct Ctx2 {           // per-CTA constants
   TimelineDev tl;
   PlaceDev out;
   int64_t now, max_window;
-  uint32_t base, mp, words, max_jobs, ring, gres, dslot;
+  uint32_t base, mp, words, max_jobs, ring, gres, dslot, cost_policy;
+  const View* req_node;
+  const View* req_task;
 };
 #define C_DICT2 (c_dicts[s2_cx.dslot])
 #define SM2() smem2_layout(s2_cx.mp, s2_cx.words, s2_cx.ring, s2_cx.gres != 0)
@@ -502,7 +507,7 @@ __device__ __forceinline__ void select2(const Smem2& sm, uint32_t mp, const JSel
 // when the job is placed on it
 __device__ __forceinline__ double new_cost2(const JobQ& jq, uint32_t q) {
   const int64_t tot_cpu = node_total_cpu2(q);
-  return __dadd_rn(SM2().cost[q], cost_delta(jq.time_limit, (jq.flags & 1u) ? tot_cpu : jq.req.cpu_raw, tot_cpu));
+  return __dadd_rn(SM2().cost[q], cost_step(s2_cx.cost_policy, jq.time_limit, (jq.flags & 1u) ? tot_cpu : jq.req.cpu_raw, tot_cpu));
 }
 
 // block-wide exclusive prefix over one value per thread (kT2 threads)
@@ -1005,6 +1010,381 @@ __device__ __noinline__ void single2(uint32_t ji) {
   }
 }
 
+// ---- general task distribution (ntasks_per_node_max > min or an uneven ntasks) --------
+// JobScheduler.cpp:5193-5222, 5258-5361: every capable node can take between
+// ntasks_per_node_min and _max tasks; the K nodes with the most tasks are kept in a
+// std::priority_queue (top = fewest tasks) until K nodes hold >= ntasks tasks; tasks
+// are then handed out in pop order. The queue is restated with libstdc++'s own heap
+// algorithm (std::push_heap / std::pop_heap: __push_heap, __adjust_heap), so equal
+// task counts leave the heap in the reference's order.
+struct Heap2 {
+  uint16_t nt[kHeapMax];   // tasks the node can take
+  uint16_t q[kHeapMax];    // node
+  uint32_t size, sum;
+};
+__shared__ Heap2 s2_heap[2];                 // [0] by res_total (backfill), [1] by the window minimum (immediate start)
+__shared__ uint16_t s2_g_nt[2][kNG];         // per chunk candidate: tasks by res_total / by the window minimum
+__shared__ uint16_t s2_g_node[kHeapMax], s2_g_n[kHeapMax];  // hand-out: node, tasks, in pop order
+__shared__ uint32_t s2_g_done;
+
+// comp(a, b) of std::priority_queue<Info>: Info::operator< is "has more tasks"
+__device__ __forceinline__ bool heap_less2(uint32_t a_nt, uint32_t b_nt) { return a_nt > b_nt; }
+__device__ inline void heap_push2(Heap2& h, uint32_t nt, uint32_t q) {  // push_back + std::push_heap
+  uint32_t hole = h.size++;
+  while (hole > 0) {
+    const uint32_t parent = (hole - 1) / 2;
+    if (!heap_less2(h.nt[parent], nt)) break;
+    h.nt[hole] = h.nt[parent]; h.q[hole] = h.q[parent];
+    hole = parent;
+  }
+  h.nt[hole] = (uint16_t)nt; h.q[hole] = (uint16_t)q;
+}
+__device__ inline void heap_pop2(Heap2& h) {  // std::pop_heap + pop_back
+  const uint32_t len = h.size - 1;
+  if (len == 0) { h.size = 0; return; }
+  const uint32_t vnt = h.nt[len], vq = h.q[len];   // value = *(last-1); *(last-1) = *first
+  uint32_t hole = 0, second = 0;
+  while ((int32_t)second < ((int32_t)len - 1) / 2) {  // __adjust_heap
+    second = 2 * (second + 1);
+    if (heap_less2(h.nt[second], h.nt[second - 1])) --second;
+    h.nt[hole] = h.nt[second]; h.q[hole] = h.q[second];
+    hole = second;
+  }
+  if ((len & 1u) == 0 && (int32_t)second == ((int32_t)len - 2) / 2) {
+    second = 2 * (second + 1);
+    h.nt[hole] = h.nt[second - 1]; h.q[hole] = h.q[second - 1];
+    hole = second - 1;
+  }
+  while (hole > 0) {  // __push_heap(first, hole, 0, value)
+    const uint32_t parent = (hole - 1) / 2;
+    if (!heap_less2(h.nt[parent], vnt)) break;
+    h.nt[hole] = h.nt[parent]; h.q[hole] = h.q[parent];
+    hole = parent;
+  }
+  h.nt[hole] = (uint16_t)vnt; h.q[hole] = (uint16_t)vq;
+  h.size = len;
+}
+
+// get_max_tasks (JobScheduler.cpp:5207-5222): tasks the row can take, 0 if not even the minimum
+__device__ __noinline__ uint32_t max_tasks2(const View& min_view, const View& req_task, uint32_t tmin, uint32_t tmax, const Row& res) {
+  Row got;
+  if (!feasible<true>(min_view, res, C_DICT2, &got)) return 0;
+  Row rest = res;
+  row_sub(rest, got);
+  uint32_t n = tmin;
+  while (n < tmax && feasible<true>(req_task, rest, C_DICT2, &got)) {
+    ++n;
+    row_sub(rest, got);
+  }
+  return n;
+}
+
+__device__ __noinline__ void single2_general(uint32_t ji) {
+  const Smem2 sm = SM2();
+  const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id(), gl = g_lane(), gi = g_index();
+  const uint32_t mp = s2_cx.mp, base = s2_cx.base, ring = s2_cx.ring;
+  const int64_t now = s2_cx.now;
+  const TimelineDev& tl = s2_cx.tl;
+  const uint32_t slot = ji % ring;
+  mbar_wait(&s2_bar[slot], (ji / ring) & 1u);
+  const JobQ& jq = s2_jobs[slot];
+  JSel2 js;
+  jsel_load(jq, sm.bits_ring + (size_t)slot * s2_cx.words, js);
+  const uint32_t K = jq.node_num, tmin = jq.ntasks_per_node, tmax = jq.ntpn_max, ntasks = jq.ntasks;
+  const bool exclusive = js.exclusive;
+  const int64_t limit = jq.time_limit;
+  const View min_view = jq.req;
+  const View req_node = s2_cx.req_node[jq.job], req_task = s2_cx.req_task[jq.job];
+  const int64_t w_end = now + limit;
+  if (K > mp || K == 0 || K >= (uint32_t)kHeapMax) {
+    if (tid == 0) s2_cx.out.reason[jq.job] = CRANE_REASON_RESOURCE;
+    return;
+  }
+  if (tid == 0) { s2_heap[0].size = 0; s2_heap[0].sum = 0; s2_heap[1].size = 0; s2_heap[1].sum = 0; s2_g_done = 0; s2_label = 0; }
+  __syncthreads();
+  // ---- the walk: capable nodes in order, 32 per round --------------------------------
+  uint32_t pos = 0;
+  while (pos < mp && !s2_g_done) {
+    const uint32_t p = pos + tid;
+    uint32_t q = 0;
+    bool cap = false;
+    if (p < mp) {
+      q = sm.ord[p];
+      cap = capable2(sm, js, q);
+    }
+    if (tid == 0) s2_cutpos = pos + kT2;
+    uint32_t totc;
+    const uint32_t rank_c = block_excl_scan(cap ? 1u : 0u, totc);
+    const uint32_t ncand = totc < (uint32_t)kNG ? totc : (uint32_t)kNG;
+    if (cap && rank_c < (uint32_t)kNG) s2_chunk[rank_c] = (uint16_t)q;
+    if (cap && rank_c == (uint32_t)kNG - 1u && totc > (uint32_t)kNG) s2_cutpos = p + 1;
+    __syncthreads();
+    const uint32_t cutpos = s2_cutpos;
+    {
+      const bool act = gi < ncand;
+      uint32_t qg = 0, g = 0, ns = 0;
+      Row tot, a0;
+      row_zero(tot);
+      row_zero(a0);
+      if (act) {
+        qg = s2_chunk[gi];
+        g = base + qg;
+        ns = sm.nseg[qg];
+        tot = node_total2(qg);
+        a0 = tl.avail0[g];
+      }
+      Win2 w;
+      g_window(tl.ent + (size_t)g * tl.cap, ns, w_end, min_view.cpu_raw, min_view.mem, true, false, tot, act && exclusive, w);
+      if (act && gl == 0) {
+        const uint32_t n_total = max_tasks2(min_view, req_task, tmin, tmax, tot);  // > 0: the node is capable
+        s2_g_nt[0][gi] = (uint16_t)n_total;
+        if (exclusive) s2_g_nt[1][gi] = w.ok ? (uint16_t)n_total : (uint16_t)0;  // JobScheduler.cpp:5285-5307
+        else s2_g_nt[1][gi] = feasible<false>(min_view, a0, C_DICT2, nullptr) ? (uint16_t)0xffffu : (uint16_t)0;  // :5310; 0xffff = to be counted below
+      }
+    }
+    __syncthreads();
+    // the window minimum row itself (cpu, mem minima too) for the candidates that need it
+    {
+      const bool act = gi < ncand && s2_g_nt[1][gi] == 0xffffu;
+      uint32_t qg = 0, g = 0, ns = 0;
+      if (act) { qg = s2_chunk[gi]; g = base + qg; ns = sm.nseg[qg]; }
+      const TlEntry* E = tl.ent + (size_t)g * tl.cap;
+      long long mcpu = INT64_MAX;
+      unsigned long long mmem = ~0ull, msw = ~0ull;
+      bool more = act;
+      for (uint32_t b0 = 0; __any_sync(kFullMask, more); b0 += kGL) {
+        const uint32_t i = b0 + gl;
+        bool inw = false;
+        if (more && i < ns) {
+          const TlEntry e = E[i];
+          inw = e.t < w_end;
+          if (inw) {
+            mcpu = e.seg.cpu_raw < mcpu ? e.seg.cpu_raw : mcpu;
+            mmem = e.seg.mem < mmem ? e.seg.mem : mmem;
+            msw = e.seg.mem_sw < msw ? e.seg.mem_sw : msw;
+          }
+        }
+        if (g_ballot(inw) != (1u << kGL) - 1u) more = false;
+      }
+#pragma unroll
+      for (int o = 1; o < kGL; o <<= 1) {
+        const long long oc = __shfl_xor_sync(kFullMask, mcpu, o);
+        const unsigned long long om = __shfl_xor_sync(kFullMask, mmem, o), os = __shfl_xor_sync(kFullMask, msw, o);
+        mcpu = oc < mcpu ? oc : mcpu;
+        mmem = om < mmem ? om : mmem;
+        msw = os < msw ? os : msw;
+      }
+      Win2 w;
+      Row tot;
+      row_zero(tot);
+      g_window(E, ns, w_end, min_view.cpu_raw, min_view.mem, false, true, tot, act, w);
+      if (act && gl == 0) {
+        const Row a0 = tl.avail0[g];
+        Row wr;
+        win_row(w, a0, min_view, wr);
+        wr.cpu_raw = a0.cpu_raw < mcpu ? a0.cpu_raw : mcpu;  // res_avail Ckmin'ed with every segment of the window
+        wr.mem = a0.mem < mmem ? a0.mem : mmem;
+        wr.mem_sw = a0.mem_sw < msw ? a0.mem_sw : msw;
+        s2_g_nt[1][gi] = (uint16_t)max_tasks2(min_view, req_task, tmin, tmax, wr);
+      }
+    }
+    __syncthreads();
+    // heaps, in node order (one thread: the reference's loop body, JobScheduler.cpp:5269-5334)
+    if (tid == 0) {
+      Heap2& ht = s2_heap[0];
+      Heap2& ha = s2_heap[1];
+      for (uint32_t c = 0; c < ncand; ++c) {
+        const uint32_t n_total = s2_g_nt[0][c], n_avail = s2_g_nt[1][c], qn = s2_chunk[c];
+        if (n_total == 0) continue;
+        if (ht.size < K || ht.sum < ntasks) {
+          ht.sum += n_total;
+          heap_push2(ht, n_total, qn);
+          if (ht.size > K) { ht.sum -= ht.nt[0]; heap_pop2(ht); }
+        }
+        if (n_avail) {
+          ha.sum += n_avail;
+          heap_push2(ha, n_avail, qn);
+          if (ha.size > K) { ha.sum -= ha.nt[0]; heap_pop2(ha); }
+          if (ha.size == K && ha.sum >= ntasks) { s2_g_done = 1; break; }
+        }
+      }
+    }
+    __syncthreads();
+    pos = cutpos;
+  }
+  // ---- decision and hand-out (JobScheduler.cpp:5338-5404) ---------------------------------
+  const bool start_now = s2_heap[1].size == K && s2_heap[1].sum >= ntasks;
+  const bool can_bf = s2_heap[0].size == K && s2_heap[0].sum >= ntasks;
+  __syncthreads();
+  if (tid == 0 && (start_now || can_bf)) {
+    Heap2& h = s2_heap[start_now ? 1 : 0];
+    int32_t rest = (int32_t)ntasks - (int32_t)K;
+    uint32_t k = 0;
+    while (h.size) {
+      const int32_t cap_n = (int32_t)h.nt[0] - 1;
+      const int32_t n = (rest < cap_n ? rest : cap_n) + 1;
+      s2_g_node[k] = h.q[0];
+      s2_g_n[k] = (uint16_t)n;
+      rest -= n - 1;
+      ++k;
+      heap_pop2(h);
+    }
+  }
+  __syncthreads();
+  bool placed = false;
+  int64_t start_time = now;
+  if (start_now || can_bf) {
+    int64_t T0 = now;
+    bool ok = true;
+    if (!start_now) {
+      // earliest common start of the K nodes (JobScheduler.h:806-849), allocation against res_total
+      bool found = false, failed = false;
+      for (uint32_t it = 0; !found && !failed; ++it) {
+        long long emax = INT64_MIN, emin = kInf;
+        for (uint32_t k0 = 0; k0 < K; k0 += kNG) {
+          const uint32_t k = k0 + gi;
+          const bool act = k < K;
+          uint32_t q = 0, g = 0, ns = 0;
+          Row alloc;
+          row_zero(alloc);
+          if (act) {
+            q = s2_g_node[k];
+            g = base + q;
+            ns = sm.nseg[q];
+            const Row tot = node_total2(q);
+            if (exclusive) alloc = tot;
+            else { View full; view_node_plus_tasks(full, req_node, req_task, s2_g_n[k]); feasible_alloc(full, tot, alloc, s2_cx.dslot); }
+          }
+          const int64_t e = g_earliest(tl.ent + (size_t)g * tl.cap, ns, alloc, T0, limit, act);
+          if (act) { emax = e > emax ? e : emax; emin = e < emin ? e : emin; }
+        }
+        if (gl == 0) { s2_e[it & 1u][gi] = emax; s2_e2[it & 1u][gi] = emin; }
+        __syncthreads();
+        long long tmx = INT64_MIN, tmn = kInf;
+        const uint32_t ng = K < (uint32_t)kNG ? K : (uint32_t)kNG;
+        for (uint32_t i = 0; i < ng; ++i) {
+          const long long x = s2_e[it & 1u][i], y = s2_e2[it & 1u][i];
+          tmx = x > tmx ? x : tmx;
+          tmn = y < tmn ? y : tmn;
+        }
+        if (tmx == kInf) failed = true;
+        else if (tmn == tmx) { found = true; T0 = tmx; }
+        else T0 = tmx;
+      }
+      ok = found && T0 - now <= s2_cx.max_window;
+    }
+    if (ok) {
+      placed = true;
+      start_time = T0;
+      for (uint32_t k0 = 0; k0 < K; k0 += kNG) {
+        const uint32_t k = k0 + gi;
+        const bool act = k < K;
+        uint32_t q = 0, g = 0, ns = 0;
+        Row tot, a0;
+        row_zero(tot);
+        row_zero(a0);
+        if (act) {
+          q = s2_g_node[k];
+          g = base + q;
+          ns = sm.nseg[q];
+          tot = node_total2(q);
+          a0 = tl.avail0[g];
+        }
+        TlEntry* E = tl.ent + (size_t)g * tl.cap;
+        // the window minimum again (immediate start: the allocation comes out of it)
+        long long mcpu = INT64_MAX;
+        unsigned long long mmem = ~0ull, msw = ~0ull;
+        bool more = act && start_now && !exclusive;
+        for (uint32_t b0 = 0; __any_sync(kFullMask, more); b0 += kGL) {
+          const uint32_t i = b0 + gl;
+          bool inw = false;
+          if (more && i < ns) {
+            const TlEntry e = E[i];
+            inw = e.t < w_end;
+            if (inw) {
+              mcpu = e.seg.cpu_raw < mcpu ? e.seg.cpu_raw : mcpu;
+              mmem = e.seg.mem < mmem ? e.seg.mem : mmem;
+              msw = e.seg.mem_sw < msw ? e.seg.mem_sw : msw;
+            }
+          }
+          if (g_ballot(inw) != (1u << kGL) - 1u) more = false;
+        }
+#pragma unroll
+        for (int o = 1; o < kGL; o <<= 1) {
+          const long long oc = __shfl_xor_sync(kFullMask, mcpu, o);
+          const unsigned long long om = __shfl_xor_sync(kFullMask, mmem, o), os = __shfl_xor_sync(kFullMask, msw, o);
+          mcpu = oc < mcpu ? oc : mcpu;
+          mmem = om < mmem ? om : mmem;
+          msw = os < msw ? os : msw;
+        }
+        Win2 w;
+        g_window(E, ns, w_end, min_view.cpu_raw, min_view.mem, false, true, tot, act && start_now && !exclusive, w);
+        Row alloc;
+        row_zero(alloc);
+        if (act) {
+          if (exclusive) alloc = tot;
+          else {
+            View full;
+            view_node_plus_tasks(full, req_node, req_task, s2_g_n[k]);
+            Row src = tot;
+            if (start_now) {
+              win_row(w, a0, min_view, src);
+              src.cpu_raw = a0.cpu_raw < mcpu ? a0.cpu_raw : mcpu;
+              src.mem = a0.mem < mmem ? a0.mem : mmem;
+              src.mem_sw = a0.mem_sw < msw ? a0.mem_sw : msw;
+            }
+            feasible_alloc(full, src, alloc, s2_cx.dslot);
+          }
+        }
+        Row seg0;
+        row_zero(seg0);
+        const uint32_t nn = g_update(E, ns, T0, T0 + limit, alloc, act, seg0);
+        uint32_t rank = 0;  // node-index ascending output slot (deviation D3)
+        if (act && K > 1)
+          for (uint32_t m = gl; m < K; m += kGL) rank += s2_g_node[m] < q ? 1u : 0u;
+#pragma unroll
+        for (int o = 1; o < kGL; o <<= 1) rank += __shfl_xor_sync(kFullMask, rank, o);
+        if (act && gl == 0) {
+          write_node2(jq, q, rank, alloc, nn, seg0);
+          s2_cx.out.alloc_ntasks[jq.alloc_off + rank] = s2_g_n[k];
+          if (T0 != now && !row_le(alloc, a0)) atomicOr(&s2_label, 1u);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (placed) {
+    if (tid == 0) {
+      s2_cx.out.start_time[jq.job] = start_time;
+      s2_cx.out.end_time[jq.job] = start_time + limit;
+      s2_cx.out.n_alloc[jq.job] = K;
+      uint8_t reason = CRANE_REASON_NONE;
+      if (start_time != now) reason = s2_label ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY;
+      s2_cx.out.reason[jq.job] = reason;
+    }
+    // the node's cost grows by its own allocation's cpu share (JobScheduler.h:46-52)
+    const bool full_rekey = K > (uint32_t)kRK;
+    for (uint32_t k = tid; k < K; k += kT2) {
+      const uint32_t q = s2_g_node[k];
+      const int64_t tot_cpu = node_total_cpu2(q);
+      const int64_t cpu = exclusive ? tot_cpu : req_node.cpu_raw + req_task.cpu_raw * (int64_t)s2_g_n[k];
+      const double nc = __dadd_rn(sm.cost[q], cost_step(s2_cx.cost_policy, limit, cpu, tot_cpu));
+      if (full_rekey) sm.cost[q] = nc; else { s2_rk_node[k] = q; s2_rk_nc[k] = nc; }
+    }
+    __syncthreads();
+    if (full_rekey) order_sort2();
+    else {
+      order_rekey2(K, kT2);
+      __syncthreads();
+      rekey_bounds2(K);
+    }
+  } else if (tid == 0) {
+    s2_cx.out.reason[jq.job] = CRANE_REASON_RESOURCE;  // JobScheduler.cpp:5802
+  }
+  (void)wid;
+  (void)lane;
+}
+
 __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
   const uint32_t part = a.part_list ? a.part_list[blockIdx.x] : blockIdx.x;
   const uint32_t base = a.cl.part_base[part];
@@ -1032,7 +1412,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
   if (tid == 0) {
     s2_cx.cl = a.cl; s2_cx.tl = a.tl; s2_cx.out = a.out;
     s2_cx.now = a.now; s2_cx.max_window = a.max_window; s2_cx.base = base; s2_cx.mp = mp; s2_cx.words = words;
-    s2_cx.max_jobs = a.max_jobs; s2_cx.ring = ring; s2_cx.gres = a.gres; s2_cx.dslot = a.dslot;
+    s2_cx.max_jobs = a.max_jobs; s2_cx.ring = ring; s2_cx.gres = a.gres; s2_cx.dslot = a.dslot; s2_cx.cost_policy = a.cost_policy; s2_cx.req_node = a.req_node; s2_cx.req_task = a.req_task;
     s2_prof_windows = 0; s2_prof_tests = 0; s2_prof_singles = 0;
     for (uint32_t s = 0; s < ring; ++s) mbar_init(&s2_bar[s], 1);
     fence_mbar_init();
@@ -1072,7 +1452,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
     ensure_issued(ji);
     PROF(0);
     if (want_single) {
-      single2(ji);
+      if (s2_jobs[ji % ring].flags & 4u) single2_general(ji); else single2(ji);
       PROF(7);
       ++ji;
       want_single = false;
@@ -1088,7 +1468,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
         myslot = j % ring;
         mbar_wait(&s2_bar[myslot], (j / ring) & 1u);
         myK = s2_jobs[myslot].node_num;
-        okj = myK >= 1 && myK <= mp && myK <= (uint32_t)kMaxT;
+        okj = myK >= 1 && myK <= mp && myK <= (uint32_t)kMaxT && !(s2_jobs[myslot].flags & 4u);
       }
       uint32_t cum = okj ? myK : (uint32_t)kMaxT + 1u;
       for (int o = 1; o < 32; o <<= 1) {
@@ -1133,7 +1513,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
         const JobQ& jq = s2_jobs[bj.slot];
         for (uint32_t c = gl; c < (uint32_t)kDeltaClasses; c += kGL) {
           const int64_t tot_cpu = s2_classrow[c].cpu_raw;
-          s2_jdelta[gi][c] = tot_cpu > 0 ? cost_delta(jq.time_limit, js.exclusive ? tot_cpu : jq.req.cpu_raw, tot_cpu) : 0.0;
+          s2_jdelta[gi][c] = tot_cpu > 0 ? cost_step(a.cost_policy, jq.time_limit, js.exclusive ? tot_cpu : jq.req.cpu_raw, tot_cpu) : 0.0;
         }
         for (uint32_t w = bj.tfirst + gl; w < bj.need; w += kGL) s2_tjob[w] = gi;
         if (gl == 0) {

@@ -90,6 +90,7 @@ struct crane_sched {
   uint64_t total_alloc = 0;
   bool have_lists_incl = false, have_lists_excl = false, have_mandated = false;
   std::vector<uint32_t> h_alloc_off;
+  DBuf<uint32_t> d_ntpn_max, d_ntasks;
   DBuf<uint32_t> d_partition, d_node_num, d_ntpn, d_part_prio, d_qos_prio, d_account, d_alloc_off;
   DBuf<int64_t> d_time_limit, d_submit;
   DBuf<uint8_t> d_exclusive;
@@ -200,7 +201,7 @@ int crane_sched_create(const crane_sched_config_t* cfg, int device, crane_sched_
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return CRANE_ENODEV;
   if (cfg->max_jobs_per_node < 2 || cfg->max_jobs_per_node > 65000) return CRANE_EINVAL;
-  if (cfg->cost_policy != 0) return CRANE_ENOSYS;
+  if (cfg->cost_policy > 1) return CRANE_ENOSYS;  // 0 MinCpuTimeRatioFirst (JobScheduler.h:40), 1 BestFit (ours, config 4)
   if (device >= 64) return CRANE_EINVAL;
   int slot = -1;
   {
@@ -251,7 +252,7 @@ void crane_sched_destroy(crane_sched_t* h) {
   REL(d_vals_b); REL(d_hist); REL(d_part_count); REL(d_part_job_off); REL(d_bitmap); REL(d_jobq); REL(d_reason);
   REL(d_out_prio); REL(d_out_start); REL(d_out_end); REL(d_out_nalloc); REL(d_out_node); REL(d_out_ntasks);
   REL(d_out_res); REL(d_prof); REL(d_qos); REL(d_user); REL(d_q_u32); REL(d_q_chain_off); REL(d_q_chain);
-  REL(d_q_i64); REL(d_q_valid); REL(d_part_owner); REL(d_part_list); REL(d_q_tres); REL(d_q_user_usage); REL(d_q_acct_usage); REL(d_q_qos_usage);
+  REL(d_q_i64); REL(d_q_valid); REL(d_part_owner); REL(d_part_list); REL(d_ntpn_max); REL(d_ntasks); REL(d_q_tres); REL(d_q_user_usage); REL(d_q_acct_usage); REL(d_q_qos_usage);
 #undef REL
   for (auto& e : h->ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -429,11 +430,13 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
     h->h_alloc_off[i] = (uint32_t)acc;
     if (pd->node_num[i] == 0) return fail(h, CRANE_EINVAL, "pending[%u]: node_num == 0", i);
     if (pd->time_limit[i] < 1) return fail(h, CRANE_EINVAL, "pending[%u]: time_limit < 1", i);
-    uint32_t t = pd->ntasks_per_node_min[i];
-    // general task distribution (ntasks_per_node_max > min; top-k heap of
-    // JobScheduler.cpp:5193-5205) is SURVEY.md §8f rank 2
-    if (t == 0 || t != pd->ntasks_per_node_max[i] || (uint64_t)t * pd->node_num[i] != pd->ntasks[i])
-      return fail(h, CRANE_ENOSYS, "pending[%u]: only ntasks_per_node_min == max and ntasks == node_num*ntasks_per_node are built", i);
+    const uint32_t t = pd->ntasks_per_node_min[i], tmax = pd->ntasks_per_node_max[i];
+    if (t == 0 || tmax < t) return fail(h, CRANE_EINVAL, "pending[%u]: ntasks_per_node_min/max", i);
+    // general task distribution (the top-K heaps of JobScheduler.cpp:5193-5205): heaps of up to 127 nodes
+    if ((tmax != t || (uint64_t)t * pd->node_num[i] != pd->ntasks[i]) && pd->node_num[i] >= (uint32_t)kHeapMax)
+      return fail(h, CRANE_ENOSYS, "pending[%u]: a job with a ntasks_per_node range wider than %d nodes", i, kHeapMax - 1);
+    if ((uint64_t)tmax * pd->node_num[i] < pd->ntasks[i] || (uint64_t)t * pd->node_num[i] > pd->ntasks[i])
+      return fail(h, CRANE_EINVAL, "pending[%u]: ntasks outside [node_num*ntpn_min, node_num*ntpn_max]", i);
     if (pd->req_node[i].cpu_raw < 0 || pd->req_task[i].cpu_raw < 0)
       return fail(h, CRANE_EINVAL, "pending[%u]: negative cpu request", i);
     acc += pd->node_num[i];
@@ -457,6 +460,8 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
   H2D(h->d_submit, pd->submit_time, N);
   H2D(h->d_node_num, pd->node_num, N);
   H2D(h->d_ntpn, pd->ntasks_per_node_min, N);
+  H2D(h->d_ntpn_max, pd->ntasks_per_node_max, N);
+  H2D(h->d_ntasks, pd->ntasks, N);
   H2D(h->d_exclusive, pd->exclusive, N);
   H2D(h->d_part_prio, pd->partition_priority, N);
   H2D(h->d_qos_prio, pd->qos_priority, N);
@@ -590,6 +595,8 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
   pd.submit_time = h->d_submit.p;
   pd.node_num = h->d_node_num.p;
   pd.ntasks_per_node_min = h->d_ntpn.p;
+  pd.ntasks_per_node_max = h->d_ntpn_max.p;
+  pd.ntasks = h->d_ntasks.p;
   pd.exclusive = h->d_exclusive.p;
   pd.partition_priority = h->d_part_prio.p;
   pd.qos_priority = h->d_qos_prio.p;
@@ -659,7 +666,7 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
     CU(cudaMemsetAsync(h->d_out_res.p, 0, sizeof(Row) * h->total_alloc, st));
   }
   if (h->n_slots) {
-    CRANE_LAUNCH(k_node_init, (h->n_slots + 127) / 128, 128, 0, st, cl, rn, tl, now, h->cfg.max_jobs_per_node);
+    CRANE_LAUNCH(k_node_init, (h->n_slots + 127) / 128, 128, 0, st, cl, rn, tl, now, h->cfg.max_jobs_per_node, h->cfg.cost_policy);
     h->timing.kernel_launches++;
   }
   CU(cudaEventRecord(h->ev[3], st));
@@ -748,6 +755,8 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
     c2.prof = h->d_prof.p;
     c2.gres = h->dict.n_entries > 0 ? 1u : 0u;
     c2.dslot = (uint32_t)h->dict_slot;
+    c2.req_node = h->d_req_node.p;
+    c2.req_task = h->d_req_task.p;
     size_t smem = commit2_smem_bytes(h->max_part_slots, h->words_per_row, c2.gres != 0, h->v2_ring);
     uint32_t grid = h->n_parts;
     if (h->shard_n > 1) {

@@ -44,6 +44,8 @@ struct PendingDev {  // SoA mirror of crane_pending_t
   const int64_t* submit_time;
   const uint32_t* node_num;
   const uint32_t* ntasks_per_node_min;
+  const uint32_t* ntasks_per_node_max;
+  const uint32_t* ntasks;
   const uint8_t* exclusive;
   const uint32_t* partition_priority;
   const uint32_t* qos_priority;
@@ -119,11 +121,12 @@ struct __align__(16) JobQ {
   uint32_t node_num;
   uint32_t alloc_off;
   uint32_t ntasks_per_node;
-  uint32_t flags;      // bit0 exclusive, bit1 has gres request, bits 8-15 requested gres names
-  uint32_t pad0;
+  uint32_t flags;      // bit0 exclusive, bit1 has gres request, bit2 general task distribution, bits 8-15 requested gres names
+  uint32_t ntpn_max;   // ntasks_per_node_max
   uint64_t spec8;      // per-entry typed counts, one byte each (clamped to 127)
   uint8_t name_need[CRANE_GRES_NAMES];  // per name max(total, sum typed), clamped to 255
-  uint64_t pad1;
+  uint32_t ntasks;     // total task count of the job
+  uint32_t pad1;
 };
 static_assert(sizeof(JobQ) == 112, "JobQ layout");
 
@@ -502,8 +505,12 @@ __global__ void k_build_jobq(PendingDev pd, const uint32_t* queue, const uint32_
   q.alloc_off = pd.alloc_off[j];
   q.ntasks_per_node = t;
   q.flags = (pd.exclusive[j] ? 1u : 0u) | (view_has_gres(q.req) ? 2u : 0u);
-  q.pad0 = 0;
+  q.ntpn_max = pd.ntasks_per_node_max[j];
+  q.ntasks = pd.ntasks[j];
   q.pad1 = 0;
+  // anything but "exactly ntasks_per_node tasks on each of node_num nodes" takes the general
+  // task distribution (JobScheduler.cpp:5193-5222, 5340-5361)
+  if (q.ntpn_max != t || (uint64_t)t * q.node_num != q.ntasks) q.flags |= 4u;
   q.spec8 = 0;
   for (uint32_t g = 0; g < CRANE_GRES_NAMES; ++g) {
     uint32_t typed = 0;
@@ -524,19 +531,19 @@ __global__ void k_build_jobq(PendingDev pd, const uint32_t* queue, const uint32_
 // K-init: per node slot, NodeState + timeline + initial cost
 // (JobScheduler.cpp:5715-5753, JobScheduler.h:295-332, 492-505)
 // ------------------------------------------------------------------------
-__global__ void k_node_init(ClusterDev cl, RunningDev rn, TimelineDev tl, int64_t now, uint32_t max_jobs) {
+__global__ void k_node_init(ClusterDev cl, RunningDev rn, TimelineDev tl, int64_t now, uint32_t max_jobs, uint32_t cost_policy) {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= cl.n_slots) return;
   const Row total = cl.slot_total[g];
   Row avail = total;
-  double cost = 0.0;
+  double cost = cost_policy == 1 ? __ll2double_rn(total.cpu_raw) : 0.0;  // NodeRater's seed (BestFit: the node's cpu count)
   uint32_t lo = rn.n ? rn.slot_off[g] : 0, hi = rn.n ? rn.slot_off[g + 1] : 0;
   for (uint32_t k = lo; k < hi; ++k) {  // allocated_res in input order
     int64_t end = rn.slot_end[k];
     if (end < now + 1) end = now + 1;   // JobScheduler.cpp:5547-5548
     const Row res = rn.slot_res[k];
     row_sub(avail, res);
-    cost = __dadd_rn(cost, cost_delta(end - now, res.cpu_raw, total.cpu_raw));
+    cost = __dadd_rn(cost, cost_step(cost_policy, end - now, res.cpu_raw, total.cpu_raw));
   }
   tl.avail0[g] = avail;
   tl.cost0[g] = cost;

@@ -239,7 +239,7 @@ def config4(n_jobs=500_000, n_nodes=20_000, seed_id=4):
                     NOW - rng.integers(0, 7 * DAY + 1, n_jobs), node_num, node_num, views,
                     np.full(n_jobs, 1000, np.uint32),
                     rng.choice([1000, 2000, 5000], n_jobs).astype(np.uint32))
-    cfg = Config(priority_type=1, scheduled_batch_size=n_jobs, **CONFIG2_WEIGHTS)
+    cfg = Config(priority_type=1, scheduled_batch_size=n_jobs, cost_policy=1, **CONFIG2_WEIGHTS)  # best-fit selection
     return cfg, cluster, Running.empty(), pend, NOW
 
 
@@ -267,7 +267,7 @@ def config5(n_jobs=200_000, n_nodes=5_000, seed_id=5):
 # ---------------------------------------------------------------------------
 def random_case(seed, n_jobs=300, n_nodes=48, n_parts=3, n_running=40, fifo=False,
                 frac_cpu=True, lists=True, exclusive=True, limit=None,
-                max_jobs_per_node=1000, short=False, one_type_per_name=False, ntpn_range=False):
+                max_jobs_per_node=1000, short=False, one_type_per_name=False, ntpn_range=False, cost_policy=0):
     """one_type_per_name: no node carries two types of the same gres name, so the
     reference's unordered_map walk over a node's types (PublicHeader.cpp:564,583)
     has a single possible order — the cases oracle/_ref can pin (tests/test_ref_pin.py)."""
@@ -419,7 +419,7 @@ def random_case(seed, n_jobs=300, n_nodes=48, n_parts=3, n_running=40, fifo=Fals
                     exclusive=excl_flag, ntpn=(tpn, tpn_max), mandated=mand,
                     incl=incl, excl=excl)
     cfg = Config(priority_type=0 if fifo else 1, scheduled_batch_size=limit or n_jobs,
-                 max_jobs_per_node=max_jobs_per_node,
+                 max_jobs_per_node=max_jobs_per_node, cost_policy=cost_policy,
                  weight_age=500, weight_fair_share=10000, weight_job_size=300,
                  weight_partition=1000, weight_qos=1_000_000, favor_small=bool(seed & 1))
     return cfg, cluster, running, pend, NOW

@@ -85,7 +85,10 @@ typedef struct crane_sched_config {
   uint32_t weight_qos;
   uint32_t scheduled_batch_size; /* `limit`, JS.cpp:5770                    */
   uint32_t max_jobs_per_node;    /* kAlgoMaxJobNumPerNode (1000)            */
-  uint32_t cost_policy;          /* 0 = MinCpuTimeRatioFirst (JS.h:40)      */
+  uint32_t cost_policy;          /* IUpdateNodeCostPolicy (JS.h:30-54): 0 = MinCpuTimeRatioFirst
+                                    (the reference's only policy), 1 = BestFit: cost = the node's free
+                                    cpu count over all allocations on it, fullest node first — not in
+                                    the reference; BASELINE config 4 ("best-fit selection")   */
   int64_t max_time_window_s;     /* kAlgoMaxTimeWindow (7 d)                */
 } crane_sched_config_t;
 

@@ -468,6 +468,22 @@ inline void UpdateCostMinCpuTimeRatio(double& cost, int64_t start, int64_t end,
   cost += delta;
 }
 
+// BestFit — NOT in the reference: BASELINE.json config 4 asks for "best-fit
+// selection", defined here through the reference's own hook
+// IUpdateNodeCostPolicy::UpdateCost (JobScheduler.h:30-38): a node's cost is
+// its free cpu count over ALL allocations on it (running jobs and everything
+// placed this tick, whenever it starts), so the fullest node comes first;
+// NodeRater seeds the cost with the node's cpu count. Raw cpu_t values as
+// doubles: integers, exact.
+inline void UpdateCostBestFit(double& cost, const ResInNode& res) {
+  cost -= static_cast<double>(res.cpu_count.raw);
+}
+inline void UpdateCostPolicy(uint32_t policy, double& cost, int64_t start, int64_t end,
+                             const ResInNode& res, const ResInNode& total) {
+  if (policy == 1) UpdateCostBestFit(cost, res);
+  else UpdateCostMinCpuTimeRatio(cost, start, end, res, total);
+}
+
 // ---------------------------------------------------------------------------
 // NodeState (JobScheduler.h:266-454)
 // ---------------------------------------------------------------------------
@@ -540,11 +556,12 @@ struct NodeSelector {
   };
   std::unordered_map<std::string, Rater> info;
   std::set<std::pair<double, NodeState*>> order;  // (cost, pointer==index) D1
+  uint32_t policy{0};                             // crane_sched_config_t::cost_policy
 
   void AddNode(int64_t now, NodeState* ns) {  // JobScheduler.h:492-505,534-544
-    double cost = 0.0;
+    double cost = policy == 1 ? static_cast<double>(ns->res_total.cpu_count.raw) : 0.0;
     for (const auto& a : ns->allocated)
-      UpdateCostMinCpuTimeRatio(cost, now, a.end_time, a.res, ns->res_total);
+      UpdateCostPolicy(policy, cost, now, a.end_time, a.res, ns->res_total);
     Rater& r = info.emplace(ns->craned_id, Rater{ns, cost, {}}).first->second;
     r.pos = order.emplace(r.cost, ns).first;
   }
@@ -552,7 +569,7 @@ struct NodeSelector {
                   const ResInNode& res) {  // JobScheduler.h:520-532
     Rater& r = info.at(id);
     order.erase(r.pos);
-    UpdateCostMinCpuTimeRatio(r.cost, s, e, res, r.node->res_total);
+    UpdateCostPolicy(policy, r.cost, s, e, res, r.node->res_total);
     r.pos = order.emplace(r.cost, r.node).first;
   }
   void Allocate(int64_t s, int64_t e,
@@ -1083,6 +1100,7 @@ extern "C" int crane_oracle_node_select(
     scheds[p] = std::make_unique<LocalScheduler>();
     scheds[p]->max_jobs_per_node = cfg->max_jobs_per_node;
     scheds[p]->max_window = cfg->max_time_window_s;
+    scheds[p]->sel.policy = cfg->cost_policy;
     for (NodeState* ns : part_nodes[p]) scheds[p]->sel.AddNode(now, ns);
   }
 

@@ -15,6 +15,11 @@ CASES = {
     # partitions larger than a batch: selection lists, resolve, re-keying
     "big_partition": lambda: synth.random_case(13, n_jobs=200, n_nodes=80, n_parts=1, n_running=10, short=True),
     "big_partition_cfg2": lambda: synth.config2(n_jobs=240, n_nodes=200),
+    # general task distribution: ntasks_per_node ranges, uneven ntasks (top-K heaps, JobScheduler.cpp:5193-5222)
+    "ntpn_range": lambda: synth.random_case(203, n_jobs=110, n_nodes=24, n_parts=2, n_running=14, ntpn_range=True),
+    # BestFit cost policy: keys move down on allocation
+    "bestfit": lambda: synth.random_case(301, n_jobs=120, n_nodes=26, n_parts=2, n_running=12, cost_policy=1),
+    "config4_tiny": lambda: synth.config4(n_jobs=150, n_nodes=24),
     "random_fifo_cap": lambda: synth.random_case(12, n_jobs=90, n_nodes=10, n_parts=2, n_running=6, fifo=True,
                                                  max_jobs_per_node=12, short=True),
 }

@@ -62,6 +62,30 @@ def test_random_sweep(oracle, gpu_lib, seed):
     check_invariants(case, got)
 
 
+@pytest.mark.parametrize("seed", range(200, 212))
+def test_general_task_distribution(oracle, gpu_lib, seed):
+    """ntasks_per_node_max > min and ntasks anywhere in [node_num*min, node_num*max]
+    (JobScheduler.cpp:5193-5222, 5258-5361): per-node task counts, the top-K heaps
+    with libstdc++'s tie behaviour, hand-out in pop order."""
+    case = synth.random_case(seed, n_jobs=400, n_nodes=60, n_parts=1 + seed % 3, n_running=40, ntpn_range=True,
+                             fifo=bool(seed % 4 == 0))
+    ref, _, _ = oracle.node_select(*case[:4], case[4])
+    got, _ = run_sched(case, gpu_lib)
+    assert_same(ref, got)
+
+
+@pytest.mark.parametrize("seed", range(300, 310))
+def test_bestfit_policy(oracle, gpu_lib, seed):
+    """cost_policy 1 (BestFit, BASELINE config 4): keys move DOWN when a node is
+    allocated, so re-keyed nodes overtake their neighbours in the order."""
+    case = synth.random_case(seed, n_jobs=400, n_nodes=60, n_parts=1 + seed % 3, n_running=40, cost_policy=1,
+                             ntpn_range=bool(seed % 2), fifo=bool(seed % 4 == 0))
+    ref, _, _ = oracle.node_select(*case[:4], case[4])
+    got, _ = run_sched(case, gpu_lib)
+    assert_same(ref, got)
+    check_invariants(case, got)
+
+
 def test_batch_limit(oracle, gpu_lib):
     """ScheduledBatchSize: ranks beyond the limit get "Priority"."""
     case = synth.random_case(50, n_jobs=500, n_nodes=40, n_running=20, limit=137)
