@@ -127,15 +127,13 @@ __device__ __forceinline__ void g_window(const TlEntry* E, uint32_t n, int64_t w
   const uint64_t ones = ~0ull;
   uint64_t c0 = ones, c1 = ones, c2 = ones, c3 = ones, g0 = ones, g1 = ones;
   bool ok = true, more = act;
-  for (uint32_t base = 0; __any_sync(kFullMask, more); base += 2 * kGL) {
-    const uint32_t i0 = base + gl, i1 = i0 + kGL;
-    const bool ld0 = more && i0 < n, ld1 = more && i1 < n;
-    TlEntry e0, e1;
+  for (uint32_t base = 0; __any_sync(kFullMask, more); base += kGL) {
+    const uint32_t i0 = base + gl;
+    const bool ld0 = more && i0 < n;
+    TlEntry e0;
     e0.t = kInf;
-    e1.t = kInf;
     if (ld0) e0 = E[i0];
-    if (ld1) e1 = E[i1];
-    const bool in0 = ld0 && e0.t < w_end, in1 = ld1 && e1.t < w_end;
+    const bool in0 = ld0 && e0.t < w_end;
     if (in0) {
       if (exclusive) ok = ok && row_le(tot, e0.seg);
       else {
@@ -145,16 +143,7 @@ __device__ __forceinline__ void g_window(const TlEntry* E, uint32_t n, int64_t w
         g1 &= e0.seg.g[1];
       }
     }
-    if (in1) {
-      if (exclusive) ok = ok && row_le(tot, e1.seg);
-      else {
-        ok = ok && e1.seg.cpu_raw >= req_cpu && e1.seg.mem >= req_mem;
-        if (!core_empty(e1.seg)) { c0 &= e1.seg.core[0]; c1 &= e1.seg.core[1]; c2 &= e1.seg.core[2]; c3 &= e1.seg.core[3]; }
-        g0 &= e1.seg.g[0];
-        g1 &= e1.seg.g[1];
-      }
-    }
-    const uint32_t gb = g_ballot(in0) & g_ballot(in1);
+    const uint32_t gb = g_ballot(in0);
     if (gb != (1u << kGL) - 1u) more = false;  // entries are time-sorted: the window (or the timeline) ends in this chunk
   }
   w.ok = g_ballot(!ok) == 0;
@@ -1539,12 +1528,9 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
     const uint32_t nslots = s2_bj[nj - 1].need;
     uint32_t ev_q = 0xffffu;      // node the results below belong to
     bool tok = false;
-    Win2 tw;
-    tw.c0 = tw.c1 = tw.c2 = tw.c3 = tw.g0 = tw.g1 = 0; tw.ok = false;
-    Row talloc, ta0, ttot;        // backfill: allocation against res_total (JobScheduler.cpp:5381-5403)
-    row_zero(talloc);
-    row_zero(ta0);
-    row_zero(ttot);
+    Row talloc;                   // the allocation: out of the window minimum (immediate start, JobScheduler.cpp:5340-5361)
+    row_zero(talloc);             // or against res_total (backfill, :5381-5403)
+    bool tshort = false;          // backfill label: the allocation does not fit res_avail now (JobScheduler.cpp:5842-5848)
     int64_t te0 = kInf;           // backfill: earliest fit >= now
     // the job my slot belongs to (fixed when the batch was formed)
     uint32_t tjob = 0, tmode = 0, tK = 1, tfirst = 0, tstate = 2;
@@ -1656,26 +1642,30 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
         const uint32_t g = base + (do_eval ? q : 0u);
         const uint32_t ns = do_eval ? sm.nseg[q] : 0u;
         const TlEntry* E = a.tl.ent + (size_t)g * a.tl.cap;
+        Row ea0, etot;
+        row_zero(ea0);
+        row_zero(etot);
         if (do_eval) {
           ev_q = q;
-          ta0 = a.tl.avail0[g];
-          if (texcl || tmode) ttot = node_total2(q);
+          ea0 = a.tl.avail0[g];
+          if (texcl || tmode) etot = node_total2(q);
         }
         Win2 w;
-        g_window(E, ns, now + tlimit, tjq->req.cpu_raw, tjq->req.mem, texcl, (tjq->flags & 2u) != 0, ttot, do_eval && !tmode, w);
+        g_window(E, ns, now + tlimit, tjq->req.cpu_raw, tjq->req.mem, texcl, (tjq->flags & 2u) != 0, etot, do_eval && !tmode, w);
         if (do_eval && !tmode) {
-          tw = w;
           tok = w.ok;
-          if (tok && !texcl) {
-            tok = ta0.cpu_raw >= tjq->req.cpu_raw && ta0.mem >= tjq->req.mem;  // res_avail itself (JobScheduler.cpp:5310)
+          if (texcl) talloc = etot;
+          else if (tok) {
+            tok = ea0.cpu_raw >= tjq->req.cpu_raw && ea0.mem >= tjq->req.mem;  // res_avail itself (JobScheduler.cpp:5310)
             if (tok) {
               Row wr;
-              win_row(w, ta0, tjq->req, wr);
-              tok = feasible<false>(tjq->req, wr, C_DICT2, nullptr);
+              win_row(w, ea0, tjq->req, wr);
+              tok = feasible<true>(tjq->req, wr, C_DICT2, &talloc);
             }
           }
         } else if (do_eval) {
-          if (texcl) talloc = ttot; else feasible<true>(tjq->req, ttot, C_DICT2, &talloc);
+          if (texcl) talloc = etot; else feasible<true>(tjq->req, etot, C_DICT2, &talloc);
+          tshort = !row_le(talloc, ea0);
         }
         const int64_t e = g_earliest(E, ns, talloc, now, tlimit, do_eval && tmode);
         if (do_eval && tmode) te0 = e;
@@ -1751,14 +1741,6 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
       const bool cact = tact && myslot < cut;
       int64_t start = now;
       if (cact && tmode) start = s2_T0[tjob];
-      if (cact && !tmode) {
-        if (texcl) talloc = ttot;
-        else {
-          Row wr;
-          win_row(tw, ta0, tjq->req, wr);
-          feasible<true>(tjq->req, wr, C_DICT2, &talloc);
-        }
-      }
       Row seg0;
       row_zero(seg0);
       const uint32_t nn = g_update(tE, tns, start, start + tlimit, talloc, cact, seg0);
@@ -1769,7 +1751,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
       for (int o = 1; o < kGL; o <<= 1) rank += __shfl_xor_sync(kFullMask, rank, o);
       if (cact && gl == 0) {
         write_node2(*tjq, tq, rank, talloc, nn, seg0);
-        if (start != now && !row_le(talloc, ta0)) atomicOr(&s2_joblabel[tjob], 1u);  // JobScheduler.cpp:5842-5848
+        if (start != now && tshort) atomicOr(&s2_joblabel[tjob], 1u);  // JobScheduler.cpp:5842-5848
       }
     }
     if (overlap) {
