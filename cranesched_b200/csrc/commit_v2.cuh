@@ -1537,9 +1537,11 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
     const JobQ* tjq = &s2_jobs[0];
     if (myslot < nslots) {
       tjob = s2_tjob[myslot];
-      const BJob2 b = s2_bj[tjob];
-      tjq = &s2_jobs[b.slot];
-      tmode = b.mode; tK = b.K; tfirst = b.tfirst; tstate = b.state;
+      // (s2_bj[].state is rewritten by the resolve below: everything here comes from
+      // words nobody writes during this phase)
+      const uint32_t jw = s2_jw[tjob];
+      tjq = &s2_jobs[s2_bj[tjob].slot];
+      tK = jw & 0xffu; tfirst = (jw >> 8) & 0xffu; tmode = (jw >> 16) & 1u; tstate = (jw >> 17) & 3u;
     }
     const bool texcl = tjq->flags & 1u;
     const int64_t tlimit = tjq->time_limit;
@@ -1619,6 +1621,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
             t.q = tv; t.job = tv != 0xffffu ? tslot : 0xffffffffu; t.nc = tnc;
             s2_task[lane] = t;
           }
+          __syncwarp();
           if (tv != 0xffffu) sm.scratch[tv] = 0;  // the marks go back to zero
           if (lane == 0) { s2_njr = njr_l; s2_cut = NTl; }
         } else if (CRANE_SPEC_EVAL && myslot < nslots && tstate == 0) {
