@@ -141,6 +141,7 @@ class RunningC(C.Structure):
         ("alloc_off", _p),
         ("alloc_node", _p),
         ("alloc_res", _p),
+        ("reservation", _p),
     ]
 
 
@@ -168,6 +169,7 @@ class PendingC(C.Structure):
         ("incl_nodes", _p),
         ("excl_off", _p),
         ("excl_nodes", _p),
+        ("reservation", _p),
     ]
 
 
@@ -308,6 +310,7 @@ class Running:
     alloc_off: np.ndarray
     alloc_node: np.ndarray
     alloc_res: np.ndarray
+    reservation: np.ndarray | None = None  # index into Reservations, 0xFFFFFFFF = none
 
     @staticmethod
     def empty() -> "Running":
@@ -329,6 +332,8 @@ class Running:
         self.alloc_off = _arr(self.alloc_off, np.uint32, n + 1)
         self.alloc_node = _arr(self.alloc_node, np.uint32)
         self.alloc_res = _arr(self.alloc_res, RES_IN_NODE)
+        if self.reservation is not None:
+            self.reservation = _arr(self.reservation, np.uint32, n)
 
     @property
     def n(self):
@@ -339,7 +344,7 @@ class Running:
             self.n, _ptr(self.start_time), _ptr(self.end_time), _ptr(self.node_num),
             _ptr(self.partition_priority), _ptr(self.qos_priority), _ptr(self.account),
             _ptr(self.view_cpu_raw), _ptr(self.view_mem), _ptr(self.alloc_off),
-            _ptr(self.alloc_node), _ptr(self.alloc_res),
+            _ptr(self.alloc_node), _ptr(self.alloc_res), _ptr(self.reservation),
         )
 
 
@@ -366,6 +371,7 @@ class Pending:
     incl_nodes: np.ndarray | None = None
     excl_off: np.ndarray | None = None
     excl_nodes: np.ndarray | None = None
+    reservation: np.ndarray | None = None  # index into Reservations, 0xFFFFFFFF = none
 
     def __post_init__(self):
         n = len(self.partition)
@@ -392,6 +398,8 @@ class Pending:
             if off is not None:
                 setattr(self, k + "_off", _arr(off, np.uint32, n + 1))
                 setattr(self, k + "_nodes", _arr(getattr(self, k + "_nodes"), np.uint32))
+        if self.reservation is not None:
+            self.reservation = _arr(self.reservation, np.uint32, n)
 
     @property
     def n(self):
@@ -406,7 +414,7 @@ class Pending:
             _ptr(self.qos), _ptr(self.user), _ptr(self.mandated_priority),
             _ptr(self.req_node), _ptr(self.req_task), _ptr(self.req_total),
             _ptr(self.incl_off), _ptr(self.incl_nodes), _ptr(self.excl_off),
-            _ptr(self.excl_nodes),
+            _ptr(self.excl_nodes), _ptr(self.reservation),
         )
 
 
@@ -556,3 +564,35 @@ class DevicePlacementsC(C.Structure):
     _fields_ = [("reason", C.c_void_p), ("start_time", C.c_void_p), ("end_time", C.c_void_p), ("n_alloc", C.c_void_p),
                 ("alloc_node", C.c_void_p), ("alloc_ntasks", C.c_void_p), ("alloc_res", C.c_void_p),
                 ("n_jobs", C.c_uint64), ("n_rows", C.c_uint64)]
+
+
+class ReservationsC(C.Structure):
+    """crane_reservations_t"""
+    _fields_ = [("n", C.c_uint32), ("start_time", C.c_void_p), ("end_time", C.c_void_p), ("node_off", C.c_void_p),
+                ("node", C.c_void_p), ("res", C.c_void_p)]
+
+
+@dataclass
+class Reservations:
+    """ResvMeta table (Node/NodeDefs.h:81-97): start, end, (node, reserved resources) pairs."""
+    start_time: np.ndarray
+    end_time: np.ndarray
+    node_off: np.ndarray
+    node: np.ndarray
+    res: np.ndarray
+
+    def __post_init__(self):
+        n = len(self.start_time)
+        self.start_time = _arr(self.start_time, np.int64, n)
+        self.end_time = _arr(self.end_time, np.int64, n)
+        self.node_off = _arr(self.node_off, np.uint32, n + 1)
+        self.node = _arr(self.node, np.uint32)
+        self.res = _arr(self.res, RES_IN_NODE)
+
+    @property
+    def n(self):
+        return len(self.start_time)
+
+    def as_c(self) -> ReservationsC:
+        return ReservationsC(self.n, _ptr(self.start_time), _ptr(self.end_time), _ptr(self.node_off),
+                             _ptr(self.node), _ptr(self.res))

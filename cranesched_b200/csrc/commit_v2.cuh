@@ -348,7 +348,7 @@ struct Ctx2 {           // per-CTA constants
   TimelineDev tl;
   PlaceDev out;
   int64_t now, max_window;
-  uint32_t base, mp, words, max_jobs, ring, gres, dslot, cost_policy;
+  uint32_t base, mp, words, max_jobs, ring, gres, dslot, cost_policy, part;
   const View* req_node;
   const View* req_task;
 };
@@ -722,6 +722,18 @@ __device__ __forceinline__ void rekey_bounds2(uint32_t cnt) {
 }
 
 
+// pending-reason label of a job that starts later (JobScheduler.cpp:5829-5865): bit 1 = a node
+// of a partition whose first reservation starts inside the job's window ("Resource Reserved"),
+// bit 0 = the allocation does not fit the node's res_avail now ("Resource"); none: "Priority"
+__device__ __forceinline__ uint32_t later_label2(uint32_t q, bool short_now, int64_t limit) {
+  uint32_t l = short_now ? 1u : 0u;
+  if (s2_cx.part < s2_cx.cl.n_parts && s2_cx.tl.first_resv[s2_cx.base + q] < s2_cx.now + limit) l |= 2u;
+  return l;
+}
+__device__ __forceinline__ uint8_t later_reason2(uint32_t label) {
+  return (label & 2u) ? CRANE_REASON_RESERVED : ((label & 1u) ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY);
+}
+
 // n-th (1-based) set bit of m, 32 if there is none
 __device__ __forceinline__ uint32_t nth_set_bit(uint32_t m, uint32_t n) {
   if ((uint32_t)__popc(m) < n || n == 0) return 32u;
@@ -960,7 +972,7 @@ __device__ __noinline__ void single2(uint32_t ji) {
         if (act && gl == 0) {
           write_node2(jq, q, rank, alloc, nn, seg0);
           // pending-reason label for future starts (JobScheduler.cpp:5842-5848)
-          if (T0 != now && !row_le(alloc, a0)) atomicOr(&s2_label, 1u);
+          if (T0 != now) atomicOr(&s2_label, later_label2(q, !row_le(alloc, a0), limit));
         }
       }
     }
@@ -972,7 +984,7 @@ __device__ __noinline__ void single2(uint32_t ji) {
       s2_cx.out.end_time[jq.job] = start_time + limit;
       s2_cx.out.n_alloc[jq.job] = K;
       uint8_t reason = CRANE_REASON_NONE;
-      if (start_time != now) reason = s2_label ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY;
+      if (start_time != now) reason = later_reason2(s2_label);
       s2_cx.out.reason[jq.job] = reason;
     }
     // cost += (end-start) * cpu ratio (JobScheduler.h:46-52)
@@ -1336,7 +1348,7 @@ __device__ __noinline__ void single2_general(uint32_t ji) {
         if (act && gl == 0) {
           write_node2(jq, q, rank, alloc, nn, seg0);
           s2_cx.out.alloc_ntasks[jq.alloc_off + rank] = s2_g_n[k];
-          if (T0 != now && !row_le(alloc, a0)) atomicOr(&s2_label, 1u);
+          if (T0 != now) atomicOr(&s2_label, later_label2(q, !row_le(alloc, a0), limit));
         }
       }
     }
@@ -1348,7 +1360,7 @@ __device__ __noinline__ void single2_general(uint32_t ji) {
       s2_cx.out.end_time[jq.job] = start_time + limit;
       s2_cx.out.n_alloc[jq.job] = K;
       uint8_t reason = CRANE_REASON_NONE;
-      if (start_time != now) reason = s2_label ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY;
+      if (start_time != now) reason = later_reason2(s2_label);
       s2_cx.out.reason[jq.job] = reason;
     }
     // the node's cost grows by its own allocation's cpu share (JobScheduler.h:46-52)
@@ -1401,7 +1413,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
   if (tid == 0) {
     s2_cx.cl = a.cl; s2_cx.tl = a.tl; s2_cx.out = a.out;
     s2_cx.now = a.now; s2_cx.max_window = a.max_window; s2_cx.base = base; s2_cx.mp = mp; s2_cx.words = words;
-    s2_cx.max_jobs = a.max_jobs; s2_cx.ring = ring; s2_cx.gres = a.gres; s2_cx.dslot = a.dslot; s2_cx.cost_policy = a.cost_policy; s2_cx.req_node = a.req_node; s2_cx.req_task = a.req_task;
+    s2_cx.max_jobs = a.max_jobs; s2_cx.ring = ring; s2_cx.gres = a.gres; s2_cx.dslot = a.dslot; s2_cx.cost_policy = a.cost_policy; s2_cx.part = part; s2_cx.req_node = a.req_node; s2_cx.req_task = a.req_task;
     s2_prof_windows = 0; s2_prof_tests = 0; s2_prof_singles = 0;
     for (uint32_t s = 0; s < ring; ++s) mbar_init(&s2_bar[s], 1);
     fence_mbar_init();
@@ -1754,7 +1766,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
       for (int o = 1; o < kGL; o <<= 1) rank += __shfl_xor_sync(kFullMask, rank, o);
       if (cact && gl == 0) {
         write_node2(*tjq, tq, rank, talloc, nn, seg0);
-        if (start != now && tshort) atomicOr(&s2_joblabel[tjob], 1u);  // JobScheduler.cpp:5842-5848
+        if (start != now) atomicOr(&s2_joblabel[tjob], later_label2(tq, tshort, tlimit));
       }
     }
     if (overlap) {
@@ -1781,7 +1793,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
         a.out.start_time[jq.job] = st;
         a.out.end_time[jq.job] = st + jq.time_limit;
         a.out.n_alloc[jq.job] = b.K;
-        a.out.reason[jq.job] = st == now ? CRANE_REASON_NONE : (s2_joblabel[tid] ? CRANE_REASON_RESOURCE : CRANE_REASON_PRIORITY);
+        a.out.reason[jq.job] = st == now ? CRANE_REASON_NONE : later_reason2(s2_joblabel[tid]);
       }
     }
     if (fjob != 0xffffffffu) {

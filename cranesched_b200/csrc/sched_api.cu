@@ -70,6 +70,14 @@ struct crane_sched {
   // cluster (host copies)
   bool have_cluster = false;
   uint32_t n_nodes = 0, n_parts = 0, n_slots = 0, max_part_slots = 0, words_per_row = 0;
+  uint32_t n_vparts = 0, n_resv = 0;  // schedulers = partitions + reservations
+  // host copies of the cluster and reservation tables (the slot layout is rebuilt when either changes)
+  std::vector<Row> c_res_total, r_res;
+  std::vector<uint8_t> c_alive, c_drain;
+  std::vector<uint32_t> c_part_off, c_part_nodes, r_node_off, r_node;
+  std::vector<int64_t> r_start, r_end;
+  std::vector<uint32_t> h_vslot_off, h_vslot_node;  // per reservation: its nodes (ascending) -> slots h_part_base[n_parts + r] + k
+  uint32_t n_gres_entries = 0;
   std::vector<uint32_t> h_part_base, h_slot_node, h_node_slot;
   GresDict dict{};
   uint32_t tl_cap = 0;
@@ -84,6 +92,10 @@ struct crane_sched {
   DBuf<uint8_t> d_slot_class;
   DBuf<double> d_cost0;
   DBuf<uint8_t> d_skip;
+  DBuf<int64_t> d_first_resv, d_resv_start, d_resv_end;
+  DBuf<uint32_t> d_slot_resv, d_rsv_off, d_rsv_id, d_vpart, d_pd_resv;
+  DBuf<Row> d_rsv_res;
+  bool have_pd_resv = false;
 
   // pending (device)
   uint32_t n_pending = 0, n_running = 0, n_accounts = 0;
@@ -252,13 +264,147 @@ void crane_sched_destroy(crane_sched_t* h) {
   REL(d_vals_b); REL(d_hist); REL(d_part_count); REL(d_part_job_off); REL(d_bitmap); REL(d_jobq); REL(d_reason);
   REL(d_out_prio); REL(d_out_start); REL(d_out_end); REL(d_out_nalloc); REL(d_out_node); REL(d_out_ntasks);
   REL(d_out_res); REL(d_prof); REL(d_qos); REL(d_user); REL(d_q_u32); REL(d_q_chain_off); REL(d_q_chain);
-  REL(d_q_i64); REL(d_q_valid); REL(d_part_owner); REL(d_part_list); REL(d_ntpn_max); REL(d_ntasks); REL(d_q_tres); REL(d_q_user_usage); REL(d_q_acct_usage); REL(d_q_qos_usage);
+  REL(d_q_i64); REL(d_q_valid); REL(d_part_owner); REL(d_part_list); REL(d_ntpn_max); REL(d_ntasks); REL(d_first_resv); REL(d_resv_start); REL(d_resv_end); REL(d_slot_resv);
+  REL(d_rsv_off); REL(d_rsv_id); REL(d_vpart); REL(d_pd_resv); REL(d_rsv_res); REL(d_q_tres); REL(d_q_user_usage); REL(d_q_acct_usage); REL(d_q_qos_usage);
 #undef REL
   for (auto& e : h->ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
   { std::lock_guard<std::mutex> lk(g_slot_mu); g_slots_used[h->device] &= ~(1u << h->dict_slot); }
   delete h;
 }
+
+// Node state a running job's allocation on `node` counts against: the node's own, or —
+// for a job inside a reservation — the reservation's state of that node
+// (JobScheduler.cpp:5715-5741)
+static uint32_t running_slot(const crane_sched* h, const crane_running_t* rn, uint32_t j, uint32_t node) {
+  const uint32_t rv = rn->reservation ? rn->reservation[j] : 0xffffffffu;
+  if (rv == 0xffffffffu) return h->h_node_slot[node];
+  if (rv >= h->n_resv) return 0xffffffffu;  // the reference logs an error and skips the job
+  const uint32_t lo = h->r_node_off[rv], hi = h->r_node_off[rv + 1];
+  const auto it = std::lower_bound(h->r_node.begin() + lo, h->r_node.begin() + hi, node);
+  if (it == h->r_node.begin() + hi || *it != node) return 0xffffffffu;
+  return h->h_part_base[h->n_parts + rv] + (uint32_t)(it - (h->r_node.begin() + lo));
+}
+
+// Slot layout of the node states: the usable nodes of every partition (contiguous per
+// partition), then the nodes of every reservation; device copies of the cluster tables.
+static int build_layout(crane_sched* h) {
+  h->h_node_slot.assign(h->n_nodes, 0xffffffffu);
+  h->h_part_base.assign(h->n_parts + 1, 0);
+  h->h_part_base.reserve(h->n_parts + h->n_resv + 1);
+  h->h_slot_node.clear();
+  std::vector<uint8_t> seen(h->n_nodes, 0);
+  std::vector<Row> slot_total;
+  uint32_t max_mp = 0;
+  for (uint32_t p = 0; p < h->n_parts; ++p) {
+    h->h_part_base[p] = (uint32_t)h->h_slot_node.size();
+    uint32_t prev = 0;
+    for (uint32_t k = h->c_part_off[p]; k < h->c_part_off[p + 1]; ++k) {
+      uint32_t n = h->c_part_nodes[k];
+      if (n >= h->n_nodes) return fail(h, CRANE_EINVAL, "cluster: node index %u out of range", n);
+      if (k > h->c_part_off[p] && n <= prev) return fail(h, CRANE_EINVAL, "cluster: partition %u node list must be ascending", p);
+      prev = n;
+      // a node shared by two partitions couples their timelines (shared
+      // NodeState, JobScheduler.cpp:5622); that is SURVEY.md §8f rank 3.
+      if (seen[n]) return fail(h, CRANE_ENOSYS, "cluster: node %u is in more than one partition (overlapping partitions are not built yet)", n);
+      seen[n] = 1;
+      if (!h->c_alive[n] || h->c_drain[n]) continue;  // JobScheduler.cpp:5629
+      const Row& t = h->c_res_total[n];
+      if (t.cpu_raw < 0 || t.cpu_raw > (int64_t)1 << 40) return fail(h, CRANE_EINVAL, "cluster: node %u cpu out of range", n);
+      for (uint32_t e = h->n_gres_entries; e < CRANE_GRES_ENTRIES; ++e)
+        if (field16(t.g, e)) return fail(h, CRANE_EINVAL, "cluster: node %u has slots for an undeclared gres entry", n);
+      h->h_node_slot[n] = (uint32_t)h->h_slot_node.size();
+      h->h_slot_node.push_back(n);
+      slot_total.push_back(t);
+    }
+    uint32_t mp = (uint32_t)h->h_slot_node.size() - h->h_part_base[p];
+    max_mp = std::max(max_mp, mp);
+  }
+  h->h_part_base[h->n_parts] = (uint32_t)h->h_slot_node.size();
+  const uint32_t n_phys = (uint32_t)h->h_slot_node.size();
+  // one more scheduler per reservation: node states holding exactly the reserved
+  // resources (JobScheduler.cpp:5689-5703), whatever the node's own state
+  h->n_vparts = h->n_parts + h->n_resv;
+  std::vector<uint32_t> slot_resv(n_phys, 0xffffffffu);
+  for (uint32_t r = 0; r < h->n_resv; ++r) {
+    for (uint32_t k = h->r_node_off[r]; k < h->r_node_off[r + 1]; ++k) {
+      h->h_slot_node.push_back(h->r_node[k]);
+      slot_total.push_back(h->r_res[k]);
+      slot_resv.push_back(r);
+    }
+    h->h_part_base.push_back((uint32_t)h->h_slot_node.size());
+    max_mp = std::max(max_mp, h->r_node_off[r + 1] - h->r_node_off[r]);
+  }
+  // reservations holding resources of a partition's node, ascending reservation id
+  std::vector<uint32_t> rsv_off((size_t)h->h_slot_node.size() + 1, 0), rsv_id;
+  std::vector<Row> rsv_res;
+  {
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> per(n_phys);
+    for (uint32_t r = 0; r < h->n_resv; ++r)
+      for (uint32_t k = h->r_node_off[r]; k < h->r_node_off[r + 1]; ++k) {
+        const uint32_t g = h->h_node_slot[h->r_node[k]];
+        if (g != 0xffffffffu) per[g].push_back({r, k});  // (nodes outside node_state_map are skipped, :5680)
+      }
+    for (uint32_t g = 0; g < n_phys; ++g) {
+      for (auto& e : per[g]) { rsv_id.push_back(e.first); rsv_res.push_back(h->r_res[e.second]); }
+      rsv_off[g + 1] = (uint32_t)rsv_id.size();
+    }
+    for (size_t g = n_phys; g < h->h_slot_node.size(); ++g) rsv_off[g + 1] = (uint32_t)rsv_id.size();
+  }
+  h->n_slots = (uint32_t)h->h_slot_node.size();
+  h->max_part_slots = max_mp;
+  h->words_per_row = std::max<uint32_t>(4, ((max_mp + 31) / 32 + 3) / 4 * 4);  // 16-byte rows for the bulk copies
+  h->v2_ring = commit2_ring_slots(max_mp, h->words_per_row, h->n_gres_entries > 0, h->v2_budget);
+  if (max_mp > 65000 || h->v2_ring == 0)
+    return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
+  // res_total classes per partition (distinct rows), cached in shared memory by the commit kernel
+  std::vector<uint8_t> slot_class(std::max<size_t>(slot_total.size(), 1), 0xff);
+  std::vector<Row> class_rows((size_t)std::max<uint32_t>(h->n_vparts, 1) * kMaxClasses);
+  memset(class_rows.data(), 0, class_rows.size() * sizeof(Row));
+  for (uint32_t p = 0; p < h->n_vparts; ++p) {
+    uint32_t ncls = 0;
+    for (uint32_t g = h->h_part_base[p]; g < h->h_part_base[p + 1]; ++g) {
+      uint32_t k = 0;
+      for (; k < ncls; ++k)
+        if (memcmp(&class_rows[(size_t)p * kMaxClasses + k], &slot_total[g], sizeof(Row)) == 0) break;
+      if (k == ncls) {
+        if (ncls == (uint32_t)kMaxClasses) continue;  // no class: the kernel reads slot_total
+        class_rows[(size_t)p * kMaxClasses + ncls++] = slot_total[g];
+      }
+      slot_class[g] = (uint8_t)k;
+    }
+  }
+
+  H2D(h->d_part_base, h->h_part_base.data(), h->h_part_base.size());
+  H2D(h->d_slot_node, h->h_slot_node.data(), h->h_slot_node.size());
+  H2D(h->d_node_slot, h->h_node_slot.data(), h->h_node_slot.size());
+  H2D(h->d_slot_total, slot_total.data(), slot_total.size());
+  H2D(h->d_slot_class, slot_class.data(), slot_class.size());
+  H2D(h->d_class_rows, class_rows.data(), class_rows.size());
+  H2D(h->d_slot_resv, slot_resv.data(), slot_resv.size());
+  H2D(h->d_rsv_off, rsv_off.data(), rsv_off.size());
+  H2D(h->d_rsv_id, rsv_id.data(), rsv_id.size());
+  H2D(h->d_rsv_res, rsv_res.data(), rsv_res.size());
+  H2D(h->d_resv_start, h->r_start.data(), h->r_start.size());
+  H2D(h->d_resv_end, h->r_end.data(), h->r_end.size());
+  CU(cudaMemcpyToSymbolAsync(c_dicts, &h->dict, sizeof(GresDict), (size_t)h->dict_slot * sizeof(GresDict), cudaMemcpyHostToDevice, h->stream));
+  size_t ns = std::max<uint32_t>(h->n_slots, 1);
+  CU(h->d_tl_n.ensure(ns));
+  CU(h->d_tl_ent.ensure(ns * h->tl_cap));
+  CU(h->d_avail0.ensure(ns));
+  CU(h->d_cost0.ensure(ns));
+  CU(h->d_skip.ensure(ns));
+  CU(h->d_first_resv.ensure(ns));
+  CU(h->d_part_count.ensure(h->n_vparts + 2));
+  CU(h->d_part_job_off.ensure(h->n_vparts + 2));
+  CU(cudaStreamSynchronize(h->stream));
+  h->have_cluster = true;
+  h->uploaded = false;
+  h->shard_rank = 0;
+  h->shard_n = 1;  // a new cluster: the partition -> rank table has to be set again
+  return CRANE_OK;
+}
+
 
 int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
   if (!h || !c) return CRANE_EINVAL;
@@ -288,82 +434,55 @@ int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* c) {
     h->dict.name_count[g]++;
     h->dict.name_mask8[g] |= 0xFFull << (8 * e);
   }
-  h->h_node_slot.assign(c->n_nodes, 0xffffffffu);
-  h->h_part_base.assign(c->n_partitions + 1, 0);
-  h->h_slot_node.clear();
-  std::vector<uint8_t> seen(c->n_nodes, 0);
-  std::vector<Row> slot_total;
-  uint32_t max_mp = 0;
-  for (uint32_t p = 0; p < c->n_partitions; ++p) {
-    h->h_part_base[p] = (uint32_t)h->h_slot_node.size();
-    uint32_t prev = 0;
-    for (uint32_t k = c->part_off[p]; k < c->part_off[p + 1]; ++k) {
-      uint32_t n = c->part_nodes[k];
-      if (n >= c->n_nodes) return fail(h, CRANE_EINVAL, "cluster: node index %u out of range", n);
-      if (k > c->part_off[p] && n <= prev) return fail(h, CRANE_EINVAL, "cluster: partition %u node list must be ascending", p);
-      prev = n;
-      // a node shared by two partitions couples their timelines (shared
-      // NodeState, JobScheduler.cpp:5622); that is SURVEY.md §8f rank 3.
-      if (seen[n]) return fail(h, CRANE_ENOSYS, "cluster: node %u is in more than one partition (overlapping partitions are not built yet)", n);
-      seen[n] = 1;
-      if (!c->alive[n] || c->drain[n]) continue;  // JobScheduler.cpp:5629
-      const Row& t = reinterpret_cast<const Row&>(c->res_total[n]);
-      if (t.cpu_raw < 0 || t.cpu_raw > (int64_t)1 << 40) return fail(h, CRANE_EINVAL, "cluster: node %u cpu out of range", n);
-      for (uint32_t e = c->n_gres_entries; e < CRANE_GRES_ENTRIES; ++e)
-        if (field16(t.g, e)) return fail(h, CRANE_EINVAL, "cluster: node %u has slots for an undeclared gres entry", n);
-      h->h_node_slot[n] = (uint32_t)h->h_slot_node.size();
-      h->h_slot_node.push_back(n);
-      slot_total.push_back(t);
-    }
-    uint32_t mp = (uint32_t)h->h_slot_node.size() - h->h_part_base[p];
-    max_mp = std::max(max_mp, mp);
-  }
-  h->h_part_base[c->n_partitions] = (uint32_t)h->h_slot_node.size();
-  h->n_slots = (uint32_t)h->h_slot_node.size();
-  h->max_part_slots = max_mp;
-  h->words_per_row = std::max<uint32_t>(4, ((max_mp + 31) / 32 + 3) / 4 * 4);  // 16-byte rows for the bulk copies
-  h->v2_ring = commit2_ring_slots(max_mp, h->words_per_row, c->n_gres_entries > 0, h->v2_budget);
-  if (max_mp > 65000 || h->v2_ring == 0)
-    return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
-  // res_total classes per partition (distinct rows), cached in shared memory by the commit kernel
-  std::vector<uint8_t> slot_class(std::max<size_t>(slot_total.size(), 1), 0xff);
-  std::vector<Row> class_rows((size_t)std::max<uint32_t>(c->n_partitions, 1) * kMaxClasses);
-  memset(class_rows.data(), 0, class_rows.size() * sizeof(Row));
-  for (uint32_t p = 0; p < c->n_partitions; ++p) {
-    uint32_t ncls = 0;
-    for (uint32_t g = h->h_part_base[p]; g < h->h_part_base[p + 1]; ++g) {
-      uint32_t k = 0;
-      for (; k < ncls; ++k)
-        if (memcmp(&class_rows[(size_t)p * kMaxClasses + k], &slot_total[g], sizeof(Row)) == 0) break;
-      if (k == ncls) {
-        if (ncls == (uint32_t)kMaxClasses) continue;  // no class: the kernel reads slot_total
-        class_rows[(size_t)p * kMaxClasses + ncls++] = slot_total[g];
-      }
-      slot_class[g] = (uint8_t)k;
-    }
-  }
+  h->n_gres_entries = c->n_gres_entries;
+  h->c_res_total.assign(reinterpret_cast<const Row*>(c->res_total), reinterpret_cast<const Row*>(c->res_total) + c->n_nodes);
+  h->c_alive.assign(c->alive, c->alive + c->n_nodes);
+  h->c_drain.assign(c->drain, c->drain + c->n_nodes);
+  h->c_part_off.assign(c->part_off, c->part_off + c->n_partitions + 1);
+  h->c_part_nodes.assign(c->part_nodes, c->part_nodes + (c->n_partitions ? c->part_off[c->n_partitions] : 0));
+  h->r_start.clear(); h->r_end.clear(); h->r_node_off.assign(1, 0); h->r_node.clear(); h->r_res.clear();  // a new cluster has no reservations yet
+  h->n_resv = 0;
+  return build_layout(h);
+}
 
-  H2D(h->d_part_base, h->h_part_base.data(), h->h_part_base.size());
-  H2D(h->d_slot_node, h->h_slot_node.data(), h->h_slot_node.size());
-  H2D(h->d_node_slot, h->h_node_slot.data(), h->h_node_slot.size());
-  H2D(h->d_slot_total, slot_total.data(), slot_total.size());
-  H2D(h->d_slot_class, slot_class.data(), slot_class.size());
-  H2D(h->d_class_rows, class_rows.data(), class_rows.size());
-  CU(cudaMemcpyToSymbolAsync(c_dicts, &h->dict, sizeof(GresDict), (size_t)h->dict_slot * sizeof(GresDict), cudaMemcpyHostToDevice, h->stream));
-  size_t ns = std::max<uint32_t>(h->n_slots, 1);
-  CU(h->d_tl_n.ensure(ns));
-  CU(h->d_tl_ent.ensure(ns * h->tl_cap));
-  CU(h->d_avail0.ensure(ns));
-  CU(h->d_cost0.ensure(ns));
-  CU(h->d_skip.ensure(ns));
-  CU(h->d_part_count.ensure(h->n_parts + 2));
-  CU(h->d_part_job_off.ensure(h->n_parts + 2));
-  CU(cudaStreamSynchronize(h->stream));
-  h->have_cluster = true;
+int crane_sched_set_reservations(crane_sched_t* h, const crane_reservations_t* rv) {
+  if (!h) return CRANE_EINVAL;
+  if (!h->have_cluster) return fail(h, CRANE_EINVAL, "set_reservations: set_cluster first");
+  CU(cudaSetDevice(h->device));
+  const uint32_t n = rv ? rv->n : 0;
+  if (n && (!rv->start_time || !rv->end_time || !rv->node_off)) return fail(h, CRANE_EINVAL, "reservations: null table");
+  if (n && rv->node_off[0] != 0) return fail(h, CRANE_EINVAL, "reservations: node_off[0] != 0");
+  for (uint32_t r = 0; r < n; ++r) {
+    if (rv->node_off[r + 1] < rv->node_off[r]) return fail(h, CRANE_EINVAL, "reservations: node_off is not monotonic");
+    if (rv->end_time[r] < rv->start_time[r]) return fail(h, CRANE_EINVAL, "reservations[%u]: end before start", r);
+    for (uint32_t k = rv->node_off[r]; k < rv->node_off[r + 1]; ++k) {
+      if (!rv->node || !rv->res) return fail(h, CRANE_EINVAL, "reservations: null node table");
+      if (rv->node[k] >= h->n_nodes) return fail(h, CRANE_EINVAL, "reservations[%u]: node out of range", r);
+      for (uint32_t k2 = rv->node_off[r]; k2 < k; ++k2)
+        if (rv->node[k2] == rv->node[k]) return fail(h, CRANE_EINVAL, "reservations[%u]: node %u listed twice", r, rv->node[k]);
+    }
+  }
+  h->have_cluster = false;
   h->uploaded = false;
-  h->shard_rank = 0;
-  h->shard_n = 1;  // a new cluster: the partition -> rank table has to be set again
-  return CRANE_OK;
+  h->ran = false;
+  h->n_resv = n;
+  h->r_start.assign(rv ? rv->start_time : nullptr, rv ? rv->start_time + n : nullptr);
+  h->r_end.assign(rv ? rv->end_time : nullptr, rv ? rv->end_time + n : nullptr);
+  h->r_node_off.assign(1, 0);
+  h->r_node.clear();
+  h->r_res.clear();
+  for (uint32_t r = 0; r < n; ++r) {
+    // node states in node-index order: equal-cost nodes are ordered by index (deviation D1)
+    std::vector<uint32_t> idx(rv->node_off[r + 1] - rv->node_off[r]);
+    for (uint32_t k = 0; k < idx.size(); ++k) idx[k] = rv->node_off[r] + k;
+    std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return rv->node[x] < rv->node[y]; });
+    for (uint32_t k : idx) {
+      h->r_node.push_back(rv->node[k]);
+      h->r_res.push_back(reinterpret_cast<const Row&>(rv->res[k]));
+    }
+    h->r_node_off.push_back((uint32_t)h->r_node.size());
+  }
+  return build_layout(h);
 }
 
 int crane_sched_set_shard(crane_sched_t* h, uint32_t rank, uint32_t n_ranks, const uint32_t* part_owner) {
@@ -382,6 +501,8 @@ int crane_sched_set_shard(crane_sched_t* h, uint32_t rank, uint32_t n_ranks, con
       h->h_part_owner.push_back(part_owner[p]);
       if (part_owner[p] == rank) h->h_part_list.push_back(p);
     }
+    if (rank == 0)
+      for (uint32_t r = 0; r < h->n_resv; ++r) h->h_part_list.push_back(h->n_parts + r);  // reservations: rank 0
     H2D(h->d_part_owner, h->h_part_owner.data(), h->h_part_owner.size());
     H2D(h->d_part_list, h->h_part_list.data(), h->h_part_list.size());
     CU(cudaStreamSynchronize(h->stream));
@@ -477,6 +598,8 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
   H2D(h->d_req_task, reinterpret_cast<const View*>(pd->req_task), N);
   H2D(h->d_req_total, reinterpret_cast<const View*>(pd->req_total), N);
   H2D(h->d_alloc_off, h->h_alloc_off.data(), N + 1);
+  h->have_pd_resv = pd->reservation != nullptr;
+  if (h->have_pd_resv) H2D(h->d_pd_resv, pd->reservation, N);
   h->have_lists_incl = pd->incl_off != nullptr;
   h->have_lists_excl = pd->excl_off != nullptr;
   if (h->have_lists_incl) {
@@ -511,7 +634,7 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
       for (uint32_t k = rn->alloc_off[j]; k < rn->alloc_off[j + 1]; ++k) {
         uint32_t n = rn->alloc_node[k];
         if (n >= h->n_nodes) return fail(h, CRANE_EINVAL, "running[%u]: node out of range", j);
-        uint32_t g = h->h_node_slot[n];
+        uint32_t g = running_slot(h, rn, j, n);
         if (g != 0xffffffffu) slot_off[g + 1]++;  // nodes outside node_state_map are ignored (JS.cpp:5719)
       }
     }
@@ -523,7 +646,7 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
     for (uint32_t j = 0; j < R; ++j) {
       acc_job[fill_a[rn->account[j]]++] = j;
       for (uint32_t k = rn->alloc_off[j]; k < rn->alloc_off[j + 1]; ++k) {
-        uint32_t g = h->h_node_slot[rn->alloc_node[k]];
+        uint32_t g = running_slot(h, rn, j, rn->alloc_node[k]);
         if (g == 0xffffffffu) continue;
         uint32_t dst = fill_s[g]++;
         slot_end[dst] = rn->end_time[j];
@@ -610,6 +733,7 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
   pd.excl_off = h->have_lists_excl ? h->d_excl_off.p : nullptr;
   pd.excl_nodes = h->d_excl_nodes.p;
   pd.alloc_off = h->d_alloc_off.p;
+  pd.reservation = h->have_pd_resv ? h->d_pd_resv.p : nullptr;
 
   RunningDev rn{};
   rn.n = R;
@@ -632,6 +756,14 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
   ClusterDev cl{};
   cl.n_slots = h->n_slots;
   cl.n_parts = h->n_parts;
+  cl.n_vparts = h->n_vparts;
+  cl.n_resv = h->n_resv;
+  cl.resv_start = h->d_resv_start.p;
+  cl.resv_end = h->d_resv_end.p;
+  cl.slot_resv = h->d_slot_resv.p;
+  cl.rsv_off = h->d_rsv_off.p;
+  cl.rsv_id = h->d_rsv_id.p;
+  cl.rsv_res = h->d_rsv_res.p;
   cl.max_part_slots = h->max_part_slots;
   cl.part_base = h->d_part_base.p;
   cl.slot_node = h->d_slot_node.p;
@@ -647,6 +779,7 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
   tl.avail0 = h->d_avail0.p;
   tl.cost0 = h->d_cost0.p;
   tl.skip = h->d_skip.p;
+  tl.first_resv = h->d_first_resv.p;
 
   PlaceDev out{};
   out.reason = h->d_reason.p;
@@ -673,7 +806,8 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
 
   // ---- priority + queue (R5,R6) --------------------------------------------
   uint32_t nq_cap = std::min<uint32_t>(N, h->cfg.scheduled_batch_size);
-  CU(cudaMemsetAsync(h->d_part_count.p, 0, sizeof(uint32_t) * (h->n_parts + 2), st));
+  CU(cudaMemsetAsync(h->d_part_count.p, 0, sizeof(uint32_t) * (h->n_vparts + 2), st));
+  CU(h->d_vpart.ensure(std::max<uint32_t>(N, 1)));
   if (N) {
     PrioCfg pc{};
     pc.type = h->cfg.priority_type;
@@ -713,11 +847,11 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
       order = h->d_vals_a.p;
     }
     CRANE_LAUNCH(k_queue_keys, (N + 255) / 256, 256, 0, st, pd, order, h->d_prio.p, h->cfg.scheduled_batch_size,
-                 h->n_parts, key2, out, h->d_part_count.p);
-    CRANE_LAUNCH(k_part_offsets, 1, 32, 0, st, h->d_part_count.p, h->n_parts, h->d_part_job_off.p);
+                 cl, now, key2, out, h->d_part_count.p, h->d_vpart.p);
+    CRANE_LAUNCH(k_part_offsets, 1, 32, 0, st, h->d_part_count.p, h->n_vparts, h->d_part_job_off.p);
     h->timing.kernel_launches += 2;
     int bits = 8;
-    while ((1ull << bits) < (uint64_t)h->n_parts + 2) bits += 8;
+    while ((1ull << bits) < (uint64_t)h->n_vparts + 2) bits += 8;
     uint64_t* k2s;
     uint32_t* queue;
     int rc = radix_sort(h, N, bits, &k2s, &queue);
@@ -726,39 +860,39 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
     if (nq_cap) {
       // n_queued <= nq_cap lives on the device (part_job_off[n_parts]); the
       // kernels below bound themselves with it.
-      CRANE_LAUNCH(k_build_jobq, (nq_cap + 127) / 128, 128, 0, st, pd, queue, h->d_part_job_off.p + h->n_parts, h->d_jobq.p, (uint32_t)h->dict_slot);
+      CRANE_LAUNCH(k_build_jobq, (nq_cap + 127) / 128, 128, 0, st, pd, queue, h->d_part_job_off.p + h->n_vparts, h->d_jobq.p, (uint32_t)h->dict_slot, h->d_vpart.p);
       h->timing.kernel_launches++;
     }
   } else {
-    CRANE_LAUNCH(k_part_offsets, 1, 32, 0, st, h->d_part_count.p, h->n_parts, h->d_part_job_off.p);
+    CRANE_LAUNCH(k_part_offsets, 1, 32, 0, st, h->d_part_count.p, h->n_vparts, h->d_part_job_off.p);
     h->timing.kernel_launches++;
   }
   CU(cudaEventRecord(h->ev[4], st));
 
   // ---- capability bitmap (R7 predicate + R8) -------------------------------
-  if (nq_cap && h->n_parts) {
+  if (nq_cap && h->n_vparts) {
     uint32_t wpb = 8;
     uint32_t nb = std::min<uint32_t>((nq_cap + wpb - 1) / wpb, 148 * 8);
-    CRANE_LAUNCH(k_feas_bitmap, nb, wpb * 32, 0, st, cl, pd, h->d_jobq.p, h->d_part_job_off.p + h->n_parts, h->words_per_row, h->d_bitmap.p,
+    CRANE_LAUNCH(k_feas_bitmap, nb, wpb * 32, 0, st, cl, pd, h->d_jobq.p, h->d_part_job_off.p + h->n_vparts, h->words_per_row, h->d_bitmap.p,
                  h->shard_n > 1 ? h->d_part_owner.p : nullptr, h->shard_rank, (uint32_t)h->dict_slot);
     h->timing.kernel_launches++;
   }
   CU(cudaEventRecord(h->ev[5], st));
 
   // ---- sequential commit (R7,R9,R10,R11) -----------------------------------
-  if (nq_cap && h->n_parts) {
+  if (nq_cap && h->n_vparts) {
     Commit2Args c2{};
     c2.cl = cl; c2.tl = tl; c2.jobq = h->d_jobq.p; c2.part_job_off = h->d_part_job_off.p; c2.bitmap = h->d_bitmap.p;
     c2.words_per_row = h->words_per_row; c2.ring = h->v2_ring; c2.out = out; c2.now = now;
     c2.max_window = h->cfg.max_time_window_s; c2.max_jobs = h->cfg.max_jobs_per_node; c2.cost_policy = h->cfg.cost_policy;
-    CU(h->d_prof.ensure((size_t)h->n_parts * 16));
+    CU(h->d_prof.ensure((size_t)h->n_vparts * 16));
     c2.prof = h->d_prof.p;
     c2.gres = h->dict.n_entries > 0 ? 1u : 0u;
     c2.dslot = (uint32_t)h->dict_slot;
     c2.req_node = h->d_req_node.p;
     c2.req_task = h->d_req_task.p;
     size_t smem = commit2_smem_bytes(h->max_part_slots, h->words_per_row, c2.gres != 0, h->v2_ring);
-    uint32_t grid = h->n_parts;
+    uint32_t grid = h->n_vparts;
     if (h->shard_n > 1) {
       c2.part_list = h->d_part_list.p;
       grid = (uint32_t)h->h_part_list.size();
@@ -845,7 +979,7 @@ int crane_sched_sync(crane_sched_t* h, float* run_ms) {
 int crane_sched_debug_profile(crane_sched_t* h, unsigned long long* dst, size_t cap) {
   if (!h || !h->ran || !dst) return CRANE_EINVAL;
   CU(cudaSetDevice(h->device));
-  size_t n = std::min(cap, (size_t)h->n_parts * 16);
+  size_t n = std::min(cap, (size_t)h->n_vparts * 16);
   CU(cudaStreamSynchronize(h->stream));
   if (n) CU(cudaMemcpy(dst, h->d_prof.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return CRANE_OK;
@@ -935,7 +1069,7 @@ int crane_sched_debug_bitmap(crane_sched_t* h, uint32_t* dst, size_t cap_words, 
   if (!h || !h->ran) return CRANE_EINVAL;
   CU(cudaSetDevice(h->device));
   uint32_t nq = 0;
-  CU(cudaMemcpy(&nq, h->d_part_job_off.p + h->n_parts, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&nq, h->d_part_job_off.p + h->n_vparts, sizeof(uint32_t), cudaMemcpyDeviceToHost));
   if (rows) *rows = nq;
   if (words_per_row) *words_per_row = h->words_per_row;
   size_t n = std::min(cap_words, (size_t)nq * h->words_per_row);

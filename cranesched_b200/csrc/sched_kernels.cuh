@@ -59,6 +59,7 @@ struct PendingDev {  // SoA mirror of crane_pending_t
   const uint32_t* excl_off;
   const uint32_t* excl_nodes;
   const uint32_t* alloc_off;  // exclusive prefix sum of node_num
+  const uint32_t* reservation;  // or null
 };
 
 struct RunningDev {
@@ -85,10 +86,19 @@ struct RunningDev {
 constexpr int kMaxClasses = 16;  // distinct res_total rows cached per partition
 
 struct ClusterDev {
-  uint32_t n_slots;           // usable nodes
-  uint32_t n_parts;
+  uint32_t n_slots;           // node states: usable nodes of the partitions, then the nodes of every reservation
+  uint32_t n_parts;           // partitions of the cluster
+  uint32_t n_vparts;          // schedulers: n_parts + one per reservation (JobScheduler.cpp:5757-5766)
+  uint32_t n_resv;
   uint32_t max_part_slots;
-  const uint32_t* part_base;  // [n_parts+1] slot ranges
+  const uint32_t* part_base;  // [n_vparts+1] slot ranges
+  // reservations (JobScheduler.cpp:5655-5713)
+  const int64_t* resv_start;  // [n_resv]
+  const int64_t* resv_end;
+  const uint32_t* slot_resv;  // [n_slots] reservation whose node state this is, 0xffffffff = a partition's node
+  const uint32_t* rsv_off;    // [n_slots+1] reservations holding resources of a partition's node, ascending id
+  const uint32_t* rsv_id;
+  const Row* rsv_res;
   const uint32_t* slot_node;  // slot -> global node index
   const uint32_t* node_slot;  // global node -> slot or 0xffffffff
   const Row* slot_total;      // res_total per slot
@@ -111,6 +121,7 @@ struct TimelineDev {
   Row* avail0;                // [n_slots] tick-start res_avail (NodeState::res_avail)
   double* cost0;              // [n_slots] initial cost (NodeRater)
   uint8_t* skip;              // [n_slots] timeline size >= max_jobs_per_node
+  int64_t* first_resv;        // [n_slots] craned_id_first_resv_map: earliest start of a reservation on the node, kInf = none
 };
 
 // per-job record in final queue order (partition-major, priority order inside)
@@ -126,7 +137,7 @@ struct __align__(16) JobQ {
   uint64_t spec8;      // per-entry typed counts, one byte each (clamped to 127)
   uint8_t name_need[CRANE_GRES_NAMES];  // per name max(total, sum typed), clamped to 255
   uint32_t ntasks;     // total task count of the job
-  uint32_t pad1;
+  uint32_t vpart;      // scheduler of the job: partition, or n_parts + reservation
 };
 static_assert(sizeof(JobQ) == 112, "JobQ layout");
 
@@ -453,7 +464,7 @@ __global__ void k_sort_scatter(const uint64_t* keys_in, const uint32_t* vals_in,
 // The remaining ranks are stably re-sorted by partition id (key2).
 // ------------------------------------------------------------------------
 __global__ void k_queue_keys(PendingDev pd, const uint32_t* order, const double* prio, uint32_t limit,
-                             uint32_t n_parts, uint64_t* key2, PlaceDev out, uint32_t* part_count) {
+                             ClusterDev cl, int64_t now, uint64_t* key2, PlaceDev out, uint32_t* part_count, uint32_t* vpart) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= pd.n) return;
   uint32_t j = order[r];
@@ -461,19 +472,30 @@ __global__ void k_queue_keys(PendingDev pd, const uint32_t* order, const double*
   out.start_time[j] = 0;
   out.end_time[j] = 0;
   out.n_alloc[j] = 0;
+  // the scheduler of the job: its reservation's (if it has started and not ended,
+  // JobScheduler.cpp:5665, 5676, 5788-5795) or its partition's
   uint32_t p = pd.partition[j];
+  const uint32_t rv = pd.reservation ? pd.reservation[j] : 0xffffffffu;
   uint8_t reason = CRANE_REASON_NONE;
+  bool found = p < cl.n_parts;
+  uint8_t miss = CRANE_REASON_PART_NOT_FOUND;
+  if (rv != 0xffffffffu) {
+    miss = CRANE_REASON_RESV_NOT_FOUND;
+    found = rv < cl.n_resv && now >= cl.resv_start[rv] && now < cl.resv_end[rv];
+    p = cl.n_parts + rv;
+  }
   uint64_t k = 0;
   if (r >= limit) {
     reason = CRANE_REASON_PRIORITY;
-    k = (uint64_t)n_parts + 1;
-  } else if (p >= n_parts) {
-    reason = CRANE_REASON_PART_NOT_FOUND;
-    k = (uint64_t)n_parts;
+    k = (uint64_t)cl.n_vparts + 1;
+  } else if (!found) {
+    reason = miss;
+    k = (uint64_t)cl.n_vparts;
   } else {
     k = p;
     atomicAdd(&part_count[p], 1u);
   }
+  vpart[j] = found ? p : 0xffffffffu;
   out.reason[j] = reason;
   key2[r] = k;
 }
@@ -491,7 +513,7 @@ __global__ void k_part_offsets(const uint32_t* part_count, uint32_t n_parts, uin
 
 // JobQ records in final queue order (coalesced 96-byte records for the commit
 // kernel); min_res_view of JobScheduler.cpp:5190-5192.
-__global__ void k_build_jobq(PendingDev pd, const uint32_t* queue, const uint32_t* n_queued_ptr, JobQ* jobq, uint32_t dslot) {
+__global__ void k_build_jobq(PendingDev pd, const uint32_t* queue, const uint32_t* n_queued_ptr, JobQ* jobq, uint32_t dslot, const uint32_t* vpart) {
   const GresDict& c_dict = c_dicts[dslot];
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= *n_queued_ptr) return;
@@ -507,7 +529,7 @@ __global__ void k_build_jobq(PendingDev pd, const uint32_t* queue, const uint32_
   q.flags = (pd.exclusive[j] ? 1u : 0u) | (view_has_gres(q.req) ? 2u : 0u);
   q.ntpn_max = pd.ntasks_per_node_max[j];
   q.ntasks = pd.ntasks[j];
-  q.pad1 = 0;
+  q.vpart = vpart[j];
   // anything but "exactly ntasks_per_node tasks on each of node_num nodes" takes the general
   // task distribution (JobScheduler.cpp:5193-5222, 5340-5361)
   if (q.ntpn_max != t || (uint64_t)t * q.node_num != q.ntasks) q.flags |= 4u;
@@ -536,7 +558,34 @@ __global__ void k_node_init(ClusterDev cl, RunningDev rn, TimelineDev tl, int64_
   if (g >= cl.n_slots) return;
   const Row total = cl.slot_total[g];
   Row avail = total;
-  double cost = cost_policy == 1 ? __ll2double_rn(total.cpu_raw) : 0.0;  // NodeRater's seed (BestFit: the node's cpu count)
+  // a reservation's own node state lives from the reservation's start to its end;
+  // before and after, nothing is scheduled into it (JobScheduler.cpp:5665, 5676, 5790-5795)
+  const uint32_t myresv = cl.slot_resv ? cl.slot_resv[g] : 0xffffffffu;
+  int64_t horizon = kInf;
+  bool dead = false;
+  if (myresv != 0xffffffffu) {
+    horizon = cl.resv_end[myresv];
+    dead = now >= horizon || now < cl.resv_start[myresv];
+  }
+  // NodeRater (JobScheduler.h:492-505): later reservations, then allocated_res — the
+  // reservations that have started (JobScheduler.cpp:5676-5683) and the running jobs
+  double cost = cost_policy == 1 ? __ll2double_rn(total.cpu_raw) : 0.0;  // (BestFit: seeded with the cpu count)
+  const uint32_t r_lo = cl.rsv_off ? cl.rsv_off[g] : 0, r_hi = cl.rsv_off ? cl.rsv_off[g + 1] : 0;
+  int64_t first = kInf;
+  for (uint32_t k = r_lo; k < r_hi; ++k) {
+    const uint32_t r = cl.rsv_id[k];
+    const int64_t rs = cl.resv_start[r], re = cl.resv_end[r];
+    if (now >= re) continue;  // expired but not cleaned up (:5665)
+    first = rs < first ? rs : first;
+    if (now < rs) cost = __dadd_rn(cost, cost_step(cost_policy, re - rs, cl.rsv_res[k].cpu_raw, total.cpu_raw));
+  }
+  for (uint32_t k = r_lo; k < r_hi; ++k) {
+    const uint32_t r = cl.rsv_id[k];
+    const int64_t rs = cl.resv_start[r], re = cl.resv_end[r];
+    if (now >= re || now < rs) continue;
+    row_sub(avail, cl.rsv_res[k]);
+    cost = __dadd_rn(cost, cost_step(cost_policy, re - now, cl.rsv_res[k].cpu_raw, total.cpu_raw));
+  }
   uint32_t lo = rn.n ? rn.slot_off[g] : 0, hi = rn.n ? rn.slot_off[g + 1] : 0;
   for (uint32_t k = lo; k < hi; ++k) {  // allocated_res in input order
     int64_t end = rn.slot_end[k];
@@ -547,32 +596,61 @@ __global__ void k_node_init(ClusterDev cl, RunningDev rn, TimelineDev tl, int64_
   }
   tl.avail0[g] = avail;
   tl.cost0[g] = cost;
+  tl.first_resv[g] = first;
+  // InitTimeAvailResMap (JobScheduler.h:295-332): every change time is a breakpoint;
+  // a segment starts from the one before it, then takes the releases of its time,
+  // then the reservations that start at its time (release before allocate).
   TlEntry* E = tl.ent + (size_t)g * tl.cap;
   uint32_t n = 1;
   E[0].t = now;
-  E[0].seg = avail;
   bool overflow = false;
-  // value of the segment at time t = avail + sum of releases with end <= t
-  for (uint32_t k = lo; k < hi && !overflow; ++k) {
-    int64_t end = rn.slot_end[k];
-    if (end < now + 1) end = now + 1;
-    const Row res = rn.slot_res[k];
+  auto add_time = [&](int64_t t) {  // sorted, distinct
+    if (overflow || t <= now) return;  // (a change at `now` itself belongs to the first segment)
     uint32_t idx = 1;
-    while (idx < n && E[idx].t < end) ++idx;
-    if (idx == n || E[idx].t != end) {
-      if (n + 2 > tl.cap) { overflow = true; break; }  // + sentinel would not fit
-      for (uint32_t m = n; m > idx; --m) E[m] = E[m - 1];
-      E[idx].t = end;
-      E[idx].seg = E[idx - 1].seg;
-      ++n;
-    }
-    for (uint32_t m = idx; m < n; ++m) row_add(E[m].seg, res);
+    while (idx < n && E[idx].t < t) ++idx;
+    if (idx < n && E[idx].t == t) return;
+    if (n + 2 > tl.cap) { overflow = true; return; }  // + sentinel would not fit
+    for (uint32_t m = n; m > idx; --m) E[m].t = E[m - 1].t;
+    E[idx].t = t;
+    ++n;
+  };
+  for (uint32_t k = r_lo; k < r_hi; ++k) {
+    const uint32_t r = cl.rsv_id[k];
+    if (now >= cl.resv_end[r]) continue;
+    if (now < cl.resv_start[r]) add_time(cl.resv_start[r]);
+    add_time(cl.resv_end[r]);
   }
-  E[n].t = kInf;  // time_avail_res_map[end].SetToZero(), JobScheduler.h:331
-  row_zero(E[n].seg);
-  ++n;
+  for (uint32_t k = lo; k < hi; ++k) {
+    int64_t end = rn.slot_end[k];
+    add_time(end < now + 1 ? now + 1 : end);
+  }
+  E[0].seg = avail;
+  for (uint32_t i = 1; i < n; ++i) {
+    const int64_t t = E[i].t;
+    Row seg = E[i - 1].seg;
+    for (uint32_t k = r_lo; k < r_hi; ++k)
+      if (now < cl.resv_end[cl.rsv_id[k]] && cl.resv_end[cl.rsv_id[k]] == t) row_add(seg, cl.rsv_res[k]);
+    for (uint32_t k = lo; k < hi; ++k) {
+      int64_t end = rn.slot_end[k];
+      if (end < now + 1) end = now + 1;
+      if (end == t) row_add(seg, rn.slot_res[k]);
+    }
+    for (uint32_t k = r_lo; k < r_hi; ++k)
+      if (now < cl.resv_start[cl.rsv_id[k]] && cl.resv_start[cl.rsv_id[k]] == t) row_sub(seg, cl.rsv_res[k]);
+    E[i].seg = seg;
+  }
+  // the zero sentinel: time_avail_res_map[end].SetToZero() (JobScheduler.h:331). For a
+  // reservation's node state `end` is the reservation's end: entries at or after it go
+  uint32_t keep = n;
+  if (horizon != kInf) {
+    keep = 1;
+    while (keep < n && E[keep].t < horizon) ++keep;
+  }
+  E[keep].t = horizon;
+  row_zero(E[keep].seg);
+  n = keep + 1;
   tl.n[g] = n;
-  tl.skip[g] = (overflow || n >= max_jobs) ? 1 : 0;  // JobScheduler.cpp:5230
+  tl.skip[g] = (overflow || dead || n >= max_jobs) ? 1 : 0;  // JobScheduler.cpp:5230
 }
 
 // ------------------------------------------------------------------------
@@ -591,8 +669,8 @@ __global__ void k_feas_bitmap(ClusterDev cl, PendingDev pd, const JobQ* jobq, co
   uint32_t warps_per_block = blockDim.x >> 5;
   for (uint32_t r = blockIdx.x * warps_per_block + warp_id(); r < n_queued; r += gridDim.x * warps_per_block) {
     JobQ jq = jobq[r];
-    uint32_t p = pd.partition[jq.job];
-    if (part_owner && part_owner[p] != rank) continue;  // another GPU commits this partition
+    uint32_t p = jq.vpart;
+    if (part_owner && (p < cl.n_parts ? part_owner[p] : 0u) != rank) continue;  // another GPU commits this partition
     uint32_t base = cl.part_base[p], mp = cl.part_base[p + 1] - base;
     const uint32_t row_words = (mp + 31) / 32;          // words beyond the job's own partition are never read
     uint32_t il = 0, ih = 0, el = 0, eh = 0;
@@ -623,7 +701,8 @@ __global__ void k_shard_mask(PendingDev pd, PlaceDev out, const uint32_t* part_o
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= pd.n) return;
   const uint32_t p = pd.partition[j];
-  const uint32_t owner = p < n_parts ? part_owner[p] : 0u;
+  const bool resv = pd.reservation && pd.reservation[j] != 0xffffffffu;  // reservations are committed by rank 0
+  const uint32_t owner = (!resv && p < n_parts) ? part_owner[p] : 0u;
   if (owner != rank) {
     out.reason[j] = 0;
     out.start_time[j] = 0;

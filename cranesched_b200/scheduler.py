@@ -61,6 +61,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.crane_sched_get_timing.argtypes = [C.c_void_p, P(abi.TimingC)]
     lib.crane_sched_qos_filter.restype = C.c_int
     lib.crane_sched_qos_filter.argtypes = [C.c_void_p, P(abi.QosTableC), C.c_void_p]
+    lib.crane_sched_set_reservations.restype = C.c_int
+    lib.crane_sched_set_reservations.argtypes = [C.c_void_p, P(abi.ReservationsC)]
     lib.crane_sched_set_shard.restype = C.c_int
     lib.crane_sched_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.crane_sched_device_placements.restype = C.c_int
@@ -74,7 +76,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 
 
 EXPORTS = ("crane_sched_create", "crane_sched_destroy", "crane_sched_last_error",
-           "crane_sched_set_cluster", "crane_sched_node_select", "crane_sched_upload",
+           "crane_sched_set_cluster", "crane_sched_set_reservations", "crane_sched_node_select", "crane_sched_upload",
            "crane_sched_run", "crane_sched_fetch", "crane_sched_sync", "crane_sched_get_timing",
            "crane_sched_qos_filter", "crane_sched_set_shard", "crane_sched_device_placements",
            "crane_sched_debug_bitmap", "crane_sched_debug_profile")
@@ -112,6 +114,11 @@ class GpuScheduler:
         c = cluster.as_c()
         self._check(self._lib.crane_sched_set_cluster(self._h, C.byref(c)))
         self.cluster = cluster
+
+    def set_reservations(self, resv: "abi.Reservations | None"):
+        """ResvMeta snapshot (JobScheduler.cpp:5655-5713); after set_cluster."""
+        c = resv.as_c() if resv is not None else None
+        self._check(self._lib.crane_sched_set_reservations(self._h, C.byref(c) if c is not None else None))
 
     # --- the NodeSelect call, host buffers in / host buffers out ------------
     def node_select(self, now: int, running: abi.Running, pending: abi.Pending,

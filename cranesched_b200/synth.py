@@ -425,6 +425,92 @@ def random_case(seed, n_jobs=300, n_nodes=48, n_parts=3, n_running=40, fifo=Fals
     return cfg, cluster, running, pend, NOW
 
 
+def random_reservations(seed, case, n_resv=4, frac_jobs=0.15, single_node=False):
+    """Reservations over a random_case-style case: a mix of expired, active and
+    later ones (ResvMeta, Node/NodeDefs.h:81-97); each reserves part of a few
+    nodes' resources (whole low cores, some slots). Returns (Reservations,
+    pending', running') with a share of the pending jobs submitted into
+    reservations (also unknown ones). single_node: one node per reservation — inside
+    a reservation the reference orders equal-cost nodes by the addresses of node
+    states created in std::unordered_map iteration order (JobScheduler.cpp:5695-5703),
+    which no harness controls; one node leaves nothing to order (tests/test_ref_pin.py)."""
+    import dataclasses
+    from .abi import Reservations
+    cfg, cl, rn, pd, now = case
+    rng = np.random.Generator(np.random.PCG64(seed * 7919 + 11))
+    start, end, off, nodes, res = [], [], [0], [], []
+    # a reservation only holds resources that are free: nodes without running
+    # allocations, and no node in two live reservations (the reference asserts on
+    # over-subscription, PublicHeader.cpp: cpu_count >= rhs.cpu_count)
+    busy = np.zeros(cl.n_nodes, bool)
+    busy[rn.alloc_node] = True
+    pool = [int(x) for x in rng.permutation(np.flatnonzero(~busy))]
+    for r in range(n_resv):
+        kind = r % 3  # 0 active, 1 later, 2 expired
+        if kind == 0:
+            st, en = now - int(rng.integers(10, 5000)), now + int(rng.integers(600, 40000))
+        elif kind == 1:
+            st = now + int(rng.integers(30, 20000)); en = st + int(rng.integers(300, 30000))
+        else:
+            st, en = now - 9000, now - int(rng.integers(0, 50))
+        k = 1 if single_node else min(int(rng.integers(1, max(2, min(6, cl.n_nodes // 3)))), len(pool))
+        k = min(k, len(pool))
+        mine, pool = pool[:k], pool[k:]
+        for n in sorted(mine):
+            tot = cl.res_total[n]
+            row = np.zeros((), RES_IN_NODE)
+            ncores = max(1, int(tot["cpu_raw"]) // 256 // int(rng.integers(2, 5)))
+            row["cpu_raw"] = ncores * 256
+            row["mem"] = int(tot["mem"]) // 4
+            row["mem_sw"] = int(tot["mem_sw"]) // 4
+            left, w = ncores, 0
+            core = np.zeros(CORE_WORDS, np.uint64)
+            while left > 0 and w < CORE_WORDS:
+                take = min(left, 64)
+                core[w] = np.uint64((1 << take) - 1) & tot["core"][w]
+                left -= take; w += 1
+            row["core"] = core
+            row["gres"] = tot["gres"] & np.uint16(0x3)  # the two lowest slots of every entry
+            nodes.append(n); res.append(row)
+        off.append(len(nodes)); start.append(st); end.append(en)
+    resv = Reservations(start, end, off, np.array(nodes, np.uint32), np.array(res, RES_IN_NODE))
+    pr = np.full(pd.n, 0xFFFFFFFF, np.uint32)
+    pick = rng.random(pd.n) < frac_jobs
+    pr[pick] = rng.integers(0, n_resv + 1, int(pick.sum())).astype(np.uint32)  # n_resv = an unknown reservation
+    pd2 = dataclasses.replace(pd, reservation=pr)
+    # running jobs: the cluster's own, plus one job inside every reservation that has
+    # started (one reserved core and 1 GiB on the reservation's first node)
+    cols = {f: getattr(rn, f) for f in rn.__dataclass_fields__ if f != "reservation"}
+    rr = [0xFFFFFFFF] * rn.n
+    extra = []
+    for r in range(n_resv):
+        if start[r] <= now < end[r] and off[r + 1] > off[r]:
+            row = np.zeros((), RES_IN_NODE)
+            src = res[off[r]]
+            low = int(src["core"][0]) & -int(src["core"][0])
+            row["cpu_raw"] = 256; row["mem"] = GiB; row["mem_sw"] = GiB
+            core = np.zeros(CORE_WORDS, np.uint64); core[0] = np.uint64(low); row["core"] = core
+            extra.append((r, nodes[off[r]], row))
+    if extra:
+        k = len(extra)
+        ap = lambda a, v, dt: np.concatenate([a, np.array(v, dt)])
+        cols["start_time"] = ap(rn.start_time, [now - 100] * k, np.int64)
+        cols["end_time"] = ap(rn.end_time, [now + 777 + 13 * i for i in range(k)], np.int64)
+        cols["node_num"] = ap(rn.node_num, [1] * k, np.uint32)
+        cols["partition_priority"] = ap(rn.partition_priority, [1000] * k, np.uint32)
+        cols["qos_priority"] = ap(rn.qos_priority, [1000] * k, np.uint32)
+        cols["account"] = ap(rn.account, [0] * k, np.uint32)
+        cols["view_cpu_raw"] = ap(rn.view_cpu_raw, [256] * k, np.int64)
+        cols["view_mem"] = ap(rn.view_mem, [GiB] * k, np.uint64)
+        cols["alloc_off"] = np.concatenate([rn.alloc_off, rn.alloc_off[-1] + 1 + np.arange(k, dtype=np.uint32)])
+        cols["alloc_node"] = ap(rn.alloc_node, [e[1] for e in extra], np.uint32)
+        cols["alloc_res"] = np.concatenate([rn.alloc_res, np.array([e[2] for e in extra], RES_IN_NODE)])
+        rr += [e[0] for e in extra]
+    from .abi import Running
+    rn2 = Running(**cols, reservation=np.array(rr, np.uint32))
+    return resv, pd2, rn2
+
+
 def random_qos(seed, cluster, pend, tight=1.0, n_parents=4, invalid_frac=0.1):
     """QoS limits + account chains + (partly pre-filled) usage for a pending table
     (config 3's QoS filter). Accounts 0..A-1 are the leaves the

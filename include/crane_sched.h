@@ -123,6 +123,8 @@ typedef struct crane_running {
   const uint32_t* alloc_off;   /* [n+1] CSR over (node, res) pairs           */
   const uint32_t* alloc_node;
   const crane_res_in_node_t* alloc_res;
+  const uint32_t* reservation; /* [n] RnJobInScheduler::reservation as an index into
+                                  crane_reservations_t, 0xFFFFFFFF = none; NULL = no job has one */
 } crane_running_t;
 
 /* Mirrors the inputs of PdJobInScheduler (JobScheduler.h:91-164). Input order
@@ -151,7 +153,30 @@ typedef struct crane_pending {
   const uint32_t* incl_nodes;
   const uint32_t* excl_off;  /* [n+1] CSR of excluded_nodes, or NULL          */
   const uint32_t* excl_nodes;
+  const uint32_t* reservation; /* [n] PdJobInScheduler::reservation as an index into
+                                  crane_reservations_t, 0xFFFFFFFF = none, an index >= n
+                                  = a name the daemon does not know ("Reservation Not
+                                  Found"); NULL = no job has one */
 } crane_pending_t;
+
+/* Reservations: what NodeSelect reads from g_meta_container->GetResvMetaMapPtr()
+ * (JobScheduler.cpp:5655-5713; ResvMeta, Node/NodeDefs.h:81-97). A reservation
+ * that has started is an allocation on its nodes until its end and — for the
+ * pending jobs submitted into it — a scheduler of its own over node states
+ * holding exactly the reserved resources, with the timeline ending at the
+ * reservation's end; one that starts later is taken out of its nodes' timelines
+ * over [start, end); an expired one (now >= end) is ignored. A job backfilled
+ * onto a node whose first reservation starts inside the job's window is
+ * labelled "Resource Reserved" (JobScheduler.cpp:5829-5841). */
+typedef struct crane_reservations {
+  uint32_t n;
+  const int64_t* start_time;        /* [n]                                    */
+  const int64_t* end_time;          /* [n]                                    */
+  const uint32_t* node_off;         /* [n+1] CSR over (node, res) pairs:
+                                       ResvMeta::res_total.EachNodeResMap()   */
+  const uint32_t* node;             /* node index (a node appears once per reservation) */
+  const crane_res_in_node_t* res;   /* resources reserved on that node        */
+} crane_reservations_t;
 
 /* pending reasons: the strings NodeSelect writes (JS.cpp:192,5784-5864,6547;
  * docs/en/reference/pending_reason.md:42-54) as codes. */
@@ -216,6 +241,11 @@ const char* crane_sched_last_error(const crane_sched_t* h);
  * g_meta_container every tick (JobScheduler.cpp:5603-5651). Call when the node
  * set, alive/drain flags or partition membership change. */
 int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* cluster);
+
+/* Replaces: the reservation snapshot of NodeSelect (JobScheduler.cpp:5655-5713).
+ * Call after crane_sched_set_cluster (which clears the reservations) whenever
+ * the reservation set changes; resv == NULL or n == 0 = none. */
+int crane_sched_set_reservations(crane_sched_t* h, const crane_reservations_t* resv);
 
 /* ---- the hot path -------------------------------------------------------- */
 /* Replaces: SchedulerAlgo::NodeSelect (JobScheduler.cpp:5543-5868), host

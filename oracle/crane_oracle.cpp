@@ -436,10 +436,12 @@ struct RnJob {
   CpuT view_cpu;
   uint64_t view_mem;
   std::map<std::string, ResInNode> allocated_res;  // ResourceV3
+  uint32_t reservation{0xffffffffu};               // index, 0xffffffff = none
 };
 
 struct PdJob {
   uint32_t index;  // input position == job-id order
+  uint32_t reservation{0xffffffffu};
   int64_t time_limit;
   uint32_t partition;
   ResView req_node, req_task, req_total;
@@ -496,25 +498,34 @@ struct NodeState {
   ResInNode res_avail;
   struct Alloc { int64_t end_time; ResInNode res; };
   std::vector<Alloc> allocated;
+  struct Resv { int64_t start_time, end_time; ResInNode res; };
+  std::vector<Resv> reserved;  // reservations that start later (JobScheduler.cpp:5704-5711)
   Timeline timeline;
 
-  // JobScheduler.h:295-332 (no pending reservations in scope -> only
-  // release events at running jobs' end times)
-  void InitTimeline(int64_t now) {
-    std::vector<std::pair<int64_t, const ResInNode*>> changes;
+  // JobScheduler.h:295-332: change events = (-res at start, +res at end) of
+  // every later reservation and +res at the end of every allocation; sorted by
+  // time, a release before an allocation at the same time; `end` is the key of
+  // the zero sentinel (+inf, or the end of the reservation this node belongs to).
+  void InitTimeline(int64_t now, int64_t end = kInfFuture) {
+    struct Change { int64_t t; bool alloc; const ResInNode* res; };
+    std::vector<Change> changes;
+    for (const auto& r : reserved) {
+      changes.push_back({r.start_time, true, &r.res});
+      changes.push_back({r.end_time, false, &r.res});
+    }
     for (const auto& a : allocated) {
-      changes.emplace_back(a.end_time, &a.res);
+      changes.push_back({a.end_time, false, &a.res});
       res_avail.Sub(a.res);
     }
-    std::stable_sort(changes.begin(), changes.end(),
-                     [](const auto& l, const auto& r) { return l.first < r.first; });
+    std::stable_sort(changes.begin(), changes.end(), [](const Change& l, const Change& r) {
+      return l.t < r.t || (l.t == r.t && l.alloc < r.alloc);
+    });
     auto cur = timeline.emplace(now, res_avail).first;
     for (const auto& ch : changes) {
-      if (ch.first != cur->first)
-        cur = timeline.emplace(ch.first, cur->second).first;
-      cur->second.Add(*ch.second);
+      if (ch.t != cur->first) cur = timeline.emplace(ch.t, cur->second).first;
+      if (ch.alloc) cur->second.Sub(*ch.res); else cur->second.Add(*ch.res);
     }
-    timeline[kInfFuture].SetToZero();
+    timeline[end].SetToZero();
   }
 
   // JobScheduler.h:334-453, allocation direction only (is_release=false).
@@ -560,6 +571,8 @@ struct NodeSelector {
 
   void AddNode(int64_t now, NodeState* ns) {  // JobScheduler.h:492-505,534-544
     double cost = policy == 1 ? static_cast<double>(ns->res_total.cpu_count.raw) : 0.0;
+    for (const auto& r : ns->reserved)  // JobScheduler.h:496-500
+      UpdateCostPolicy(policy, cost, r.start_time, r.end_time, r.res, ns->res_total);
     for (const auto& a : ns->allocated)
       UpdateCostPolicy(policy, cost, now, a.end_time, a.res, ns->res_total);
     Rater& r = info.emplace(ns->craned_id, Rater{ns, cost, {}}).first->second;
@@ -990,6 +1003,9 @@ std::string NodeName(uint32_t idx) {
 // ===========================================================================
 // C interface
 // ===========================================================================
+namespace { const crane_reservations_t* g_resv = nullptr; }
+extern "C" void crane_oracle_set_reservations(const crane_reservations_t* resv) { g_resv = resv; }
+
 extern "C" int crane_oracle_node_select(
     const crane_sched_config_t* cfg, const crane_cluster_t* cl, int64_t now,
     const crane_running_t* running, const crane_pending_t* pending,
@@ -1031,6 +1047,7 @@ extern "C" int crane_oracle_node_select(
     j->qos_priority = pending->qos_priority[i];
     j->account = "acct" + std::to_string(pending->account[i]);
     j->priority = pending->mandated_priority ? pending->mandated_priority[i] : 0.0;
+    if (pending->reservation) j->reservation = pending->reservation[i];
     pd.push_back(std::move(j));
   }
   std::vector<std::unique_ptr<RnJob>> rn;
@@ -1045,6 +1062,7 @@ extern "C" int crane_oracle_node_select(
     j->account = "acct" + std::to_string(running->account[i]);
     j->view_cpu = CpuT::FromRaw(running->view_cpu_raw[i]);
     j->view_mem = running->view_mem[i];
+    if (running->reservation) j->reservation = running->reservation[i];
     for (uint32_t k = running->alloc_off[i]; k < running->alloc_off[i + 1]; ++k)
       j->allocated_res[node_names[running->alloc_node[k]]].Add(
           FromAbi(dict, running->alloc_res[k]));
@@ -1060,8 +1078,15 @@ extern "C" int crane_oracle_node_select(
   for (auto& j : rn) j->end_time = std::max(j->end_time, now + 1);      // :5547
 
   std::vector<char> part_has_jobs(cl->n_partitions, 0);                 // :5551
-  for (const auto& j : pd)
-    if (j->partition < cl->n_partitions) part_has_jobs[j->partition] = 1;
+  const uint32_t n_resv = g_resv ? g_resv->n : 0;
+  std::vector<char> resv_has_jobs(n_resv, 0);
+  for (const auto& j : pd) {  // :5557-5562: a job sits in its reservation's list or in its partition's
+    if (j->reservation != 0xffffffffu) {
+      if (j->reservation < n_resv) resv_has_jobs[j->reservation] = 1;
+    } else if (j->partition < cl->n_partitions) {
+      part_has_jobs[j->partition] = 1;
+    }
+  }
 
   // node_state_map (:5597-5651). One vector in node-index order => pointer
   // order == index order (deviation D1).
@@ -1085,14 +1110,74 @@ extern "C" int crane_oracle_node_select(
       part_nodes[p].push_back(&states[n]);
     }
   }
-  for (const auto& j : rn)                                              // :5715
-    for (const auto& [id, res] : j->allocated_res) {
-      auto it = state_by_name.find(id);
-      if (it != state_by_name.end())
-        it->second->allocated.push_back({j->end_time, res});
+  // reservations (:5655-5713)
+  struct ResvSched {
+    int64_t end_time{0};
+    // node states holding the reserved resources, ONE vector in node-index order: the cost
+    // set orders equal costs by NodeState address (JobScheduler.h:588), deviation D1
+    std::vector<NodeState> states;
+    std::map<std::string, NodeState*> nodes;
+    std::unique_ptr<LocalScheduler> sched;
+  };
+  std::vector<std::unique_ptr<ResvSched>> resv_scheds(n_resv);
+  std::unordered_map<std::string, int64_t> first_resv;  // craned_id_first_resv_map
+  for (uint32_t r = 0; r < n_resv; ++r) {
+    const int64_t rs = g_resv->start_time[r], re = g_resv->end_time[r];
+    if (now >= re) continue;  // expired but not cleaned up
+    for (uint32_t k = g_resv->node_off[r]; k < g_resv->node_off[r + 1]; ++k) {
+      const std::string& id = node_names[g_resv->node[k]];
+      auto it = first_resv.find(id);
+      if (it == first_resv.end()) first_resv[id] = rs;
+      else if (rs < it->second) it->second = rs;
     }
+    if (now >= rs) {
+      for (uint32_t k = g_resv->node_off[r]; k < g_resv->node_off[r + 1]; ++k) {
+        auto it = state_by_name.find(node_names[g_resv->node[k]]);
+        if (it != state_by_name.end()) it->second->allocated.push_back({re, FromAbi(dict, g_resv->res[k])});
+      }
+      if (!resv_has_jobs[r]) continue;
+      auto rsd = std::make_unique<ResvSched>();
+      rsd->end_time = re;
+      std::vector<uint32_t> ks;
+      for (uint32_t k = g_resv->node_off[r]; k < g_resv->node_off[r + 1]; ++k) ks.push_back(k);
+      std::sort(ks.begin(), ks.end(), [&](uint32_t x, uint32_t y) { return g_resv->node[x] < g_resv->node[y]; });
+      rsd->states.resize(ks.size());
+      for (size_t i = 0; i < ks.size(); ++i) {
+        NodeState& ns = rsd->states[i];
+        ns.craned_id = node_names[g_resv->node[ks[i]]];
+        ns.index = g_resv->node[ks[i]];
+        ns.res_total = FromAbi(dict, g_resv->res[ks[i]]);
+        ns.res_avail = ns.res_total;
+        rsd->nodes[ns.craned_id] = &ns;
+      }
+      resv_scheds[r] = std::move(rsd);
+    } else {
+      for (uint32_t k = g_resv->node_off[r]; k < g_resv->node_off[r + 1]; ++k) {
+        auto it = state_by_name.find(node_names[g_resv->node[k]]);
+        if (it != state_by_name.end()) it->second->reserved.push_back({rs, re, FromAbi(dict, g_resv->res[k])});
+      }
+    }
+  }
+  for (const auto& j : rn) {                                            // :5715
+    if (j->reservation == 0xffffffffu) {
+      for (const auto& [id, res] : j->allocated_res) {
+        auto it = state_by_name.find(id);
+        if (it != state_by_name.end())
+          it->second->allocated.push_back({j->end_time, res});
+      }
+    } else {
+      if (j->reservation >= n_resv || !resv_scheds[j->reservation]) continue;  // :5727 (error logged, job skipped)
+      for (const auto& [id, res] : j->allocated_res) {
+        auto it = resv_scheds[j->reservation]->nodes.find(id);
+        if (it != resv_scheds[j->reservation]->nodes.end()) it->second->allocated.push_back({j->end_time, res});
+      }
+    }
+  }
   for (uint32_t n = 0; n < M; ++n)                                      // :5746
     if (in_map[n]) states[n].InitTimeline(now);
+  for (auto& rsd : resv_scheds)
+    if (rsd)
+      for (auto& ns : rsd->states) ns.InitTimeline(now, rsd->end_time);
 
   std::vector<std::unique_ptr<LocalScheduler>> scheds(cl->n_partitions);
   for (uint32_t p = 0; p < cl->n_partitions; ++p) {                     // :5757
@@ -1103,6 +1188,15 @@ extern "C" int crane_oracle_node_select(
     scheds[p]->sel.policy = cfg->cost_policy;
     for (NodeState* ns : part_nodes[p]) scheds[p]->sel.AddNode(now, ns);
   }
+  for (auto& rsd : resv_scheds) {                                       // :5763
+    if (!rsd) continue;
+    rsd->sched = std::make_unique<LocalScheduler>();
+    rsd->sched->max_jobs_per_node = cfg->max_jobs_per_node;
+    rsd->sched->max_window = cfg->max_time_window_s;
+    rsd->sched->sel.policy = cfg->cost_policy;
+    // node states in node-index order: pointer order == index order (deviation D1)
+    for (NodeState& ns : rsd->states) rsd->sched->sel.AddNode(now, &ns);
+  }
 
   std::vector<PdJob*> order;
   OrderJobs(*cfg, now, pd, rn, order);                                  // :5769
@@ -1112,11 +1206,22 @@ extern "C" int crane_oracle_node_select(
     if (max_jobs && done >= max_jobs) break;
     ++done;
     if (job->reason != CRANE_REASON_NONE) continue;
-    if (job->partition >= cl->n_partitions || !scheds[job->partition]) {
-      job->reason = CRANE_REASON_PART_NOT_FOUND;                        // :5784
-      continue;
+    LocalScheduler* s = nullptr;
+    ResvSched* rsd = nullptr;
+    if (job->reservation == 0xffffffffu) {
+      if (job->partition >= cl->n_partitions || !scheds[job->partition]) {
+        job->reason = CRANE_REASON_PART_NOT_FOUND;                      // :5784
+        continue;
+      }
+      s = scheds[job->partition].get();
+    } else {
+      if (job->reservation >= n_resv || !resv_scheds[job->reservation]) {
+        job->reason = CRANE_REASON_RESV_NOT_FOUND;                      // :5793
+        continue;
+      }
+      rsd = resv_scheds[job->reservation].get();
+      s = rsd->sched.get();
     }
-    LocalScheduler* s = scheds[job->partition].get();
     bool ok = s->Schedule(now, job);
     if (!ok) {
       job->reason = CRANE_REASON_RESOURCE;                              // :5802
@@ -1125,11 +1230,29 @@ extern "C" int crane_oracle_node_select(
     job->end_time = job->start_time + job->time_limit;
     s->sel.Allocate(job->start_time, job->end_time, job->allocated_res);  // :5827
     if (job->start_time != now) {                                       // :5829
-      for (const std::string& id : job->craned_ids) {
-        const ResInNode& avail = state_by_name.at(id)->res_avail;
-        if (!ResLe(job->allocated_res.at(id), avail)) {
-          job->reason = CRANE_REASON_RESOURCE;
-          break;
+      if (!rsd) {
+        for (const std::string& id : job->craned_ids) {
+          auto it = first_resv.find(id);
+          if (it != first_resv.end() && it->second < now + job->time_limit) {
+            job->reason = CRANE_REASON_RESERVED;
+            break;
+          }
+        }
+        if (job->reason != CRANE_REASON_NONE) continue;
+        for (const std::string& id : job->craned_ids) {
+          const ResInNode& avail = state_by_name.at(id)->res_avail;
+          if (!ResLe(job->allocated_res.at(id), avail)) {
+            job->reason = CRANE_REASON_RESOURCE;
+            break;
+          }
+        }
+      } else {
+        for (const std::string& id : job->craned_ids) {
+          const ResInNode& avail = rsd->nodes.at(id)->res_avail;
+          if (!ResLe(job->allocated_res.at(id), avail)) {
+            job->reason = CRANE_REASON_RESOURCE;
+            break;
+          }
         }
       }
       if (job->reason == CRANE_REASON_NONE) job->reason = CRANE_REASON_PRIORITY;
@@ -1142,6 +1265,8 @@ extern "C" int crane_oracle_node_select(
   if (jobs_done) *jobs_done = done;
 
   // --- write-back in the C-ABI layout --------------------------------------
+  std::unordered_map<std::string, uint32_t> index_by_name;
+  for (uint32_t i = 0; i < M; ++i) index_by_name.emplace(node_names[i], i);
   uint32_t off = 0;
   for (uint32_t i = 0; i < N; ++i) {
     const PdJob* j = pd[i].get();
@@ -1161,7 +1286,7 @@ extern "C" int crane_oracle_node_select(
       uint32_t k = 0;  // std::map iterates node names == node index ascending
       for (const auto& [id, res] : j->allocated_res) {
         if (k >= j->node_num) break;
-        out->alloc_node[off + k] = state_by_name.at(id)->index;
+        out->alloc_node[off + k] = index_by_name.at(id);
         out->alloc_ntasks[off + k] = j->node_task_num.at(id);
         ToAbi(dict, res, &out->alloc_res[off + k]);
         ++k;

@@ -35,6 +35,11 @@ int crane_oracle_node_select(const crane_sched_config_t* cfg,
                              crane_placements_t* out, double* elapsed_ms,
                              uint32_t max_jobs, uint32_t* jobs_done);
 
+/* Reservations for the next crane_oracle_node_select calls (JobScheduler.cpp:5655-5713);
+ * the pointer must stay valid; NULL = none. pending->reservation / running->reservation
+ * refer to it. */
+void crane_oracle_set_reservations(const crane_reservations_t* resv);
+
 /* ResourceView::GetFeasibleResourceInNode (PublicHeader.cpp:519-599) on one
  * (request, availability) pair. Returns 1 feasible / 0 not; *alloc written when
  * feasible. */

@@ -53,15 +53,20 @@ def lib():
 
 
 def node_select(cfg: abi.Config, cluster: abi.Cluster, running: abi.Running,
-                pending: abi.Pending, now: int, max_jobs: int = 0):
+                pending: abi.Pending, now: int, max_jobs: int = 0, resv: "abi.Reservations | None" = None):
     """Returns (Placements, elapsed_ms, jobs_done)."""
     out = abi.Placements.for_pending(pending)
+    c_resv = resv.as_c() if resv is not None else None
+    lib().crane_oracle_set_reservations.restype = None
+    lib().crane_oracle_set_reservations.argtypes = [C.c_void_p]
+    lib().crane_oracle_set_reservations(C.byref(c_resv) if c_resv is not None else None)
     c_cfg, c_cl, c_rn, c_pd, c_out = cfg.as_c(), cluster.as_c(), running.as_c(), pending.as_c(), out.as_c()
     ms = C.c_double(0.0)
     done = C.c_uint32(0)
     rc = lib().crane_oracle_node_select(C.byref(c_cfg), C.byref(c_cl), now, C.byref(c_rn),
                                          C.byref(c_pd), C.byref(c_out), C.byref(ms),
                                          max_jobs, C.byref(done))
+    lib().crane_oracle_set_reservations(None)
     if rc != 0:
         raise RuntimeError(f"crane_oracle_node_select rc={rc}")
     return out, ms.value, done.value

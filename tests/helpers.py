@@ -4,11 +4,13 @@ from cranesched_b200 import abi
 from cranesched_b200.scheduler import GpuScheduler
 
 
-def run_sched(case, lib_path=None, device=0):
+def run_sched(case, lib_path=None, device=0, resv=None):
     cfg, cluster, running, pending, now = case
     s = GpuScheduler(cfg, device, lib_path)
     try:
         s.set_cluster(cluster)
+        if resv is not None:
+            s.set_reservations(resv)
         out = s.node_select(now, running, pending)
         timing = s.timing()
     finally:

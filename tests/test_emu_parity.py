@@ -25,6 +25,18 @@ CASES = {
 }
 
 
+def test_emulated_reservations(oracle, emu_lib):
+    """Reservations end to end through the emulated kernels: own schedulers, later
+    reservations cut out of the timelines, "Resource Reserved" / "Reservation Not Found"."""
+    for seed in (501, 504):
+        case = synth.random_case(seed, n_jobs=130, n_nodes=26, n_parts=1 + seed % 3, n_running=10)
+        resv, pd2, rn2 = synth.random_reservations(seed, case, n_resv=5)
+        cfg, cl, rn, pd, now = case
+        ref, _, _ = oracle.node_select(cfg, cl, rn2, pd2, now, resv=resv)
+        got, _ = run_sched((cfg, cl, rn2, pd2, now), emu_lib, resv=resv)
+        assert_same(ref, got)
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_emulated_kernels_match_oracle(oracle, emu_lib, name):
     case = CASES[name]()

@@ -86,6 +86,21 @@ def test_bestfit_policy(oracle, gpu_lib, seed):
     check_invariants(case, got)
 
 
+@pytest.mark.parametrize("seed", range(500, 512))
+def test_reservations(oracle, gpu_lib, seed):
+    """Reservations (JobScheduler.cpp:5655-5753, 5788-5795, 5829-5861): schedulers of
+    their own over the reserved resources, later reservations cut out of the
+    timelines, running jobs inside reservations, the "Resource Reserved" and
+    "Reservation Not Found" reasons."""
+    case = synth.random_case(seed, n_jobs=400, n_nodes=60, n_parts=1 + seed % 3, n_running=30,
+                             fifo=bool(seed % 4 == 0), ntpn_range=bool(seed % 3 == 0))
+    resv, pd2, rn2 = synth.random_reservations(seed, case, n_resv=6)
+    cfg, cl, rn, pd, now = case
+    ref, _, _ = oracle.node_select(cfg, cl, rn2, pd2, now, resv=resv)
+    got, _ = run_sched((cfg, cl, rn2, pd2, now), gpu_lib, resv=resv)
+    assert_same(ref, got)
+
+
 def test_batch_limit(oracle, gpu_lib):
     """ScheduledBatchSize: ranks beyond the limit get "Priority"."""
     case = synth.random_case(50, n_jobs=500, n_nodes=40, n_running=20, limit=137)

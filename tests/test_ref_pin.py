@@ -146,3 +146,23 @@ def test_earliest_start_known_answers():
     assert ask([a, b], 2, 10**9) == 1600  # last segment before the sentinel: no end in sight, accepted
     assert ask([[(1000, 0), (inf, 0)]], 1, 10) is None
     assert ask([[(1000, 0), (1000 + 8 * 86400, 4), (inf, 0)]], 1, 10) is None  # beyond the 7-day window
+
+
+@pytest.mark.parametrize("seed", range(400, 416))
+def test_reservations(oracle, seed):
+    """Reservations (JobScheduler.cpp:5655-5753, 5788-5795, 5829-5861): expired, started
+    and later ones; jobs submitted into them (also into unknown ones: "Reservation Not
+    Found"), running jobs inside them, "Resource Reserved" for backfills that run into
+    a reservation. One node per reservation: inside a reservation the reference orders
+    equal-cost nodes by the addresses of node states created in unordered_map order."""
+    case = synth.random_case(seed, n_jobs=200, n_nodes=30, n_parts=1 + seed % 3, n_running=12,
+                             one_type_per_name=True, lists=bool(seed % 2))
+    resv, pd2, rn2 = synth.random_reservations(seed, case, n_resv=6, single_node=True)
+    cfg, cl, rn, pd, now = case
+    a, _, _ = oracle.node_select(cfg, cl, rn2, pd2, now, resv=resv)
+    ex = pyref.RefExtra(resv_start=resv.start_time, resv_end=resv.end_time, resv_off=resv.node_off, resv_node=resv.node,
+                        resv_res=resv.res, pd_resv=pd2.reservation, rn_resv=rn2.reservation)
+    b, _ = pyref.node_select(cfg, cl, rn2, pd2, now, ex)
+    d = a.diff(b)
+    assert not d, "oracle differs from the reference's own NodeSelect:\n" + "\n".join(d[:8])
+    assert (a.reason == abi.REASON_RESERVED).any() or (a.reason == 5).any() or seed % 4
