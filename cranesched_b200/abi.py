@@ -405,6 +405,27 @@ class Pending:
     def n(self):
         return len(self.partition)
 
+    def take(self, idx) -> "Pending":
+        """Rows `idx` (ascending) as a table of their own."""
+        idx = np.asarray(idx, np.int64)
+        cols = {}
+        for f in self.__dataclass_fields__:
+            v = getattr(self, f)
+            if v is None or f in ("incl_off", "incl_nodes", "excl_off", "excl_nodes"):
+                continue
+            cols[f] = v[idx]
+        for k in ("incl", "excl"):
+            off = getattr(self, k + "_off")
+            if off is not None:
+                nodes = getattr(self, k + "_nodes")
+                new_off, new_nodes = [0], []
+                for j in idx:
+                    new_nodes += nodes[off[j]:off[j + 1]].tolist()
+                    new_off.append(len(new_nodes))
+                cols[k + "_off"] = np.array(new_off, np.uint32)
+                cols[k + "_nodes"] = np.array(new_nodes, np.uint32)
+        return Pending(**cols)
+
     def as_c(self) -> PendingC:
         return PendingC(
             self.n, _ptr(self.partition), _ptr(self.time_limit), _ptr(self.submit_time),

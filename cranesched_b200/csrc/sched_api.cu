@@ -47,6 +47,23 @@ struct DBuf {
     if (e == cudaSuccess) cap = want;
     return e;
   }
+  // like ensure(), but the first `keep` elements survive a reallocation
+  cudaError_t grow(size_t n, size_t keep, cudaStream_t st) {
+    if (n <= cap) return cudaSuccess;
+    T* old = p;
+    size_t want = n + n / 2 + 16;
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&q), want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (old && keep) {
+      e = cudaMemcpyAsync(q, old, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (old) cudaFree(old);
+    p = q;
+    cap = want;
+    return e;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -102,6 +119,12 @@ struct crane_sched {
   uint64_t total_alloc = 0;
   bool have_lists_incl = false, have_lists_excl = false, have_mandated = false;
   std::vector<uint32_t> h_alloc_off;
+  // device-resident pending table: host mirrors of the small columns, tombstones
+  std::vector<uint32_t> h_pd_account, h_incl_off, h_excl_off;
+  std::vector<uint8_t> h_dead;
+  uint32_t n_dead = 0;
+  DBuf<uint8_t> d_dead;
+  DBuf<uint32_t> d_erase_rows;
   DBuf<uint32_t> d_ntpn_max, d_ntasks;
   DBuf<uint32_t> d_partition, d_node_num, d_ntpn, d_part_prio, d_qos_prio, d_account, d_alloc_off;
   DBuf<int64_t> d_time_limit, d_submit;
@@ -265,7 +288,7 @@ void crane_sched_destroy(crane_sched_t* h) {
   REL(d_out_prio); REL(d_out_start); REL(d_out_end); REL(d_out_nalloc); REL(d_out_node); REL(d_out_ntasks);
   REL(d_out_res); REL(d_prof); REL(d_qos); REL(d_user); REL(d_q_u32); REL(d_q_chain_off); REL(d_q_chain);
   REL(d_q_i64); REL(d_q_valid); REL(d_part_owner); REL(d_part_list); REL(d_ntpn_max); REL(d_ntasks); REL(d_first_resv); REL(d_resv_start); REL(d_resv_end); REL(d_slot_resv);
-  REL(d_rsv_off); REL(d_rsv_id); REL(d_vpart); REL(d_pd_resv); REL(d_rsv_res); REL(d_q_tres); REL(d_q_user_usage); REL(d_q_acct_usage); REL(d_q_qos_usage);
+  REL(d_rsv_off); REL(d_rsv_id); REL(d_dead); REL(d_erase_rows); REL(d_vpart); REL(d_pd_resv); REL(d_rsv_res); REL(d_q_tres); REL(d_q_user_usage); REL(d_q_acct_usage); REL(d_q_qos_usage);
 #undef REL
   for (auto& e : h->ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -525,30 +548,53 @@ int crane_sched_device_placements(crane_sched_t* h, crane_device_placements_t* o
   return CRANE_OK;
 }
 
-int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_pending_t* pd) {
-  if (!h || !pd) return CRANE_EINVAL;
-  if (!h->have_cluster) return fail(h, CRANE_EINVAL, "upload: set_cluster first");
-  CU(cudaSetDevice(h->device));
-  h->uploaded = false;  // a failed upload leaves nothing runnable behind
-  h->ran = false;
-  CU(cudaEventRecord(h->ev[0], h->stream));
-  const uint32_t N = pd->n;
-  const uint32_t R = rn ? rn->n : 0;
-  if (R && (!rn->start_time || !rn->end_time || !rn->node_num || !rn->partition_priority || !rn->qos_priority ||
-            !rn->account || !rn->view_cpu_raw || !rn->view_mem || !rn->alloc_off))
-    return fail(h, CRANE_EINVAL, "running: null column");
-  for (uint32_t j = 0; j < R; ++j)
-    if (rn->alloc_off[j + 1] < rn->alloc_off[j]) return fail(h, CRANE_EINVAL, "running: alloc_off is not monotonic");
+}  // extern "C" (the split upload lives in an unnamed namespace)
+
+namespace {
+
+template <class T>
+int h2d_at(crane_sched* h, DBuf<T>& dst, const T* src, size_t base, size_t n) {
+  CU(dst.grow(std::max<size_t>(base + n, 1), base, h->stream));
+  if (n) CU(cudaMemcpyAsync(dst.p + base, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  return CRANE_OK;
+}
+#define H2D_AT(buf, src, base, n)                                  \
+  do {                                                             \
+    int rc__ = h2d_at(h, buf, src, (size_t)(base), (size_t)(n));   \
+    if (rc__ != CRANE_OK) return rc__;                             \
+  } while (0)
+
+// Appends the rows of `pd` to the device-resident pending table (rows keep job-id
+// order: the reference's pending map is a btree over job ids, JobScheduler.cpp:1092).
+int pending_append(crane_sched* h, const crane_pending_t* pd) {
+  const uint32_t base = h->n_pending, N = pd->n;
   if (N && (!pd->partition || !pd->time_limit || !pd->submit_time || !pd->node_num || !pd->ntasks ||
             !pd->ntasks_per_node_min || !pd->ntasks_per_node_max || !pd->exclusive || !pd->partition_priority ||
             !pd->qos_priority || !pd->account || !pd->req_node || !pd->req_task || !pd->req_total))
     return fail(h, CRANE_EINVAL, "pending: null column");
-  // ---- validation + alloc_off (prefix sum of node_num) --------------------
-  h->h_alloc_off.resize((size_t)N + 1);
-  uint64_t acc = 0;
-  uint32_t max_account = 0;
+  if ((uint64_t)base + N > 0xfffffff0ull) return fail(h, CRANE_EINVAL, "pending: too many rows");
+  // optional columns are all-or-nothing over the life of the table
+  if (base) {
+    if ((pd->qos != nullptr && pd->user != nullptr) != h->have_qos_cols || (pd->mandated_priority != nullptr) != h->have_mandated ||
+        (pd->reservation != nullptr) != h->have_pd_resv || (pd->incl_off != nullptr) != h->have_lists_incl ||
+        (pd->excl_off != nullptr) != h->have_lists_excl)
+      return fail(h, CRANE_EINVAL, "pending_append: optional columns (qos/user, mandated_priority, reservation, node lists) must match the table's");
+  } else {
+    h->have_qos_cols = pd->qos != nullptr && pd->user != nullptr;
+    h->have_mandated = pd->mandated_priority != nullptr;
+    h->have_pd_resv = pd->reservation != nullptr;
+    h->have_lists_incl = pd->incl_off != nullptr;
+    h->have_lists_excl = pd->excl_off != nullptr;
+    h->h_alloc_off.assign(1, 0);
+    h->h_incl_off.assign(1, 0);
+    h->h_excl_off.assign(1, 0);
+    h->h_pd_account.clear();
+    h->h_dead.clear();
+    h->n_dead = 0;
+  }
+  // ---- validation + alloc_off (prefix sum of node_num over all rows) -----------
+  uint64_t acc = h->h_alloc_off.back();
   for (uint32_t i = 0; i < N; ++i) {
-    h->h_alloc_off[i] = (uint32_t)acc;
     if (pd->node_num[i] == 0) return fail(h, CRANE_EINVAL, "pending[%u]: node_num == 0", i);
     if (pd->time_limit[i] < 1) return fail(h, CRANE_EINVAL, "pending[%u]: time_limit < 1", i);
     const uint32_t t = pd->ntasks_per_node_min[i], tmax = pd->ntasks_per_node_max[i];
@@ -560,59 +606,84 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
       return fail(h, CRANE_EINVAL, "pending[%u]: ntasks outside [node_num*ntpn_min, node_num*ntpn_max]", i);
     if (pd->req_node[i].cpu_raw < 0 || pd->req_task[i].cpu_raw < 0)
       return fail(h, CRANE_EINVAL, "pending[%u]: negative cpu request", i);
+    if (pd->account[i] > (1u << 24)) return fail(h, CRANE_EINVAL, "account ids must be dense (< 2^24)");
     acc += pd->node_num[i];
     if (acc > 0xfffffff0ull) return fail(h, CRANE_EINVAL, "pending: sum(node_num) overflows");
-    max_account = std::max(max_account, pd->account[i]);
   }
-  h->h_alloc_off[N] = (uint32_t)acc;
-  h->total_alloc = acc;
   if ((pd->incl_off && !pd->incl_nodes && pd->incl_off[N]) || (pd->excl_off && !pd->excl_nodes && pd->excl_off[N]))
     return fail(h, CRANE_EINVAL, "pending: node list CSR without node array");
   for (uint32_t i = 0; i < N; ++i)
     if ((pd->incl_off && pd->incl_off[i + 1] < pd->incl_off[i]) || (pd->excl_off && pd->excl_off[i + 1] < pd->excl_off[i]))
       return fail(h, CRANE_EINVAL, "pending[%u]: node list offsets are not monotonic", i);
-  for (uint32_t k = 0; k < R; ++k) max_account = std::max(max_account, rn->account[k]);
-  if (max_account > (1u << 24)) return fail(h, CRANE_EINVAL, "account ids must be dense (< 2^24)");
-  const uint32_t A = (N + R) ? max_account + 1 : 0;
-
-  // ---- pending columns -----------------------------------------------------
-  H2D(h->d_partition, pd->partition, N);
-  H2D(h->d_time_limit, pd->time_limit, N);
-  H2D(h->d_submit, pd->submit_time, N);
-  H2D(h->d_node_num, pd->node_num, N);
-  H2D(h->d_ntpn, pd->ntasks_per_node_min, N);
-  H2D(h->d_ntpn_max, pd->ntasks_per_node_max, N);
-  H2D(h->d_ntasks, pd->ntasks, N);
-  H2D(h->d_exclusive, pd->exclusive, N);
-  H2D(h->d_part_prio, pd->partition_priority, N);
-  H2D(h->d_qos_prio, pd->qos_priority, N);
-  H2D(h->d_account, pd->account, N);
-  h->have_qos_cols = pd->qos != nullptr && pd->user != nullptr;
-  if (h->have_qos_cols) {
-    H2D(h->d_qos, pd->qos, N);
-    H2D(h->d_user, pd->user, N);
-  }
-  h->have_mandated = pd->mandated_priority != nullptr;
-  if (h->have_mandated) H2D(h->d_mandated, pd->mandated_priority, N);
-  H2D(h->d_req_node, reinterpret_cast<const View*>(pd->req_node), N);
-  H2D(h->d_req_task, reinterpret_cast<const View*>(pd->req_task), N);
-  H2D(h->d_req_total, reinterpret_cast<const View*>(pd->req_total), N);
-  H2D(h->d_alloc_off, h->h_alloc_off.data(), N + 1);
-  h->have_pd_resv = pd->reservation != nullptr;
-  if (h->have_pd_resv) H2D(h->d_pd_resv, pd->reservation, N);
-  h->have_lists_incl = pd->incl_off != nullptr;
-  h->have_lists_excl = pd->excl_off != nullptr;
-  if (h->have_lists_incl) {
+  if (h->have_lists_incl)
     for (uint32_t k = 0; k < pd->incl_off[N]; ++k)
       if (pd->incl_nodes[k] >= h->n_nodes && pd->incl_nodes[k] != 0xFFFFFFFFu)  // 0xFFFFFFFF = a host the cluster does not know
         return fail(h, CRANE_EINVAL, "pending: included node out of range");
-    H2D(h->d_incl_off, pd->incl_off, N + 1);
-    H2D(h->d_incl_nodes, pd->incl_nodes, pd->incl_off[N]);
+  // ---- columns ----------------------------------------------------------------
+  H2D_AT(h->d_partition, pd->partition, base, N);
+  H2D_AT(h->d_time_limit, pd->time_limit, base, N);
+  H2D_AT(h->d_submit, pd->submit_time, base, N);
+  H2D_AT(h->d_node_num, pd->node_num, base, N);
+  H2D_AT(h->d_ntpn, pd->ntasks_per_node_min, base, N);
+  H2D_AT(h->d_ntpn_max, pd->ntasks_per_node_max, base, N);
+  H2D_AT(h->d_ntasks, pd->ntasks, base, N);
+  H2D_AT(h->d_exclusive, pd->exclusive, base, N);
+  H2D_AT(h->d_part_prio, pd->partition_priority, base, N);
+  H2D_AT(h->d_qos_prio, pd->qos_priority, base, N);
+  H2D_AT(h->d_account, pd->account, base, N);
+  if (h->have_qos_cols) {
+    H2D_AT(h->d_qos, pd->qos, base, N);
+    H2D_AT(h->d_user, pd->user, base, N);
+  }
+  if (h->have_mandated) H2D_AT(h->d_mandated, pd->mandated_priority, base, N);
+  H2D_AT(h->d_req_node, reinterpret_cast<const View*>(pd->req_node), base, N);
+  H2D_AT(h->d_req_task, reinterpret_cast<const View*>(pd->req_task), base, N);
+  H2D_AT(h->d_req_total, reinterpret_cast<const View*>(pd->req_total), base, N);
+  if (h->have_pd_resv) H2D_AT(h->d_pd_resv, pd->reservation, base, N);
+  {
+    std::vector<uint8_t> zeros(N, 0);
+    H2D_AT(h->d_dead, zeros.data(), base, N);
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  // host mirrors
+  for (uint32_t i = 0; i < N; ++i) {
+    h->h_alloc_off.push_back(h->h_alloc_off.back() + pd->node_num[i]);
+    h->h_pd_account.push_back(pd->account[i]);
+    h->h_dead.push_back(0);
+  }
+  H2D_AT(h->d_alloc_off, h->h_alloc_off.data() + base, base, (size_t)N + 1);
+  if (h->have_lists_incl) {
+    const uint32_t nb = h->h_incl_off.back();
+    for (uint32_t i = 0; i < N; ++i) h->h_incl_off.push_back(nb + pd->incl_off[i + 1]);
+    H2D_AT(h->d_incl_off, h->h_incl_off.data() + base, base, (size_t)N + 1);
+    H2D_AT(h->d_incl_nodes, pd->incl_nodes, nb, pd->incl_off[N]);
   }
   if (h->have_lists_excl) {
-    H2D(h->d_excl_off, pd->excl_off, N + 1);
-    H2D(h->d_excl_nodes, pd->excl_nodes, pd->excl_off[N]);
+    const uint32_t nb = h->h_excl_off.back();
+    for (uint32_t i = 0; i < N; ++i) h->h_excl_off.push_back(nb + pd->excl_off[i + 1]);
+    H2D_AT(h->d_excl_off, h->h_excl_off.data() + base, base, (size_t)N + 1);
+    H2D_AT(h->d_excl_nodes, pd->excl_nodes, nb, pd->excl_off[N]);
   }
+  CU(cudaStreamSynchronize(h->stream));
+  h->n_pending = base + N;
+  h->total_alloc = h->h_alloc_off.back();
+  return CRANE_OK;
+}
+
+// The running table of this tick + the work and output buffers for the resident pending table.
+int set_running(crane_sched* h, const crane_running_t* rn) {
+  const uint32_t N = h->n_pending;
+  const uint32_t R = rn ? rn->n : 0;
+  if (R && (!rn->start_time || !rn->end_time || !rn->node_num || !rn->partition_priority || !rn->qos_priority ||
+            !rn->account || !rn->view_cpu_raw || !rn->view_mem || !rn->alloc_off))
+    return fail(h, CRANE_EINVAL, "running: null column");
+  for (uint32_t j = 0; j < R; ++j)
+    if (rn->alloc_off[j + 1] < rn->alloc_off[j]) return fail(h, CRANE_EINVAL, "running: alloc_off is not monotonic");
+  uint32_t max_account = 0;
+  for (uint32_t i = 0; i < N; ++i) max_account = std::max(max_account, h->h_pd_account[i]);
+  for (uint32_t k = 0; k < R; ++k) max_account = std::max(max_account, rn->account[k]);
+  if (max_account > (1u << 24)) return fail(h, CRANE_EINVAL, "account ids must be dense (< 2^24)");
+  const uint32_t A = (N + R) ? max_account + 1 : 0;
 
   // ---- running jobs: columns + regrouping by node slot and by account ------
   // (flattening of RnJobInScheduler::allocated_res; order inside a node /
@@ -621,11 +692,9 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
   std::vector<uint8_t> acc_present(std::max<uint32_t>(A, 1), 0);
   std::vector<int64_t> slot_end;
   std::vector<Row> slot_res;
-  for (uint32_t i = 0; i < N; ++i) acc_present[pd->account[i]] = 1;
+  for (uint32_t i = 0; i < N; ++i)
+    if (!h->h_dead[i]) acc_present[h->h_pd_account[i]] = 1;
   if (R) {
-    if (!rn->start_time || !rn->end_time || !rn->node_num || !rn->partition_priority || !rn->qos_priority ||
-        !rn->account || !rn->view_cpu_raw || !rn->view_mem || !rn->alloc_off)
-      return fail(h, CRANE_EINVAL, "running: null column");
     const uint32_t E = rn->alloc_off[R];
     if (E && (!rn->alloc_node || !rn->alloc_res)) return fail(h, CRANE_EINVAL, "running: null allocation table");
     for (uint32_t j = 0; j < R; ++j) {
@@ -672,7 +741,6 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
   // staging vectors above are pageable: the copies have completed on return,
   // but make it explicit before they go out of scope
   CU(cudaStreamSynchronize(h->stream));
-  h->n_pending = N;
   h->n_running = R;
   h->n_accounts = A;
 
@@ -697,6 +765,81 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
   CU(h->d_out_node.ensure(ta));
   CU(h->d_out_ntasks.ensure(ta));
   CU(h->d_out_res.ensure(ta));
+  return CRANE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t crane_sched_pending_rows(const crane_sched_t* h) { return h ? h->n_pending : 0; }
+
+int crane_sched_pending_reset(crane_sched_t* h) {
+  if (!h) return CRANE_EINVAL;
+  h->n_pending = 0;
+  h->total_alloc = 0;
+  h->n_dead = 0;
+  h->h_alloc_off.assign(1, 0);
+  h->h_pd_account.clear();
+  h->h_dead.clear();
+  h->uploaded = false;
+  h->ran = false;
+  return CRANE_OK;
+}
+
+int crane_sched_pending_append(crane_sched_t* h, const crane_pending_t* rows, uint32_t* first_row) {
+  if (!h || !rows) return CRANE_EINVAL;
+  if (!h->have_cluster) return fail(h, CRANE_EINVAL, "pending_append: set_cluster first");
+  CU(cudaSetDevice(h->device));
+  h->uploaded = false;  // the running table and the work buffers follow with crane_sched_set_running
+  h->ran = false;
+  const uint32_t base = h->n_pending;
+  int rc = pending_append(h, rows);
+  if (rc != CRANE_OK) return rc;
+  if (first_row) *first_row = base;
+  return CRANE_OK;
+}
+
+int crane_sched_pending_erase(crane_sched_t* h, const uint32_t* rows, uint32_t n) {
+  if (!h || (n && !rows)) return CRANE_EINVAL;
+  CU(cudaSetDevice(h->device));
+  for (uint32_t k = 0; k < n; ++k)
+    if (rows[k] >= h->n_pending) return fail(h, CRANE_EINVAL, "pending_erase: row %u out of range", rows[k]);
+  h->uploaded = false;
+  h->ran = false;
+  if (!n) return CRANE_OK;
+  for (uint32_t k = 0; k < n; ++k)
+    if (!h->h_dead[rows[k]]) { h->h_dead[rows[k]] = 1; h->n_dead++; }
+  H2D(h->d_erase_rows, rows, n);
+  CRANE_LAUNCH(k_mark_dead, (n + 255) / 256, 256, 0, h->stream, h->d_erase_rows.p, n, h->d_dead.p);
+  CU(cudaStreamSynchronize(h->stream));
+  return CRANE_OK;
+}
+
+int crane_sched_set_running(crane_sched_t* h, const crane_running_t* rn) {
+  if (!h) return CRANE_EINVAL;
+  if (!h->have_cluster) return fail(h, CRANE_EINVAL, "set_running: set_cluster first");
+  CU(cudaSetDevice(h->device));
+  h->uploaded = false;
+  h->ran = false;
+  int rc = set_running(h, rn);
+  if (rc != CRANE_OK) return rc;
+  h->uploaded = true;
+  return CRANE_OK;
+}
+
+int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_pending_t* pd) {
+  if (!h || !pd) return CRANE_EINVAL;
+  if (!h->have_cluster) return fail(h, CRANE_EINVAL, "upload: set_cluster first");
+  CU(cudaSetDevice(h->device));
+  h->uploaded = false;  // a failed upload leaves nothing runnable behind
+  h->ran = false;
+  CU(cudaEventRecord(h->ev[0], h->stream));
+  crane_sched_pending_reset(h);
+  int rc = pending_append(h, pd);
+  if (rc != CRANE_OK) { crane_sched_pending_reset(h); return rc; }
+  rc = set_running(h, rn);
+  if (rc != CRANE_OK) return rc;
   CU(cudaEventRecord(h->ev[1], h->stream));
   h->uploaded = true;
   h->ran = false;
@@ -734,6 +877,7 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
   pd.excl_nodes = h->d_excl_nodes.p;
   pd.alloc_off = h->d_alloc_off.p;
   pd.reservation = h->have_pd_resv ? h->d_pd_resv.p : nullptr;
+  pd.dead = h->n_dead ? h->d_dead.p : nullptr;
 
   RunningDev rn{};
   rn.n = R;
@@ -834,8 +978,8 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
     CRANE_LAUNCH(k_priority, (N + 255) / 256, 256, 0, st, pd, pc, now, h->d_bounds.p, h->d_acc_service.p,
                  h->d_prio.p, h->d_keys_a.p, h->d_vals_a.p);
     h->timing.kernel_launches++;
-    if (pc.type != 0) {
-      int rc = radix_sort(h, N, 64, &keys, &vals);
+    if (pc.type != 0 || h->n_dead) {  // (FIFO keeps input order; erased rows only have to go behind the live ones)
+      int rc = radix_sort(h, N, pc.type != 0 ? 64 : 8, &keys, &vals);
       if (rc != CRANE_OK) return rc;
     }
     // keys2 go to the buffer not holding `vals`

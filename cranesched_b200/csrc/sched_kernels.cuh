@@ -60,6 +60,7 @@ struct PendingDev {  // SoA mirror of crane_pending_t
   const uint32_t* excl_nodes;
   const uint32_t* alloc_off;  // exclusive prefix sum of node_num
   const uint32_t* reservation;  // or null
+  const uint8_t* dead;          // erased rows of the device-resident table (or null): not in the queue
 };
 
 struct RunningDev {
@@ -233,6 +234,7 @@ __global__ void k_bounds(PendingDev pd, RunningDev rn, int64_t now, uint64_t max
                      nod_mn = ~0ull, nod_mx = 0, mem_mn = ~0ull, mem_mx = 0, cpu_mn = ~0ull, cpu_mx = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     unsigned long long qos, part, nodes, mem, cpu;
+    if (i < pd.n && pd.dead && pd.dead[i]) continue;
     if (i < pd.n) {
       unsigned long long age = (unsigned long long)(now - pd.submit_time[i]);
       if (age > max_age) age = max_age;
@@ -366,7 +368,7 @@ __global__ void k_priority(PendingDev pd, PrioCfg cfg, int64_t now, const Bounds
   // order because the LSD sort is stable (deviation D2). BasicPriority: key 0.
   uint64_t bits = (uint64_t)__double_as_longlong(p);
   uint64_t orderable = (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
-  key_out[i] = cfg.type == 0 ? 0ull : ~orderable;
+  key_out[i] = (pd.dead && pd.dead[i]) ? (cfg.type == 0 ? 1ull : ~0ull) : (cfg.type == 0 ? 0ull : ~orderable);  // erased rows sort last
   idx_out[i] = i;
 }
 
@@ -485,7 +487,11 @@ __global__ void k_queue_keys(PendingDev pd, const uint32_t* order, const double*
     p = cl.n_parts + rv;
   }
   uint64_t k = 0;
-  if (r >= limit) {
+  if (pd.dead && pd.dead[j]) {
+    reason = CRANE_REASON_ERASED;
+    found = false;
+    k = (uint64_t)cl.n_vparts + 1;
+  } else if (r >= limit) {
     reason = CRANE_REASON_PRIORITY;
     k = (uint64_t)cl.n_vparts + 1;
   } else if (!found) {
@@ -693,6 +699,11 @@ __global__ void k_feas_bitmap(ClusterDev cl, PendingDev pd, const JobQ* jobq, co
       if (lane == 0) bitmap[(size_t)r * words_per_row + w] = word;
     }
   }
+}
+
+__global__ void k_mark_dead(const uint32_t* rows, uint32_t n, uint8_t* dead) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) dead[rows[k]] = 1;
 }
 
 // One queue over several GPUs: the placement columns of jobs another rank owns

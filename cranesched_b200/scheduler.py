@@ -63,6 +63,16 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.crane_sched_qos_filter.argtypes = [C.c_void_p, P(abi.QosTableC), C.c_void_p]
     lib.crane_sched_set_reservations.restype = C.c_int
     lib.crane_sched_set_reservations.argtypes = [C.c_void_p, P(abi.ReservationsC)]
+    lib.crane_sched_pending_reset.restype = C.c_int
+    lib.crane_sched_pending_reset.argtypes = [C.c_void_p]
+    lib.crane_sched_pending_append.restype = C.c_int
+    lib.crane_sched_pending_append.argtypes = [C.c_void_p, P(abi.PendingC), P(C.c_uint32)]
+    lib.crane_sched_pending_erase.restype = C.c_int
+    lib.crane_sched_pending_erase.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.crane_sched_set_running.restype = C.c_int
+    lib.crane_sched_set_running.argtypes = [C.c_void_p, P(abi.RunningC)]
+    lib.crane_sched_pending_rows.restype = C.c_uint32
+    lib.crane_sched_pending_rows.argtypes = [C.c_void_p]
     lib.crane_sched_set_shard.restype = C.c_int
     lib.crane_sched_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.crane_sched_device_placements.restype = C.c_int
@@ -76,7 +86,8 @@ def load_library(path: str | None = None) -> C.CDLL:
 
 
 EXPORTS = ("crane_sched_create", "crane_sched_destroy", "crane_sched_last_error",
-           "crane_sched_set_cluster", "crane_sched_set_reservations", "crane_sched_node_select", "crane_sched_upload",
+           "crane_sched_set_cluster", "crane_sched_set_reservations", "crane_sched_node_select", "crane_sched_upload", "crane_sched_pending_reset", "crane_sched_pending_append", "crane_sched_pending_erase",
+           "crane_sched_set_running", "crane_sched_pending_rows",
            "crane_sched_run", "crane_sched_fetch", "crane_sched_sync", "crane_sched_get_timing",
            "crane_sched_qos_filter", "crane_sched_set_shard", "crane_sched_device_placements",
            "crane_sched_debug_bitmap", "crane_sched_debug_profile")
@@ -133,6 +144,27 @@ class GpuScheduler:
         c_rn, c_pd = running.as_c(), pending.as_c()
         self._keep = [running, pending]
         self._check(self._lib.crane_sched_upload(self._h, C.byref(c_rn), C.byref(c_pd)))
+
+    # --- the pending table resident on the device across ticks ---------------------
+    def pending_reset(self):
+        self._check(self._lib.crane_sched_pending_reset(self._h))
+
+    def pending_append(self, rows: abi.Pending) -> int:
+        """Submit (JobScheduler.cpp:4254): returns the index of the first new row."""
+        c, first = rows.as_c(), C.c_uint32(0)
+        self._check(self._lib.crane_sched_pending_append(self._h, C.byref(c), C.byref(first)))
+        return first.value
+
+    def pending_erase(self, rows):
+        r = np.ascontiguousarray(rows, np.uint32)
+        self._check(self._lib.crane_sched_pending_erase(self._h, r.ctypes.data, len(r)))
+
+    def set_running(self, running: abi.Running):
+        c = running.as_c()
+        self._check(self._lib.crane_sched_set_running(self._h, C.byref(c)))
+
+    def pending_rows(self) -> int:
+        return int(self._lib.crane_sched_pending_rows(self._h))
 
     def run(self, now: int):
         self._check(self._lib.crane_sched_run(self._h, now))

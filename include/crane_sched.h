@@ -195,6 +195,7 @@ enum {
   CRANE_REASON_QOS_MEM = 19,       /* "QosMemResourceLimit"                   */
   CRANE_REASON_QOS_GRES = 20,      /* "QosGresResourceLimit"                  */
   CRANE_REASON_QOS_INVALID = 21,   /* "InvalidQOS"                            */
+  CRANE_REASON_ERASED = 255,       /* a row removed with crane_sched_pending_erase */
 };
 
 /* The fields NodeSelect writes into PdJobInScheduler (JobScheduler.h:116-132).
@@ -265,6 +266,23 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* running,
                        const crane_pending_t* pending);
 int crane_sched_run(crane_sched_t* h, int64_t now);
 int crane_sched_fetch(crane_sched_t* h, crane_placements_t* out);
+
+/* The pending table kept resident on the device across ticks:
+ * the reference rebuilds its PdJobInScheduler vector from the pending map every
+ * tick (JobScheduler.cpp:1090-1113); here a submit appends its row(s)
+ * (JobScheduler.cpp:4254), a start or cancel erases its row, and a tick is
+ *     crane_sched_set_running(h, running); crane_sched_run(h, now); crane_sched_fetch(h, out)
+ * without any H2D of pending jobs. Rows keep their indices (outputs are indexed
+ * by row; `out` must be sized for crane_sched_pending_rows(h) rows and the sum of
+ * node_num over ALL rows); an erased row reports CRANE_REASON_ERASED and takes
+ * part in nothing (priority bounds, batch limit, queue). Rows must arrive in
+ * job-id order (equal priorities keep row order). crane_sched_upload ==
+ * pending_reset; pending_append; set_running. Re-upload to compact. */
+int crane_sched_pending_reset(crane_sched_t* h);
+int crane_sched_pending_append(crane_sched_t* h, const crane_pending_t* rows, uint32_t* first_row);
+int crane_sched_pending_erase(crane_sched_t* h, const uint32_t* rows, uint32_t n);
+int crane_sched_set_running(crane_sched_t* h, const crane_running_t* running);
+uint32_t crane_sched_pending_rows(const crane_sched_t* h);
 
 /* Blocks until the handle's stream is idle; *run_ms (optional) receives the
  * device time of the last crane_sched_run (CUDA events on that stream). */

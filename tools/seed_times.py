@@ -5,7 +5,7 @@ import numpy as np
 from cranesched_b200 import synth, sharding
 from cranesched_b200.scheduler import GpuScheduler
 for rank in range(8):
-    cfg, cl, rn, pd, now = sharding.shard_workload(2, rank, 8)
+    cfg, cl, rn, pd, now = sharding.shard_workload(2, rank, 8)  # seed 1000*rank + 2
     s = GpuScheduler(cfg, 0); s.set_cluster(cl)
     out = s.node_select(now, rn, pd); out = s.node_select(now, rn, pd)
     t = s.timing(); s.close()
