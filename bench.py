@@ -304,7 +304,7 @@ def main():
                      "wall_ms_per_step_incl_flush": wall_ms / args.steps, "clocks": clk})
     else:
         # ---- ONE queue over `world` GPUs: partitions dealt to the ranks ------------
-        owner = sharding.deal_partitions(pd, cl.n_partitions, world)
+        owner = sharding.deal_partitions(pd, cl.n_partitions, world, cl)
         sched = GpuScheduler(cfg, local_rank)
         sched.set_cluster(cl)
         out = abi.Placements.for_pending(pd, pinned=True)

@@ -219,6 +219,7 @@ class TimingC(C.Structure):
         ("d2h_ms", C.c_float),
         ("total_ms", C.c_float),
         ("kernel_launches", C.c_uint32),
+        ("qos_ms", C.c_float),
     ]
 
 

@@ -11,6 +11,17 @@ namespace crane_b200 {
 
 namespace {
 const char* kReasonString[] = {"", "Priority", "Resource", "Resource Reserved", "Partition Not Found"};
+const char* QosReasonString(uint8_t code) {
+  switch (code) {
+    case CRANE_REASON_QOS_CPU: return "QosCpuResourceLimit";
+    case CRANE_REASON_QOS_JOBS: return "QosJobsResourceLimit";
+    case CRANE_REASON_QOS_WALL: return "QosWallTimeLimit";
+    case CRANE_REASON_QOS_MEM: return "QosMemResourceLimit";
+    case CRANE_REASON_QOS_GRES: return "QosGresResourceLimit";
+    case CRANE_REASON_QOS_INVALID: return "InvalidQOS";
+    default: return nullptr;
+  }
+}
 }
 
 struct SchedulerAlgo::Impl {
@@ -70,6 +81,64 @@ struct SchedulerAlgo::Impl {
       for (uint32_t b = 0; b < CRANE_MAX_SLOTS; ++b)
         if (o.gres[e] >> b & 1) r.gres[gres_entries[e].first][gres_entries[e].second].insert(node_slots[node][e][b]);
     return r;
+  }
+  // a max_tres map of struct Qos: counts + which names / types are listed at all
+  crane_tres_limit_t ToLimit(const ResourceView& v) const {
+    crane_tres_limit_t L;
+    memset(&L, 0, sizeof L);
+    L.view.cpu_raw = v.cpu_count_raw;
+    L.view.mem = v.memory_bytes;
+    L.view.mem_sw = v.memory_sw_bytes;
+    for (const auto& [name, gc] : v.gres_map) {
+      auto nit = gres_name_id.find(name);
+      if (nit == gres_name_id.end()) continue;  // a name no node offers: no job can ask for it
+      L.gres_name_present |= (uint8_t)(1u << nit->second);
+      L.view.gres_total[nit->second] = (uint16_t)std::min<uint64_t>(gc.total, 0xFFFF);
+      for (const auto& [type, cnt] : gc.specified) {
+        auto eit = gres_entry_id.find({name, type});
+        if (eit == gres_entry_id.end()) continue;
+        L.gres_spec_present |= (uint8_t)(1u << eit->second);
+        L.view.gres_spec[eit->second] = (uint16_t)std::min<uint64_t>(cnt, 0xFFFF);
+      }
+    }
+    return L;
+  }
+  crane_meta_resource_t ToMeta(const MetaResource& r) const {
+    crane_meta_resource_t o;
+    memset(&o, 0, sizeof o);
+    o.cpu_raw = r.resource.cpu_count_raw;
+    o.mem = r.resource.memory_bytes;
+    o.mem_sw = r.resource.memory_sw_bytes;
+    for (const auto& [name, gc] : r.resource.gres_map) {
+      auto nit = gres_name_id.find(name);
+      if (nit == gres_name_id.end()) continue;
+      o.gres_total[nit->second] = (uint32_t)gc.total;
+      for (const auto& [type, cnt] : gc.specified) {
+        auto eit = gres_entry_id.find({name, type});
+        if (eit != gres_entry_id.end()) o.gres_spec[eit->second] = (uint32_t)cnt;
+      }
+    }
+    o.jobs_count = r.jobs_count;
+    o.wall_time = r.wall_time;
+    return o;
+  }
+  void FromMeta(const crane_meta_resource_t& o, MetaResource& r) const {
+    r.resource.cpu_count_raw = o.cpu_raw;
+    r.resource.memory_bytes = o.mem;
+    r.resource.memory_sw_bytes = o.mem_sw;
+    for (const auto& [name, g] : gres_name_id) {
+      uint64_t any = o.gres_total[g];
+      for (uint32_t e = 0; e < gres_entries.size(); ++e)
+        if (gres_entries[e].first == name) any |= o.gres_spec[e];
+      if (!any && !r.resource.gres_map.count(name)) continue;
+      GresCount& gc = r.resource.gres_map[name];
+      gc.total = o.gres_total[g];
+      for (uint32_t e = 0; e < gres_entries.size(); ++e)
+        if (gres_entries[e].first == name && (o.gres_spec[e] || gc.specified.count(gres_entries[e].second)))
+          gc.specified[gres_entries[e].second] = o.gres_spec[e];
+    }
+    r.jobs_count = o.jobs_count;
+    r.wall_time = o.wall_time;
   }
   crane_res_view_t ToView(const ResourceView& v) const {
     crane_res_view_t o;
@@ -341,6 +410,90 @@ void SchedulerAlgo::NodeSelect(int64_t now, const std::vector<std::unique_ptr<Rn
       j.allocated_res.emplace(id, m.FromRow(o_node[k], o_res[k]));
     }
   }
+}
+
+void SchedulerAlgo::CheckAndMallocQosResource(const std::map<std::string, Qos>& qos_table, QosUsage& usage,
+                                              const std::vector<std::unique_ptr<PdJobInScheduler>>& pending_jobs) {
+  Impl& m = *m_;
+  const uint32_t N = (uint32_t)pending_jobs.size();
+  // account chains (PdJobInScheduler::account_chain); parents the jobs themselves never name get ids now
+  std::vector<uint32_t> chain_off(N + 1, 0), chain;
+  for (uint32_t i = 0; i < N; ++i) {
+    for (const auto& a : pending_jobs[i]->account_chain) chain.push_back(m.Intern(m.account_id, a));
+    chain_off[i + 1] = (uint32_t)chain.size();
+  }
+  // the qos / user ids are the ones NodeSelect uploaded with the pending table
+  const uint32_t Q = (uint32_t)m.qos_id.size(), U = (uint32_t)m.user_id.size(), A = (uint32_t)m.account_id.size();
+  if (N == 0 || Q == 0) return;
+  std::vector<std::string> qos_name(Q), user_name(U), acct_name(A);
+  for (const auto& [s, id] : m.qos_id) qos_name[id] = s;
+  for (const auto& [s, id] : m.user_id) user_name[id] = s;
+  for (const auto& [s, id] : m.account_id) acct_name[id] = s;
+  std::vector<uint8_t> valid(Q, 0);
+  std::vector<uint32_t> mju(Q, 0), mja(Q, 0), mj(Q, 0);
+  std::vector<int64_t> mcpu(Q, 0), mwall(Q, 0);
+  std::vector<crane_tres_limit_t> tu(Q), ta(Q), tq(Q);
+  memset(tu.data(), 0, sizeof(crane_tres_limit_t) * Q);
+  memset(ta.data(), 0, sizeof(crane_tres_limit_t) * Q);
+  memset(tq.data(), 0, sizeof(crane_tres_limit_t) * Q);
+  for (uint32_t q = 0; q < Q; ++q) {
+    auto it = qos_table.find(qos_name[q]);
+    if (it == qos_table.end() || it->second.deleted) continue;  // GetExistedQosInfo fails: "InvalidQOS"
+    const Qos& s = it->second;
+    valid[q] = 1;
+    mju[q] = s.max_jobs_per_user; mja[q] = s.max_jobs_per_account; mj[q] = s.max_jobs;
+    mcpu[q] = s.max_cpus_per_user_raw; mwall[q] = s.max_wall;
+    tu[q] = m.ToLimit(s.max_tres_per_user); ta[q] = m.ToLimit(s.max_tres_per_account); tq[q] = m.ToLimit(s.max_tres);
+  }
+  // dense usage tables; what the maps do not hold is zero
+  std::vector<crane_meta_resource_t> uu((size_t)U * Q), au((size_t)A * Q), qu(Q);
+  memset(uu.data(), 0, uu.size() * sizeof(crane_meta_resource_t));
+  memset(au.data(), 0, au.size() * sizeof(crane_meta_resource_t));
+  memset(qu.data(), 0, qu.size() * sizeof(crane_meta_resource_t));
+  auto load = [&](const std::map<std::string, std::map<std::string, MetaResource>>& src,
+                  const std::unordered_map<std::string, uint32_t>& ids, std::vector<crane_meta_resource_t>& dst) {
+    for (const auto& [key, per_qos] : src) {
+      auto kit = ids.find(key);
+      if (kit == ids.end()) continue;  // nobody in this queue touches it
+      for (const auto& [qn, r] : per_qos) {
+        auto qit = m.qos_id.find(qn);
+        if (qit != m.qos_id.end()) dst[(size_t)kit->second * Q + qit->second] = m.ToMeta(r);
+      }
+    }
+  };
+  load(usage.user, m.user_id, uu);
+  load(usage.account, m.account_id, au);
+  for (const auto& [qn, r] : usage.qos) {
+    auto qit = m.qos_id.find(qn);
+    if (qit != m.qos_id.end()) qu[qit->second] = m.ToMeta(r);
+  }
+  const std::vector<crane_meta_resource_t> uu0 = uu, au0 = au, qu0 = qu;
+
+  crane_qos_table_t t;
+  memset(&t, 0, sizeof t);
+  t.n_qos = Q; t.n_users = U; t.n_accounts = A;
+  t.valid = valid.data();
+  t.max_jobs_per_user = mju.data(); t.max_jobs_per_account = mja.data(); t.max_jobs = mj.data();
+  t.max_cpus_per_user_raw = mcpu.data(); t.max_wall = mwall.data();
+  t.max_tres_per_user = tu.data(); t.max_tres_per_account = ta.data(); t.max_tres = tq.data();
+  t.chain_off = chain_off.data(); t.chain_acct = chain.data();
+  t.user_usage = uu.data(); t.account_usage = au.data(); t.qos_usage = qu.data();
+  std::vector<uint8_t> reason(N);
+  int rc = crane_sched_qos_filter(m.h, &t, reason.data());
+  if (rc != CRANE_OK) throw std::runtime_error(std::string("crane_sched_qos_filter: ") + crane_sched_last_error(m.h));
+
+  for (uint32_t i = 0; i < N; ++i)
+    if (const char* why = QosReasonString(reason[i])) pending_jobs[i]->reason = why;
+  // usage back into the maps: only the entries the pass changed
+  auto store = [&](const std::vector<crane_meta_resource_t>& now_, const std::vector<crane_meta_resource_t>& before,
+                   const std::vector<std::string>& names, std::map<std::string, std::map<std::string, MetaResource>>& dst) {
+    for (size_t k = 0; k < now_.size(); ++k)
+      if (memcmp(&now_[k], &before[k], sizeof(crane_meta_resource_t)) != 0) m.FromMeta(now_[k], dst[names[k / Q]][qos_name[k % Q]]);
+  };
+  store(uu, uu0, user_name, usage.user);
+  store(au, au0, acct_name, usage.account);
+  for (uint32_t q = 0; q < Q; ++q)
+    if (memcmp(&qu[q], &qu0[q], sizeof(crane_meta_resource_t)) != 0) m.FromMeta(qu[q], usage.qos[qos_name[q]]);
 }
 
 }  // namespace crane_b200

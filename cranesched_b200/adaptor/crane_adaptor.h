@@ -125,6 +125,37 @@ struct PriorityConfig {
   uint32_t WeightAge{1000}, WeightFairShare{0}, WeightJobSize{0}, WeightPartition{0}, WeightQoS{0};
 };
 
+// Qos (Account/AccountDefs.h:27-50): the limits CheckQosResource_ reads
+// (AccountMetaContainer.cpp:382-491). A gres name / type absent from a max_tres
+// map is unlimited, as upstream.
+struct Qos {
+  bool deleted{false};
+  uint32_t max_jobs_per_user{UINT32_MAX};
+  uint32_t max_jobs_per_account{UINT32_MAX};
+  uint32_t max_jobs{UINT32_MAX};
+  int64_t max_cpus_per_user_raw{INT64_MAX};
+  int64_t max_wall{0};  // seconds; 0 = unlimited
+  ResourceView max_tres{INT64_MAX, UINT64_MAX, UINT64_MAX, {}};
+  ResourceView max_tres_per_user{INT64_MAX, UINT64_MAX, UINT64_MAX, {}};
+  ResourceView max_tres_per_account{INT64_MAX, UINT64_MAX, UINT64_MAX, {}};
+};
+
+// MetaResource (Accounting/AccountMetaContainer.h:30-47) without the submit counter
+// (CheckAndMallocQosResource does not touch it)
+struct MetaResource {
+  ResourceView resource;
+  uint32_t jobs_count{0};
+  int64_t wall_time{0};
+};
+
+// the usage maps of AccountMetaContainer (AccountMetaContainer.h:52-75):
+// user -> qos, account -> qos, qos. An entry that is missing reads as zero.
+struct QosUsage {
+  std::map<std::string, std::map<std::string, MetaResource>> user;
+  std::map<std::string, std::map<std::string, MetaResource>> account;
+  std::map<std::string, MetaResource> qos;
+};
+
 class SchedulerAlgo {
  public:
   SchedulerAlgo(const PriorityConfig& prio, uint32_t scheduled_batch_size, int device = 0);
@@ -144,6 +175,17 @@ class SchedulerAlgo {
   // on invariant violations, Logger.h:114-123).
   void NodeSelect(int64_t now, const std::vector<std::unique_ptr<RnJobInScheduler>>& running_jobs,
                   const std::vector<std::unique_ptr<PdJobInScheduler>>& pending_jobs);
+
+  // Replaces the AccountMetaContainer::CheckAndMallocQosResource call the commit
+  // loop makes for every job NodeSelect starts now (JobScheduler.cpp:1262;
+  // AccountMetaContainer.cpp:164-191), for the whole vector at once and in its
+  // order: a job over a limit keeps pending with the reference's reason string
+  // ("QosCpuResourceLimit", "QosJobsResourceLimit", "QosWallTimeLimit",
+  // "QosMemResourceLimit", "QosGresResourceLimit", "InvalidQOS"), every other
+  // started job is added to `usage` at its user, account-chain and qos levels.
+  // Call right after NodeSelect with the same pending_jobs.
+  void CheckAndMallocQosResource(const std::map<std::string, Qos>& qos_table, QosUsage& usage,
+                                 const std::vector<std::unique_ptr<PdJobInScheduler>>& pending_jobs);
 
  private:
   struct Impl;

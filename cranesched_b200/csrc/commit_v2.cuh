@@ -79,22 +79,31 @@ struct Smem2 {
   uint16_t* list;               // = tmp: picks of the one-job path
   uint8_t* skip;                // [mp]  timeline at the size cap (JobScheduler.cpp:5230)
   uint8_t* cls;                 // [mp]  res_total class
+  uint8_t* memb;                // [mp]  bit p: the node belongs to partition p of this scheduler (only with several)
   uint32_t nblk, ring;
 };
-__host__ __device__ inline size_t commit2_fixed_bytes(uint32_t mp, bool gres) {
+constexpr int kMaxCompParts = 8;   // partitions of one scheduler that share nodes (one NodeState, several LocalSchedulers)
+// shared memory of the order of one MORE partition over the same nodes: cost, bounds, ord, tmp, posn
+__host__ __device__ inline size_t commit2_extra_bytes(uint32_t mp) {
   const size_t nblk = (mp + kBlk - 1) / kBlk;
-  return (size_t)mp * 8 * (gres ? 3 : 2) + nblk * 8 * 3 + ((size_t)mp + 4) * 4 + (size_t)mp * 2 * 4 + (size_t)mp * 2 + 256;
+  return (((size_t)mp * 8 + nblk * 8 * 3 + (size_t)mp * 2 * 3) + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t commit2_fixed_bytes(uint32_t mp, bool gres, uint32_t nparts = 1) {
+  const size_t nblk = (mp + kBlk - 1) / kBlk;
+  size_t b = (size_t)mp * 8 * (gres ? 3 : 2) + nblk * 8 * 3 + ((size_t)mp + 4) * 4 + (size_t)mp * 2 * 4 + (size_t)mp * 2 + 256;
+  if (nparts > 1) b += 16 + (nparts - 1) * commit2_extra_bytes(mp) + mp;  // + membership byte per node
+  return b;
 }
 // ring slots that fit next to a partition of mp nodes (0 = the partition does not fit)
-__host__ __device__ inline uint32_t commit2_ring_slots(uint32_t mp, uint32_t words, bool gres, size_t budget) {
-  const size_t fixed = commit2_fixed_bytes(mp, gres);
+__host__ __device__ inline uint32_t commit2_ring_slots(uint32_t mp, uint32_t words, bool gres, size_t budget, uint32_t nparts = 1) {
+  const size_t fixed = commit2_fixed_bytes(mp, gres, nparts);
   if (fixed >= budget) return 0;
   size_t r = (budget - fixed) / ((size_t)words * 4);
   if (r > (size_t)kRingMax) r = kRingMax;
   return r >= (size_t)kMaxJ + 4 ? (uint32_t)r : 0u;
 }
-__host__ __device__ inline size_t commit2_smem_bytes(uint32_t mp, uint32_t words, bool gres, uint32_t ring) {
-  return commit2_fixed_bytes(mp, gres) + (size_t)ring * words * 4;
+__host__ __device__ inline size_t commit2_smem_bytes(uint32_t mp, uint32_t words, bool gres, uint32_t ring, uint32_t nparts = 1) {
+  return commit2_fixed_bytes(mp, gres, nparts) + (size_t)ring * words * 4;
 }
 
 // ---- groups of 8 lanes ---------------------------------------------------------
@@ -280,7 +289,7 @@ __device__ __forceinline__ uint32_t g_update(TlEntry* E, uint32_t n, int64_t sta
 extern __shared__ __align__(16) unsigned char crane_dyn_smem2[];
 #define CRANE_DYN_BASE() (crane_dyn_smem2)
 #endif
-__device__ __forceinline__ Smem2 smem2_layout(uint32_t mp, uint32_t words, uint32_t ring, bool gres) {
+__device__ __forceinline__ Smem2 smem2_layout(uint32_t mp, uint32_t words, uint32_t ring, bool gres, uint32_t nparts = 1, uint32_t part = 0) {
   Smem2 sm;
   sm.nblk = (mp + kBlk - 1) / kBlk;
   sm.ring = ring;
@@ -302,6 +311,25 @@ __device__ __forceinline__ Smem2 smem2_layout(uint32_t mp, uint32_t words, uint3
   sm.list = sm.tmp;  // the one-job path's picks: consumed before the re-key writes tmp
   sm.skip = ptr; ptr += mp;
   sm.cls = ptr; ptr += mp;
+  sm.memb = nullptr;
+  if (nparts > 1) {
+    // overlapping partitions: one order per partition over the same node states
+    // (NodeSelector per LocalScheduler, JobScheduler.cpp:5757-5762); partition 0 uses
+    // the arrays above, every further one a block of its own
+    ptr += (16u - (uint32_t)(reinterpret_cast<uintptr_t>(ptr) & 15u)) & 15u;
+    if (part > 0) {
+      unsigned char* x = ptr + (size_t)(part - 1) * commit2_extra_bytes(mp);
+      sm.cost = reinterpret_cast<double*>(x); x += (size_t)mp * 8;
+      sm.bmax_cpu = reinterpret_cast<long long*>(x); x += (size_t)sm.nblk * 8;
+      sm.bmax_cpug = reinterpret_cast<long long*>(x); x += (size_t)sm.nblk * 8;
+      sm.bmax_g = reinterpret_cast<unsigned long long*>(x); x += (size_t)sm.nblk * 8;
+      sm.ord = reinterpret_cast<uint16_t*>(x); x += (size_t)mp * 2;
+      sm.tmp = reinterpret_cast<uint16_t*>(x); x += (size_t)mp * 2;
+      sm.posn = reinterpret_cast<uint16_t*>(x);
+      sm.list = sm.tmp;
+    }
+    sm.memb = ptr + (size_t)(nparts - 1) * commit2_extra_bytes(mp);
+  }
   return sm;
 }
 
@@ -340,6 +368,8 @@ struct Commit2Args {
   const View* req_node;       // pending.req_node / req_task (general task distribution only)
   const View* req_task;
   const uint32_t* part_list;  // partitions this launch commits (one CTA each), or null = all
+  const uint32_t* sched_nparts;  // [n_vparts] partitions per scheduler
+  const uint8_t* slot_memb;      // [n_slots] bit p: the node is in partition p of its scheduler
   unsigned long long* prof;
 };
 
@@ -349,13 +379,19 @@ struct Ctx2 {           // per-CTA constants
   PlaceDev out;
   int64_t now, max_window;
   uint32_t base, mp, words, max_jobs, ring, gres, dslot, cost_policy, part;
+  uint32_t ncp;   // partitions of this scheduler (1, or the partitions of a connected component of overlapping ones)
+  uint32_t npos;  // positions of the current partition's order (= mp with one partition)
   const View* req_node;
   const View* req_task;
 };
 #define C_DICT2 (c_dicts[s2_cx.dslot])
-#define SM2() smem2_layout(s2_cx.mp, s2_cx.words, s2_cx.ring, s2_cx.gres != 0)
+#define SM2() smem2_layout(s2_cx.mp, s2_cx.words, s2_cx.ring, s2_cx.gres != 0, s2_cx.ncp, s2_cx.ncp > 1 ? s2_curp : 0u)
+// the arrays every partition of a scheduler shares (node summaries), and all arrays of a scheduler with one partition
+#define SM2S() smem2_layout(s2_cx.mp, s2_cx.words, s2_cx.ring, s2_cx.gres != 0)
 
 __shared__ Ctx2 s2_cx;
+__shared__ uint32_t s2_curp;                   // partition of the job in hand (schedulers with several)
+__shared__ uint32_t s2_mcount[kMaxCompParts];  // members per partition
 __shared__ JobQ s2_jobs[kRingMax];
 __shared__ __align__(8) uint64_t s2_bar[kRingMax];
 __shared__ Row s2_classrow[kMaxClasses];
@@ -382,12 +418,12 @@ __shared__ long long s2_gmax_cpu, s2_gmax_cpug;  // maxima over all blocks
 __shared__ unsigned long long s2_gmax_g;
 
 __device__ __forceinline__ Row node_total2(uint32_t q) {
-  const uint8_t c = SM2().cls[q];
+  const uint8_t c = SM2S().cls[q];
   if (c != 0xff) return s2_classrow[c];
   return s2_cx.cl.slot_total[s2_cx.base + q];
 }
 __device__ __forceinline__ int64_t node_total_cpu2(uint32_t q) {
-  const uint8_t c = SM2().cls[q];
+  const uint8_t c = SM2S().cls[q];
   if (c != 0xff) return s2_classrow[c].cpu_raw;
   return s2_cx.cl.slot_total[s2_cx.base + q].cpu_raw;
 }
@@ -494,9 +530,9 @@ __device__ __forceinline__ void select2(const Smem2& sm, uint32_t mp, const JSel
 
 // MinCpuTimeRatioFirst::UpdateCost (JobScheduler.h:46-52): cost the node gets
 // when the job is placed on it
-__device__ __forceinline__ double new_cost2(const JobQ& jq, uint32_t q) {
+__device__ __forceinline__ double new_cost2(const JobQ& jq, uint32_t q, const double* cost) {
   const int64_t tot_cpu = node_total_cpu2(q);
-  return __dadd_rn(SM2().cost[q], cost_step(s2_cx.cost_policy, jq.time_limit, (jq.flags & 1u) ? tot_cpu : jq.req.cpu_raw, tot_cpu));
+  return __dadd_rn(cost[q], cost_step(s2_cx.cost_policy, jq.time_limit, (jq.flags & 1u) ? tot_cpu : jq.req.cpu_raw, tot_cpu));
 }
 
 // block-wide exclusive prefix over one value per thread (kT2 threads)
@@ -526,7 +562,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t& total)
 // block), then the maxima over all blocks
 __device__ __noinline__ void bounds_recompute2(uint32_t b_first, uint32_t b_last) {
   const Smem2 sm = SM2();
-  const uint32_t mp = s2_cx.mp, gl = g_lane();
+  const uint32_t mp = s2_cx.npos, gl = g_lane();  // positions of the current order
   const uint32_t nb = b_last >= sm.nblk ? sm.nblk : b_last + 1;
   for (uint32_t b0 = b_first; b0 < nb; b0 += kNG) {  // uniform trip count over the CTA
     const uint32_t b = b0 + g_index();
@@ -580,10 +616,13 @@ __device__ __noinline__ void bounds_recompute2(uint32_t b_first, uint32_t b_last
 __device__ __noinline__ void order_sort2() {
   const Smem2 sm = SM2();
   const uint32_t mp = s2_cx.mp;
+  const uint32_t bit = s2_cx.ncp > 1 ? 1u << s2_curp : 0u;  // several partitions: only this one's members are ordered
   for (uint32_t q = threadIdx.x; q < mp; q += kT2) {
+    if (bit && !(sm.memb[q] & bit)) { sm.posn[q] = 0xffffu; continue; }
     const double c = sm.cost[q];
     uint32_t rank = 0;
     for (uint32_t o = 0; o < mp; ++o) {
+      if (bit && !(sm.memb[o] & bit)) continue;
       const double co = sm.cost[o];
       rank += (co < c || (co == c && o < q)) ? 1u : 0u;
     }
@@ -604,7 +643,7 @@ __device__ __noinline__ void order_sort2() {
 // (survivors before its lower bound) + (its rank among the new keys).
 __device__ __noinline__ void order_rekey2(uint32_t cnt, uint32_t nthr) {
   const Smem2 sm = SM2();
-  const uint32_t mp = s2_cx.mp, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+  const uint32_t mp = s2_cx.npos, tid = threadIdx.x, lane = lane_id(), wid = warp_id();  // positions of the current order
   if (cnt == 0) return;
   const uint32_t ngr = nthr / kGL, nwp = nthr / 32;  // the first nthr threads of the CTA take part (named barrier 1)
   if (tid == 0) { s2_pmin = mp; s2_pmax = 0; }
@@ -718,7 +757,7 @@ __device__ __noinline__ void order_rekey2(uint32_t cnt, uint32_t nthr) {
 }
 // bounds of the blocks a re-key touched (all threads, after order_rekey2)
 __device__ __forceinline__ void rekey_bounds2(uint32_t cnt) {
-  if (cnt) bounds_recompute2(s2_pmin / kBlk, (s2_pmax < s2_cx.mp ? s2_pmax : s2_cx.mp - 1) / kBlk);
+  if (cnt) bounds_recompute2(s2_pmin / kBlk, (s2_pmax < s2_cx.npos ? s2_pmax : s2_cx.npos - 1) / kBlk);
 }
 
 
@@ -727,7 +766,7 @@ __device__ __forceinline__ void rekey_bounds2(uint32_t cnt) {
 // bit 0 = the allocation does not fit the node's res_avail now ("Resource"); none: "Priority"
 __device__ __forceinline__ uint32_t later_label2(uint32_t q, bool short_now, int64_t limit) {
   uint32_t l = short_now ? 1u : 0u;
-  if (s2_cx.part < s2_cx.cl.n_parts && s2_cx.tl.first_resv[s2_cx.base + q] < s2_cx.now + limit) l |= 2u;
+  if (s2_cx.part < s2_cx.cl.n_comp && s2_cx.tl.first_resv[s2_cx.base + q] < s2_cx.now + limit) l |= 2u;
   return l;
 }
 __device__ __forceinline__ uint8_t later_reason2(uint32_t label) {
@@ -748,7 +787,7 @@ __device__ __forceinline__ uint32_t nth_set_bit(uint32_t m, uint32_t n) {
 
 // outputs of one placed (job, node) pair and the node's new summary, by lane 0 of its group
 __device__ __forceinline__ void write_node2(const JobQ& jq, uint32_t q, uint32_t rank, const Row& alloc, uint32_t nn, const Row& seg0) {
-  const Smem2 sm = SM2();
+  const Smem2 sm = SM2S();
   sm.nseg[q] = (uint16_t)nn;
   if (nn >= s2_cx.max_jobs) sm.skip[q] = 1;
   sm.cpu0[q] = seg0.cpu_raw;
@@ -760,14 +799,53 @@ __device__ __forceinline__ void write_node2(const JobQ& jq, uint32_t q, uint32_t
   s2_cx.tl.n[s2_cx.base + q] = nn;
 }
 
+// Scheduler of several overlapping partitions: membership bytes, one cost array and
+// one order per partition over the shared node states; every NodeSelector starts from
+// the same NodeRater costs (JobScheduler.h:492-505). All threads; s2_cx is set.
+__device__ __noinline__ void init_orders2(const uint8_t* slot_memb) {
+  const uint32_t tid = threadIdx.x, mp = s2_cx.mp, ncp = s2_cx.ncp;
+  const Smem2 s0 = smem2_layout(mp, s2_cx.words, s2_cx.ring, s2_cx.gres != 0, ncp, 0);
+  for (uint32_t q = tid; q < mp; q += kT2) s0.memb[q] = slot_memb[s2_cx.base + q];
+  for (uint32_t p = 1; p < ncp; ++p) {
+    const Smem2 sp = smem2_layout(mp, s2_cx.words, s2_cx.ring, s2_cx.gres != 0, ncp, p);
+    for (uint32_t q = tid; q < mp; q += kT2) sp.cost[q] = s0.cost[q];
+  }
+  __syncthreads();
+  if (tid < ncp) {
+    uint32_t c = 0;
+    for (uint32_t q = 0; q < mp; ++q) c += (s0.memb[q] >> tid) & 1u;
+    s2_mcount[tid] = c;
+  }
+  __syncthreads();
+  for (uint32_t p = 0; p < ncp; ++p) {
+    if (tid == 0) { s2_curp = p; s2_cx.npos = s2_mcount[p]; }
+    __syncthreads();
+    order_sort2();
+    __syncthreads();
+  }
+}
+
 // ---- one job, start to finish (any node_num): JobScheduler.cpp:5224-5404 ----------
 // The walk over the order in windows of 256 positions; every pre-filter
 // candidate is tested exactly (one group each, 32 per round), the first K
 // passing ones are the pick. Fewer than K: backfill on the first K capable nodes.
+// Scheduler with several (overlapping) partitions: the job in hand decides whose order is walked
+__device__ __forceinline__ void enter_partition2(const JobQ& jq) {
+  if (s2_cx.ncp > 1) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s2_curp = (jq.flags >> 16) & 7u;
+      s2_cx.npos = s2_mcount[s2_curp];
+    }
+    __syncthreads();
+  }
+}
+
 __device__ __noinline__ void single2(uint32_t ji) {
+  enter_partition2(s2_jobs[ji % s2_cx.ring]);
   const Smem2 sm = SM2();
   const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id(), gl = g_lane(), gi = g_index();
-  const uint32_t mp = s2_cx.mp, base = s2_cx.base, ring = s2_cx.ring;
+  const uint32_t mp = s2_cx.npos, base = s2_cx.base, ring = s2_cx.ring;
   const int64_t now = s2_cx.now;
   const TimelineDev& tl = s2_cx.tl;
   uint16_t* const list2 = reinterpret_cast<uint16_t*>(sm.scratch);  // first capable nodes
@@ -991,7 +1069,7 @@ __device__ __noinline__ void single2(uint32_t ji) {
     full_rekey = K > (uint32_t)kRK;
     for (uint32_t k = tid; k < K; k += kT2) {
       const uint32_t q = nodes[k];
-      const double nc = new_cost2(jq, q);
+      const double nc = new_cost2(jq, q, sm.cost);
       if (full_rekey) sm.cost[q] = nc; else { s2_rk_node[k] = q; s2_rk_nc[k] = nc; }
     }
   } else if (tid == 0) {
@@ -999,7 +1077,7 @@ __device__ __noinline__ void single2(uint32_t ji) {
   }
   __syncthreads();
   // list2 lives in the scratch words: back to zero
-  for (uint32_t i = tid; i < (K + 1) / 2 + 1 && i < mp + 4; i += kT2) sm.scratch[i] = 0;
+  for (uint32_t i = tid; i < (K + 1) / 2 + 1 && i < s2_cx.mp + 4; i += kT2) sm.scratch[i] = 0;
   __syncthreads();
   if (placed) {
     if (full_rekey) order_sort2();
@@ -1081,9 +1159,10 @@ __device__ __noinline__ uint32_t max_tasks2(const View& min_view, const View& re
 }
 
 __device__ __noinline__ void single2_general(uint32_t ji) {
+  enter_partition2(s2_jobs[ji % s2_cx.ring]);
   const Smem2 sm = SM2();
   const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id(), gl = g_lane(), gi = g_index();
-  const uint32_t mp = s2_cx.mp, base = s2_cx.base, ring = s2_cx.ring;
+  const uint32_t mp = s2_cx.npos, base = s2_cx.base, ring = s2_cx.ring;
   const int64_t now = s2_cx.now;
   const TimelineDev& tl = s2_cx.tl;
   const uint32_t slot = ji % ring;
@@ -1408,18 +1487,20 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
     sm.nseg[q] = (uint16_t)a.tl.n[g];
     sm.cls[q] = a.cl.slot_class[g];
   }
+  const uint32_t ncp = a.sched_nparts ? a.sched_nparts[part] : 1u;
   for (uint32_t p = tid; p < mp + 4; p += kT2) sm.scratch[p] = 0;
   if (tid < kMaxClasses) s2_classrow[tid] = a.cl.class_rows[(size_t)part * kMaxClasses + tid];
   if (tid == 0) {
     s2_cx.cl = a.cl; s2_cx.tl = a.tl; s2_cx.out = a.out;
     s2_cx.now = a.now; s2_cx.max_window = a.max_window; s2_cx.base = base; s2_cx.mp = mp; s2_cx.words = words;
+    s2_cx.ncp = ncp; s2_cx.npos = mp; s2_curp = 0;
     s2_cx.max_jobs = a.max_jobs; s2_cx.ring = ring; s2_cx.gres = a.gres; s2_cx.dslot = a.dslot; s2_cx.cost_policy = a.cost_policy; s2_cx.part = part; s2_cx.req_node = a.req_node; s2_cx.req_task = a.req_task;
     s2_prof_windows = 0; s2_prof_tests = 0; s2_prof_singles = 0;
     for (uint32_t s = 0; s < ring; ++s) mbar_init(&s2_bar[s], 1);
     fence_mbar_init();
   }
   __syncthreads();
-  order_sort2();
+  if (ncp > 1) init_orders2(a.slot_memb); else order_sort2();
 
   const uint32_t r_begin = a.part_job_off[part], r_end = a.part_job_off[part + 1];
   const uint32_t njobs = r_end - r_begin;
@@ -1448,15 +1529,18 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
   uint32_t ji = 0;
   uint32_t jcap = kMaxJ;     // jobs offered to the next batch: twice what the last one placed (a batch that is cut
                              // early wastes the selection of the jobs behind the cut)
-  bool want_single = false;  // the job at ji goes down the one-job path
+  bool want_single = s2_cx.ncp > 1;  // the job at ji goes down the one-job path (overlapping partitions: every job,
+                                     // each in its own partition's order)
   while (ji < njobs) {
     ensure_issued(ji);
     PROF(0);
     if (want_single) {
+      if (wid == 0 && lane == 0) mbar_wait(&s2_bar[ji % ring], (ji / ring) & 1u);
+      __syncthreads();
       if (s2_jobs[ji % ring].flags & 4u) single2_general(ji); else single2(ji);
       PROF(7);
       ++ji;
-      want_single = false;
+      want_single = s2_cx.ncp > 1;
       __syncthreads();
       continue;
     }
@@ -1618,7 +1702,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
             if ((cm >> lane) & 1u) {
               sm.scratch[lq] = 1;
               const uint8_t c = sm.cls[lq];
-              nc = c < kDeltaClasses ? __dadd_rn(cq, s2_jdelta[t][c]) : new_cost2(s2_jobs[s2_bj[t].slot], lq);
+              nc = c < kDeltaClasses ? __dadd_rn(cq, s2_jdelta[t][c]) : new_cost2(s2_jobs[s2_bj[t].slot], lq, sm.cost);
             }
             // pick number i of the job goes to task slot tf + i
             const uint32_t src = mine ? (K == 1 ? kth : nth_set_bit(cm, lane - tf + 1u)) : 0u;

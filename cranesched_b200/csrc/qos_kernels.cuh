@@ -8,12 +8,22 @@
 // DoMallocResource_ (546-587) adds the job to the usage at all of them.
 //
 // Every usage entry is keyed by the qos, so jobs of different qos never touch
-// the same entry: the pass is sequential only within one qos. One warp owns
-// one qos id and walks the job table in job-id order (ballot-compacted, 32
-// jobs per coalesced probe); for one job the levels are checked lane-parallel
-// (lane 0 = user, lanes 1..C = account chain in order, lane C+1 = qos) and the
-// lowest failing lane gives the reason, which is the reference's first-failure
-// order.
+// the same entry: the pass is sequential only within one qos.
+//   k_qos_keys    key = qos for the jobs the pass has to walk (started now, known
+//                 qos), sentinel otherwise; "InvalidQOS" is written here (it
+//                 touches no usage). A stable radix sort of (key, job) then
+//                 gives every qos its jobs in job-id order.
+//   k_qos_offsets the segment of every qos in the sorted list.
+//   k_qos_chain   one CTA per qos. The usage entries of the qos — its column of
+//                 the (user,qos) and (account,qos) tables and the qos entry —
+//                 are staged in shared memory when they fit (else they stay in
+//                 global memory: same code, generic pointers). Warps 1-3 sum
+//                 the allocations of the next 96 jobs (ResourceV3::View) into a
+//                 shared buffer while warp 0 walks the current 96 in order: the
+//                 levels of one job are checked lane-parallel (lane 0 = user,
+//                 lanes 1..C = account chain in order, lane C+1 = qos) and the
+//                 lowest failing lane gives the reason, which is the
+//                 reference's first-failure order.
 #pragma once
 
 #include "algebra.cuh"
@@ -61,16 +71,21 @@ struct QosUse {
 __device__ __forceinline__ uint8_t qos_check_tres(const GresDict& d, const QosUse& u, const crane_tres_limit_t& L) {
   if (u.cpu_raw > L.view.cpu_raw) return CRANE_REASON_QOS_CPU;
   if (u.mem > L.view.mem) return CRANE_REASON_QOS_MEM;
-  for (uint32_t g = 0; g < CRANE_GRES_NAMES; ++g) {
+  // (all loops have constant bounds and are unrolled: u stays in registers)
+#pragma unroll
+  for (int g = 0; g < CRANE_GRES_NAMES; ++g) {
     const uint32_t first = d.name_first[g], cnt = d.name_count[g];
     if (cnt == 0) continue;
     bool in_req = u.tot[g] != 0;
-    for (uint32_t e = first; e < first + cnt; ++e) in_req |= u.spec[e] != 0;
+#pragma unroll
+    for (int e = 0; e < CRANE_GRES_ENTRIES; ++e)
+      if ((uint32_t)e >= first && (uint32_t)e < first + cnt) in_req |= u.spec[e] != 0;
     if (!in_req) continue;
     if (!((L.gres_name_present >> g) & 1u)) return CRANE_REASON_NONE;
     if (u.tot[g] > L.view.gres_total[g]) return CRANE_REASON_QOS_GRES;
-    for (uint32_t e = first; e < first + cnt; ++e) {
-      if (u.spec[e] == 0) continue;
+#pragma unroll
+    for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) {
+      if ((uint32_t)e < first || (uint32_t)e >= first + cnt || u.spec[e] == 0) continue;
       if (!((L.gres_spec_present >> e) & 1u)) return CRANE_REASON_NONE;
       if (u.spec[e] > L.view.gres_spec[e]) return CRANE_REASON_QOS_GRES;
     }
@@ -85,104 +100,179 @@ __device__ __forceinline__ T warp_sum(T v) {
   return v;
 }
 
-__global__ void __launch_bounds__(32) k_qos_filter(QosDev q, GresDict dict) {
-  const uint32_t lane = threadIdx.x;
+constexpr int kQosBatch = 96;     // jobs prepared by warps 1-3 per round
+constexpr int kQosThreads = 128;
+
+__global__ void k_qos_keys(QosDev q, uint64_t* keys, uint32_t* vals, uint64_t sentinel) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q.n_jobs) return;
+  uint64_t key = sentinel;
+  if (q.reason[i] == CRANE_REASON_NONE && q.n_alloc[i] != 0) {
+    const uint32_t jq = q.qos[i];
+    // "InvalidQOS" (AccountMetaContainer.cpp:168-169): no usage is touched
+    if (jq >= q.n_qos || !q.valid[jq]) q.reason[i] = CRANE_REASON_QOS_INVALID;
+    else key = jq;
+  }
+  keys[i] = key;
+  vals[i] = i;
+}
+
+// off[w] = first position of key >= w in the sorted keys, w = 0..n_qos
+__global__ void k_qos_offsets(const uint64_t* keys, uint32_t n, uint32_t n_qos, uint32_t* off) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w > n_qos) return;
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) / 2;
+    if (keys[mid] < (uint64_t)w) lo = mid + 1; else hi = mid;
+  }
+  off[w] = lo;
+}
+
+struct QosPrep {   // what the walk needs of one job, prepared off the chain
+  QosUse a;
+  int64_t tl;
+  uint32_t job, user, C, pad;
+  uint16_t chain[30];  // account chain, in order
+  uint16_t pad2[2];
+};
+
+__global__ void __launch_bounds__(kQosThreads) k_qos_chain(QosDev q, GresDict dict, const uint32_t* list, const uint32_t* off,
+                                                           uint32_t tables_in_smem) {
+  unsigned char* const qos_dyn = CRANE_DYN_BASE();  // dynamic shared memory: the usage column of this qos
+  __shared__ QosPrep s_prep[2][kQosBatch];
+  __shared__ crane_tres_limit_t s_lim[3];
+  __shared__ crane_meta_resource_t s_qos_entry;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const uint32_t w = blockIdx.x;
-  const uint32_t N = q.n_jobs;
-  if (w == q.n_qos) {
-    // "InvalidQOS" (AccountMetaContainer.cpp:168-169): no usage is touched, so
-    // the jobs of all unknown / deleted qos are independent
-    for (uint32_t i = lane; i < N; i += 32) {
-      const uint32_t jq = q.qos[i];
-      if (q.reason[i] == CRANE_REASON_NONE && q.n_alloc[i] != 0 && (jq >= q.n_qos || !q.valid[jq]))
-        q.reason[i] = CRANE_REASON_QOS_INVALID;
+  const uint32_t begin = off[w], end = off[w + 1];
+  if (begin == end) return;  // (an invalid qos has no jobs in the list)
+  const uint32_t Q = q.n_qos, U = q.n_users, A = q.n_accounts;
+  crane_meta_resource_t* const s_user = reinterpret_cast<crane_meta_resource_t*>(qos_dyn);
+  crane_meta_resource_t* const s_acct = s_user + U;
+  constexpr uint32_t kWords = sizeof(crane_meta_resource_t) / 4;
+  if (tables_in_smem) {
+    for (uint32_t i = tid; i < (U + A) * kWords; i += kQosThreads) {
+      const uint32_t e = i / kWords, k = i % kWords;
+      const crane_meta_resource_t* src = e < U ? q.user_usage + (size_t)e * Q + w : q.account_usage + (size_t)(e - U) * Q + w;
+      reinterpret_cast<uint32_t*>(s_user)[i] = reinterpret_cast<const uint32_t*>(src)[k];
     }
-    return;
   }
-  if (!q.valid[w]) return;
+  if (tid < kWords) reinterpret_cast<uint32_t*>(&s_qos_entry)[tid] = reinterpret_cast<const uint32_t*>(q.qos_usage + w)[tid];
+  if (tid == 0) { s_lim[0] = q.tres_user[w]; s_lim[1] = q.tres_account[w]; s_lim[2] = q.tres_qos[w]; }
   const int64_t max_wall = q.max_wall[w];
-  for (uint32_t base = 0; base < N; base += 32) {
-    const uint32_t i = base + lane;
-    const bool mine = i < N && q.qos[i] == w && q.reason[i] == CRANE_REASON_NONE && q.n_alloc[i] != 0;
-    uint32_t todo = __ballot_sync(0xffffffffu, mine);
-    while (todo) {
-      const uint32_t j = base + (uint32_t)__ffs((int)todo) - 1u;
-      todo &= todo - 1u;
-      // ---- allocated_res.View() -------------------------------------------
-      const uint32_t n = q.n_alloc[j];
-      const Row* rows = q.alloc_res + q.alloc_off[j];
-      QosUse a;
-      a.cpu_raw = 0; a.mem = 0; a.mem_sw = 0;
+  const uint32_t mj_user = q.max_jobs_per_user[w], mj_acct = q.max_jobs_per_account[w], mj_qos = q.max_jobs[w];
+  const int64_t max_cpus_user = q.max_cpus_per_user_raw[w];
+
+  // allocated_res.View() of the jobs [b0, b0 + kQosBatch) of the list, one job per thread of warps 1-3
+  auto prepare = [&](uint32_t b0, uint32_t buf) {
+    const uint32_t t = tid - 32u;
+    if (b0 + t >= end) return;
+    const uint32_t j = list[b0 + t];
+    QosPrep& P = s_prep[buf][t];
+    const uint32_t n = q.n_alloc[j];
+    const Row* rows = q.alloc_res + q.alloc_off[j];
+    QosUse a;
+    a.cpu_raw = 0; a.mem = 0; a.mem_sw = 0;
 #pragma unroll
-      for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) a.spec[e] = 0;
-      if (n == 1) {
-        const Row r = rows[0];
-        a.cpu_raw = r.cpu_raw; a.mem = r.mem; a.mem_sw = r.mem_sw;
+    for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) a.spec[e] = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+      const Row r = rows[k];
+      a.cpu_raw += r.cpu_raw; a.mem += r.mem; a.mem_sw += r.mem_sw;
 #pragma unroll
-        for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) a.spec[e] = (uint32_t)popc32(field16(r.g, e));
-      } else {
-        for (uint32_t k = lane; k < n; k += 32) {
-          const Row r = rows[k];
-          a.cpu_raw += r.cpu_raw; a.mem += r.mem; a.mem_sw += r.mem_sw;
+      for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) a.spec[e] += (uint32_t)popc32(field16(r.g, e));
+    }
 #pragma unroll
-          for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) a.spec[e] += (uint32_t)popc32(field16(r.g, e));
+    for (int g = 0; g < CRANE_GRES_NAMES; ++g) a.tot[g] = 0;
+#pragma unroll
+    for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) {
+      if ((uint32_t)e >= dict.n_entries) continue;
+      const uint32_t name = dict.entry_name[e];
+#pragma unroll
+      for (int g = 0; g < CRANE_GRES_NAMES; ++g)
+        if (name == (uint32_t)g) a.tot[g] += a.spec[e];
+    }
+    P.a = a;
+    P.tl = q.time_limit[j];
+    P.job = j;
+    P.user = q.user[j];
+    const uint32_t c0 = q.chain_off[j];
+    P.C = q.chain_off[j + 1] - c0;
+    for (uint32_t c = 0; c < P.C; ++c) P.chain[c] = (uint16_t)q.chain_acct[c0 + c];
+  };
+
+  if (wid) prepare(begin, 0);
+  __syncthreads();
+  uint32_t buf = 0;
+  for (uint32_t b0 = begin; b0 < end; b0 += kQosBatch, buf ^= 1u) {
+    if (wid) {
+      prepare(b0 + kQosBatch, buf ^ 1u);
+    } else {
+      const uint32_t cnt = end - b0 < (uint32_t)kQosBatch ? end - b0 : (uint32_t)kQosBatch;
+      for (uint32_t k = 0; k < cnt; ++k) {
+        const QosPrep& P = s_prep[buf][k];
+        const QosUse a = P.a;
+        const int64_t tl = P.tl;
+        const uint32_t C = P.C;
+        // ---- CheckQosResource_: one level per lane ---------------------------
+        crane_meta_resource_t* val = nullptr;
+        const crane_tres_limit_t* lim = nullptr;
+        uint32_t max_jobs = 0;
+        if (lane == 0) {
+          val = tables_in_smem ? s_user + P.user : q.user_usage + (size_t)P.user * Q + w;
+          lim = &s_lim[0];
+          max_jobs = mj_user;
+        } else if (lane <= C) {
+          const uint32_t acct = P.chain[lane - 1];
+          val = tables_in_smem ? s_acct + acct : q.account_usage + (size_t)acct * Q + w;
+          lim = &s_lim[1];
+          max_jobs = mj_acct;
+        } else if (lane == C + 1) {
+          val = &s_qos_entry;
+          lim = &s_lim[2];
+          max_jobs = mj_qos;
         }
-        a.cpu_raw = warp_sum(a.cpu_raw); a.mem = warp_sum(a.mem); a.mem_sw = warp_sum(a.mem_sw);
+        uint8_t result = CRANE_REASON_NONE;
+        if (val) {
+          QosUse u = a;  // resource_use = allocated view + val.resource
+          u.cpu_raw += val->cpu_raw; u.mem += val->mem; u.mem_sw += val->mem_sw;
 #pragma unroll
-        for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) a.spec[e] = warp_sum(a.spec[e]);
+          for (int g = 0; g < CRANE_GRES_NAMES; ++g) u.tot[g] += val->gres_total[g];
+#pragma unroll
+          for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) u.spec[e] += val->gres_spec[e];
+          if (lane == 0 && u.cpu_raw > max_cpus_user) result = CRANE_REASON_QOS_CPU;
+          else if ((uint64_t)val->jobs_count + 1ull > (uint64_t)max_jobs) result = CRANE_REASON_QOS_JOBS;
+          else if (max_wall > 0 && val->wall_time + tl > max_wall) result = CRANE_REASON_QOS_WALL;
+          else result = qos_check_tres(dict, u, *lim);
+        }
+        const uint32_t failed = __ballot_sync(0xffffffffu, result != CRANE_REASON_NONE);
+        if (failed) {
+          const uint8_t first = (uint8_t)__shfl_sync(0xffffffffu, (uint32_t)result, __ffs((int)failed) - 1);
+          if (lane == 0) q.reason[P.job] = first;
+        } else if (val) {
+          // DoMallocResource_ / MetaResource::operator+= (AccountMetaContainer.cpp:33-39, 546-587)
+          val->cpu_raw += a.cpu_raw; val->mem += a.mem; val->mem_sw += a.mem_sw;
+#pragma unroll
+          for (int g = 0; g < CRANE_GRES_NAMES; ++g) val->gres_total[g] += a.tot[g];
+#pragma unroll
+          for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) val->gres_spec[e] += a.spec[e];
+          val->jobs_count += 1;
+          val->wall_time += tl;
+        }
+        __syncwarp();  // usage written by one lane is read by another for the next job
       }
-#pragma unroll
-      for (int g = 0; g < CRANE_GRES_NAMES; ++g) a.tot[g] = 0;
-      for (uint32_t e = 0; e < dict.n_entries; ++e) a.tot[dict.entry_name[e]] += a.spec[e];
-      // ---- CheckQosResource_: one level per lane ---------------------------
-      const uint32_t c0 = q.chain_off[j], C = q.chain_off[j + 1] - c0;
-      const int64_t tl = q.time_limit[j];
-      crane_meta_resource_t* val = nullptr;
-      const crane_tres_limit_t* lim = nullptr;
-      uint32_t max_jobs = 0;
-      if (lane == 0) {
-        val = q.user_usage + (size_t)q.user[j] * q.n_qos + w;
-        lim = q.tres_user + w;
-        max_jobs = q.max_jobs_per_user[w];
-      } else if (lane <= C) {
-        val = q.account_usage + (size_t)q.chain_acct[c0 + lane - 1] * q.n_qos + w;
-        lim = q.tres_account + w;
-        max_jobs = q.max_jobs_per_account[w];
-      } else if (lane == C + 1) {
-        val = q.qos_usage + w;
-        lim = q.tres_qos + w;
-        max_jobs = q.max_jobs[w];
-      }
-      uint8_t result = CRANE_REASON_NONE;
-      if (val) {
-        QosUse u = a;  // resource_use = allocated view + val.resource
-        u.cpu_raw += val->cpu_raw; u.mem += val->mem; u.mem_sw += val->mem_sw;
-#pragma unroll
-        for (int g = 0; g < CRANE_GRES_NAMES; ++g) u.tot[g] += val->gres_total[g];
-#pragma unroll
-        for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) u.spec[e] += val->gres_spec[e];
-        if (lane == 0 && u.cpu_raw > q.max_cpus_per_user_raw[w]) result = CRANE_REASON_QOS_CPU;
-        else if ((uint64_t)val->jobs_count + 1ull > (uint64_t)max_jobs) result = CRANE_REASON_QOS_JOBS;
-        else if (max_wall > 0 && val->wall_time + tl > max_wall) result = CRANE_REASON_QOS_WALL;
-        else result = qos_check_tres(dict, u, *lim);
-      }
-      const uint32_t failed = __ballot_sync(0xffffffffu, result != CRANE_REASON_NONE);
-      if (failed) {
-        const uint8_t first = (uint8_t)__shfl_sync(0xffffffffu, (uint32_t)result, __ffs((int)failed) - 1);
-        if (lane == 0) q.reason[j] = first;
-      } else if (val) {
-        // DoMallocResource_ / MetaResource::operator+= (AccountMetaContainer.cpp:33-39, 546-587)
-        val->cpu_raw += a.cpu_raw; val->mem += a.mem; val->mem_sw += a.mem_sw;
-#pragma unroll
-        for (int g = 0; g < CRANE_GRES_NAMES; ++g) val->gres_total[g] += a.tot[g];
-#pragma unroll
-        for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) val->gres_spec[e] += a.spec[e];
-        val->jobs_count += 1;
-        val->wall_time += tl;
-      }
-      __syncwarp();  // usage written by one lane is read by another for the next job
+    }
+    __syncthreads();
+  }
+  // ---- usage back to the tables --------------------------------------------------
+  if (tables_in_smem) {
+    for (uint32_t i = tid; i < (U + A) * kWords; i += kQosThreads) {
+      const uint32_t e = i / kWords, k = i % kWords;
+      crane_meta_resource_t* dst = e < U ? q.user_usage + (size_t)e * Q + w : q.account_usage + (size_t)(e - U) * Q + w;
+      reinterpret_cast<uint32_t*>(dst)[k] = reinterpret_cast<const uint32_t*>(s_user)[i];
     }
   }
+  if (tid < kWords) reinterpret_cast<uint32_t*>(q.qos_usage + w)[tid] = reinterpret_cast<const uint32_t*>(&s_qos_entry)[tid];
 }
 
 }  // namespace crane

@@ -20,6 +20,7 @@
 #include <mutex>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -78,16 +79,19 @@ struct crane_sched {
   crane_sched_config_t cfg{};
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[8]{};
+  cudaEvent_t ev[10]{};  // 0-1 upload, 2-7 run / fetch, 8-9 qos filter
   std::string err;
   crane_sched_timing_t timing{};
   size_t v2_budget = 0;       // dynamic shared memory k_commit2 may use
+  bool h2d_timed = false;     // ev[0], ev[1] were recorded (crane_sched_upload)
   uint32_t v2_ring = 0;
 
   // cluster (host copies)
   bool have_cluster = false;
   uint32_t n_nodes = 0, n_parts = 0, n_slots = 0, max_part_slots = 0, words_per_row = 0;
-  uint32_t n_vparts = 0, n_resv = 0;  // schedulers = partitions + reservations
+  uint32_t n_vparts = 0, n_resv = 0;  // schedulers = groups of overlapping partitions + reservations
+  uint32_t n_comp = 0, max_comp_parts = 1;
+  std::vector<uint32_t> h_part_comp, h_part_cidx, h_sched_nparts;
   // host copies of the cluster and reservation tables (the slot layout is rebuilt when either changes)
   std::vector<Row> c_res_total, r_res;
   std::vector<uint8_t> c_alive, c_drain;
@@ -110,7 +114,9 @@ struct crane_sched {
   DBuf<double> d_cost0;
   DBuf<uint8_t> d_skip;
   DBuf<int64_t> d_first_resv, d_resv_start, d_resv_end;
-  DBuf<uint32_t> d_slot_resv, d_rsv_off, d_rsv_id, d_vpart, d_pd_resv;
+  DBuf<uint32_t> d_q_off;
+  DBuf<uint32_t> d_slot_resv, d_rsv_off, d_rsv_id, d_vpart, d_pd_resv, d_sched_nparts, d_part_comp, d_part_cidx, d_sched_owner;
+  DBuf<uint8_t> d_slot_memb;
   DBuf<Row> d_rsv_res;
   bool have_pd_resv = false;
 
@@ -288,7 +294,7 @@ void crane_sched_destroy(crane_sched_t* h) {
   REL(d_out_prio); REL(d_out_start); REL(d_out_end); REL(d_out_nalloc); REL(d_out_node); REL(d_out_ntasks);
   REL(d_out_res); REL(d_prof); REL(d_qos); REL(d_user); REL(d_q_u32); REL(d_q_chain_off); REL(d_q_chain);
   REL(d_q_i64); REL(d_q_valid); REL(d_part_owner); REL(d_part_list); REL(d_ntpn_max); REL(d_ntasks); REL(d_first_resv); REL(d_resv_start); REL(d_resv_end); REL(d_slot_resv);
-  REL(d_rsv_off); REL(d_rsv_id); REL(d_dead); REL(d_erase_rows); REL(d_vpart); REL(d_pd_resv); REL(d_rsv_res); REL(d_q_tres); REL(d_q_user_usage); REL(d_q_acct_usage); REL(d_q_qos_usage);
+  REL(d_rsv_off); REL(d_rsv_id); REL(d_dead); REL(d_erase_rows); REL(d_q_off); REL(d_sched_nparts); REL(d_part_comp); REL(d_part_cidx); REL(d_sched_owner); REL(d_slot_memb); REL(d_vpart); REL(d_pd_resv); REL(d_rsv_res); REL(d_q_tres); REL(d_q_user_usage); REL(d_q_acct_usage); REL(d_q_qos_usage);
 #undef REL
   for (auto& e : h->ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -306,31 +312,71 @@ static uint32_t running_slot(const crane_sched* h, const crane_running_t* rn, ui
   const uint32_t lo = h->r_node_off[rv], hi = h->r_node_off[rv + 1];
   const auto it = std::lower_bound(h->r_node.begin() + lo, h->r_node.begin() + hi, node);
   if (it == h->r_node.begin() + hi || *it != node) return 0xffffffffu;
-  return h->h_part_base[h->n_parts + rv] + (uint32_t)(it - (h->r_node.begin() + lo));
+  return h->h_part_base[h->n_comp + rv] + (uint32_t)(it - (h->r_node.begin() + lo));
 }
 
 // Slot layout of the node states: the usable nodes of every partition (contiguous per
 // partition), then the nodes of every reservation; device copies of the cluster tables.
 static int build_layout(crane_sched* h) {
   h->h_node_slot.assign(h->n_nodes, 0xffffffffu);
-  h->h_part_base.assign(h->n_parts + 1, 0);
-  h->h_part_base.reserve(h->n_parts + h->n_resv + 1);
   h->h_slot_node.clear();
-  std::vector<uint8_t> seen(h->n_nodes, 0);
   std::vector<Row> slot_total;
   uint32_t max_mp = 0;
-  for (uint32_t p = 0; p < h->n_parts; ++p) {
-    h->h_part_base[p] = (uint32_t)h->h_slot_node.size();
-    uint32_t prev = 0;
-    for (uint32_t k = h->c_part_off[p]; k < h->c_part_off[p + 1]; ++k) {
-      uint32_t n = h->c_part_nodes[k];
-      if (n >= h->n_nodes) return fail(h, CRANE_EINVAL, "cluster: node index %u out of range", n);
-      if (k > h->c_part_off[p] && n <= prev) return fail(h, CRANE_EINVAL, "cluster: partition %u node list must be ascending", p);
-      prev = n;
-      // a node shared by two partitions couples their timelines (shared
-      // NodeState, JobScheduler.cpp:5622); that is SURVEY.md §8f rank 3.
-      if (seen[n]) return fail(h, CRANE_ENOSYS, "cluster: node %u is in more than one partition (overlapping partitions are not built yet)", n);
-      seen[n] = 1;
+  // Partitions that share a node share its NodeState (JobScheduler.cpp:5622): their job
+  // loops are coupled through its timeline, so one scheduler (one CTA) takes every
+  // connected component of overlapping partitions; each partition keeps its own order.
+  std::vector<uint32_t> uf(h->n_parts);
+  for (uint32_t p = 0; p < h->n_parts; ++p) uf[p] = p;
+  auto find = [&](uint32_t x) { while (uf[x] != x) { uf[x] = uf[uf[x]]; x = uf[x]; } return x; };
+  {
+    std::vector<uint32_t> first(h->n_nodes, 0xffffffffu);
+    for (uint32_t p = 0; p < h->n_parts; ++p) {
+      uint32_t prev = 0;
+      for (uint32_t k = h->c_part_off[p]; k < h->c_part_off[p + 1]; ++k) {
+        const uint32_t n = h->c_part_nodes[k];
+        if (n >= h->n_nodes) return fail(h, CRANE_EINVAL, "cluster: node index %u out of range", n);
+        if (k > h->c_part_off[p] && n <= prev) return fail(h, CRANE_EINVAL, "cluster: partition %u node list must be ascending", p);
+        prev = n;
+        if (first[n] == 0xffffffffu) first[n] = p;
+        else { const uint32_t a = find(first[n]), c = find(p); if (a != c) uf[std::max(a, c)] = std::min(a, c); }
+      }
+    }
+  }
+  h->h_part_comp.assign(h->n_parts, 0);
+  h->h_part_cidx.assign(h->n_parts, 0);
+  h->h_sched_nparts.clear();
+  std::vector<std::vector<uint32_t>> comp_parts;
+  {
+    std::vector<uint32_t> id(h->n_parts, 0xffffffffu);
+    for (uint32_t p = 0; p < h->n_parts; ++p) {
+      const uint32_t r = find(p);
+      if (id[r] == 0xffffffffu) { id[r] = (uint32_t)comp_parts.size(); comp_parts.emplace_back(); }
+      h->h_part_comp[p] = id[r];
+      h->h_part_cidx[p] = (uint32_t)comp_parts[id[r]].size();
+      comp_parts[id[r]].push_back(p);
+    }
+  }
+  h->n_comp = (uint32_t)comp_parts.size();
+  h->h_part_base.assign(h->n_comp + 1, 0);
+  h->h_part_base.reserve(h->n_comp + h->n_resv + 1);
+  std::vector<uint8_t> slot_memb;
+  uint32_t max_cp = 1;
+  for (uint32_t c = 0; c < h->n_comp; ++c) {
+    h->h_part_base[c] = (uint32_t)h->h_slot_node.size();
+    if (comp_parts[c].size() > (size_t)kMaxCompParts)
+      return fail(h, CRANE_ENOSYS, "cluster: %zu partitions overlap in one connected group (at most %d)", comp_parts[c].size(), kMaxCompParts);
+    max_cp = std::max<uint32_t>(max_cp, (uint32_t)comp_parts[c].size());
+    h->h_sched_nparts.push_back((uint32_t)comp_parts[c].size());
+    std::vector<std::pair<uint32_t, uint8_t>> nodes;  // (node, membership bits), ascending node index
+    for (uint32_t i = 0; i < comp_parts[c].size(); ++i) {
+      const uint32_t p = comp_parts[c][i];
+      for (uint32_t k = h->c_part_off[p]; k < h->c_part_off[p + 1]; ++k) nodes.push_back({h->c_part_nodes[k], (uint8_t)(1u << i)});
+    }
+    std::sort(nodes.begin(), nodes.end());
+    for (size_t i = 0; i < nodes.size();) {
+      const uint32_t n = nodes[i].first;
+      uint8_t bits = 0;
+      for (; i < nodes.size() && nodes[i].first == n; ++i) bits |= nodes[i].second;
       if (!h->c_alive[n] || h->c_drain[n]) continue;  // JobScheduler.cpp:5629
       const Row& t = h->c_res_total[n];
       if (t.cpu_raw < 0 || t.cpu_raw > (int64_t)1 << 40) return fail(h, CRANE_EINVAL, "cluster: node %u cpu out of range", n);
@@ -339,22 +385,25 @@ static int build_layout(crane_sched* h) {
       h->h_node_slot[n] = (uint32_t)h->h_slot_node.size();
       h->h_slot_node.push_back(n);
       slot_total.push_back(t);
+      slot_memb.push_back(bits);
     }
-    uint32_t mp = (uint32_t)h->h_slot_node.size() - h->h_part_base[p];
-    max_mp = std::max(max_mp, mp);
+    max_mp = std::max(max_mp, (uint32_t)h->h_slot_node.size() - h->h_part_base[c]);
   }
-  h->h_part_base[h->n_parts] = (uint32_t)h->h_slot_node.size();
+  h->h_part_base[h->n_comp] = (uint32_t)h->h_slot_node.size();
+  h->max_comp_parts = max_cp;
   const uint32_t n_phys = (uint32_t)h->h_slot_node.size();
   // one more scheduler per reservation: node states holding exactly the reserved
   // resources (JobScheduler.cpp:5689-5703), whatever the node's own state
-  h->n_vparts = h->n_parts + h->n_resv;
+  h->n_vparts = h->n_comp + h->n_resv;
   std::vector<uint32_t> slot_resv(n_phys, 0xffffffffu);
   for (uint32_t r = 0; r < h->n_resv; ++r) {
     for (uint32_t k = h->r_node_off[r]; k < h->r_node_off[r + 1]; ++k) {
       h->h_slot_node.push_back(h->r_node[k]);
       slot_total.push_back(h->r_res[k]);
       slot_resv.push_back(r);
+      slot_memb.push_back(1);
     }
+    h->h_sched_nparts.push_back(1);
     h->h_part_base.push_back((uint32_t)h->h_slot_node.size());
     max_mp = std::max(max_mp, h->r_node_off[r + 1] - h->r_node_off[r]);
   }
@@ -377,7 +426,7 @@ static int build_layout(crane_sched* h) {
   h->n_slots = (uint32_t)h->h_slot_node.size();
   h->max_part_slots = max_mp;
   h->words_per_row = std::max<uint32_t>(4, ((max_mp + 31) / 32 + 3) / 4 * 4);  // 16-byte rows for the bulk copies
-  h->v2_ring = commit2_ring_slots(max_mp, h->words_per_row, h->n_gres_entries > 0, h->v2_budget);
+  h->v2_ring = commit2_ring_slots(max_mp, h->words_per_row, h->n_gres_entries > 0, h->v2_budget, h->max_comp_parts);
   if (max_mp > 65000 || h->v2_ring == 0)
     return fail(h, CRANE_ENOSYS, "cluster: partition with %u usable nodes exceeds the per-SM state budget", max_mp);
   // res_total classes per partition (distinct rows), cached in shared memory by the commit kernel
@@ -405,6 +454,10 @@ static int build_layout(crane_sched* h) {
   H2D(h->d_slot_class, slot_class.data(), slot_class.size());
   H2D(h->d_class_rows, class_rows.data(), class_rows.size());
   H2D(h->d_slot_resv, slot_resv.data(), slot_resv.size());
+  H2D(h->d_slot_memb, slot_memb.data(), slot_memb.size());
+  H2D(h->d_sched_nparts, h->h_sched_nparts.data(), h->h_sched_nparts.size());
+  H2D(h->d_part_comp, h->h_part_comp.data(), h->h_part_comp.size());
+  H2D(h->d_part_cidx, h->h_part_cidx.data(), h->h_part_cidx.size());
   H2D(h->d_rsv_off, rsv_off.data(), rsv_off.size());
   H2D(h->d_rsv_id, rsv_id.data(), rsv_id.size());
   H2D(h->d_rsv_res, rsv_res.data(), rsv_res.size());
@@ -519,13 +572,18 @@ int crane_sched_set_shard(crane_sched_t* h, uint32_t rank, uint32_t n_ranks, con
   h->h_part_list.clear();
   if (n_ranks > 1) {
     if (!part_owner && h->n_parts) return fail(h, CRANE_EINVAL, "set_shard: null owner table");
+    std::vector<uint32_t> sched_owner(h->n_vparts, 0);  // reservations: rank 0
     for (uint32_t p = 0; p < h->n_parts; ++p) {
       if (part_owner[p] >= n_ranks) return fail(h, CRANE_EINVAL, "set_shard: partition %u owned by rank %u of %u", p, part_owner[p], n_ranks);
       h->h_part_owner.push_back(part_owner[p]);
-      if (part_owner[p] == rank) h->h_part_list.push_back(p);
+      const uint32_t c = h->h_part_comp[p];
+      if (h->h_part_cidx[p] == 0) sched_owner[c] = part_owner[p];
+      else if (sched_owner[c] != part_owner[p])
+        return fail(h, CRANE_EINVAL, "set_shard: partitions that share nodes must have one owner (partition %u)", p);
     }
-    if (rank == 0)
-      for (uint32_t r = 0; r < h->n_resv; ++r) h->h_part_list.push_back(h->n_parts + r);  // reservations: rank 0
+    for (uint32_t c = 0; c < h->n_vparts; ++c)
+      if (sched_owner[c] == rank) h->h_part_list.push_back(c);
+    H2D(h->d_sched_owner, sched_owner.data(), sched_owner.size());
     H2D(h->d_part_owner, h->h_part_owner.data(), h->h_part_owner.size());
     H2D(h->d_part_list, h->h_part_list.data(), h->h_part_list.size());
     CU(cudaStreamSynchronize(h->stream));
@@ -812,6 +870,7 @@ int crane_sched_pending_erase(crane_sched_t* h, const uint32_t* rows, uint32_t n
     if (!h->h_dead[rows[k]]) { h->h_dead[rows[k]] = 1; h->n_dead++; }
   H2D(h->d_erase_rows, rows, n);
   CRANE_LAUNCH(k_mark_dead, (n + 255) / 256, 256, 0, h->stream, h->d_erase_rows.p, n, h->d_dead.p);
+  CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
   return CRANE_OK;
 }
@@ -841,6 +900,7 @@ int crane_sched_upload(crane_sched_t* h, const crane_running_t* rn, const crane_
   rc = set_running(h, rn);
   if (rc != CRANE_OK) return rc;
   CU(cudaEventRecord(h->ev[1], h->stream));
+  h->h2d_timed = true;
   h->uploaded = true;
   h->ran = false;
   return CRANE_OK;
@@ -850,6 +910,7 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
   if (!h) return CRANE_EINVAL;
   if (!h->uploaded) return fail(h, CRANE_EINVAL, "run: upload first");
   CU(cudaSetDevice(h->device));
+  (void)cudaGetLastError();  // a stale error of an earlier, unrelated call in this process is not this run's
   cudaStream_t st = h->stream;
   const uint32_t N = h->n_pending, R = h->n_running;
   h->timing.kernel_launches = 0;
@@ -901,6 +962,10 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
   cl.n_slots = h->n_slots;
   cl.n_parts = h->n_parts;
   cl.n_vparts = h->n_vparts;
+  cl.n_comp = h->n_comp;
+  cl.part_comp = h->d_part_comp.p;
+  cl.part_cidx = h->d_part_cidx.p;
+  cl.slot_memb = h->max_comp_parts > 1 ? h->d_slot_memb.p : nullptr;
   cl.n_resv = h->n_resv;
   cl.resv_start = h->d_resv_start.p;
   cl.resv_end = h->d_resv_end.p;
@@ -1004,7 +1069,7 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
     if (nq_cap) {
       // n_queued <= nq_cap lives on the device (part_job_off[n_parts]); the
       // kernels below bound themselves with it.
-      CRANE_LAUNCH(k_build_jobq, (nq_cap + 127) / 128, 128, 0, st, pd, queue, h->d_part_job_off.p + h->n_vparts, h->d_jobq.p, (uint32_t)h->dict_slot, h->d_vpart.p);
+      CRANE_LAUNCH(k_build_jobq, (nq_cap + 127) / 128, 128, 0, st, pd, queue, h->d_part_job_off.p + h->n_vparts, h->d_jobq.p, (uint32_t)h->dict_slot, h->d_vpart.p, h->n_comp, h->d_part_cidx.p);
       h->timing.kernel_launches++;
     }
   } else {
@@ -1018,7 +1083,7 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
     uint32_t wpb = 8;
     uint32_t nb = std::min<uint32_t>((nq_cap + wpb - 1) / wpb, 148 * 8);
     CRANE_LAUNCH(k_feas_bitmap, nb, wpb * 32, 0, st, cl, pd, h->d_jobq.p, h->d_part_job_off.p + h->n_vparts, h->words_per_row, h->d_bitmap.p,
-                 h->shard_n > 1 ? h->d_part_owner.p : nullptr, h->shard_rank, (uint32_t)h->dict_slot);
+                 h->shard_n > 1 ? h->d_sched_owner.p : nullptr, h->shard_rank, (uint32_t)h->dict_slot);
     h->timing.kernel_launches++;
   }
   CU(cudaEventRecord(h->ev[5], st));
@@ -1032,10 +1097,12 @@ int crane_sched_run(crane_sched_t* h, int64_t now) {
     CU(h->d_prof.ensure((size_t)h->n_vparts * 16));
     c2.prof = h->d_prof.p;
     c2.gres = h->dict.n_entries > 0 ? 1u : 0u;
+    c2.sched_nparts = h->max_comp_parts > 1 ? h->d_sched_nparts.p : nullptr;
+    c2.slot_memb = h->d_slot_memb.p;
     c2.dslot = (uint32_t)h->dict_slot;
     c2.req_node = h->d_req_node.p;
     c2.req_task = h->d_req_task.p;
-    size_t smem = commit2_smem_bytes(h->max_part_slots, h->words_per_row, c2.gres != 0, h->v2_ring);
+    size_t smem = commit2_smem_bytes(h->max_part_slots, h->words_per_row, c2.gres != 0, h->v2_ring, h->max_comp_parts);
     uint32_t grid = h->n_vparts;
     if (h->shard_n > 1) {
       c2.part_list = h->d_part_list.p;
@@ -1082,7 +1149,8 @@ int crane_sched_fetch(crane_sched_t* h, crane_placements_t* out) {
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
   float ms = 0;
-  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing.h2d_ms = ms;
+  // (the upload events exist only after crane_sched_upload: a resident table is filled piecewise)
+  if (h->h2d_timed) { cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing.h2d_ms = ms; } else h->timing.h2d_ms = 0.f;
   cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->timing.init_ms = ms;
   cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->timing.priority_ms = ms;
   cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->timing.feas_ms = ms;
@@ -1135,7 +1203,8 @@ int crane_sched_qos_filter(crane_sched_t* h, const crane_qos_table_t* qt, uint8_
   if (!h->have_qos_cols) return fail(h, CRANE_EINVAL, "qos_filter: pending.qos / pending.user were not uploaded");
   CU(cudaSetDevice(h->device));
   const uint32_t N = h->n_pending, Q = qt->n_qos, U = qt->n_users, A = qt->n_accounts;
-  if (Q == 0 || Q > 65535) return fail(h, CRANE_EINVAL, "qos_filter: n_qos out of range");
+  if (Q == 0 || Q >= 65535) return fail(h, CRANE_EINVAL, "qos_filter: n_qos out of range");
+  if (A > 65535) return fail(h, CRANE_ENOSYS, "qos_filter: more than 65535 accounts");
   if (!qt->valid || !qt->max_jobs_per_user || !qt->max_jobs_per_account || !qt->max_jobs ||
       !qt->max_cpus_per_user_raw || !qt->max_wall || !qt->max_tres_per_user || !qt->max_tres_per_account ||
       !qt->max_tres || !qt->chain_off || !qt->user_usage || !qt->qos_usage || (A && !qt->account_usage))
@@ -1190,15 +1259,36 @@ int crane_sched_qos_filter(crane_sched_t* h, const crane_qos_table_t* qt, uint8_
   q.n_alloc = h->d_out_nalloc.p; q.alloc_off = h->d_alloc_off.p; q.alloc_res = h->d_out_res.p;
   q.reason = h->d_reason.p;
   if (N) {
-    CRANE_LAUNCH(k_qos_filter, Q + 1, 32, 0, h->stream, q, h->dict);
+    // the jobs the pass walks, grouped by qos in job-id order: key + stable radix sort
+    const int bits = Q < 255 ? 8 : 16;
+    const uint64_t sentinel = (1ull << bits) - 1;
+    CU(cudaEventRecord(h->ev[8], h->stream));
+    CU(h->d_keys_a.ensure(N)); CU(h->d_keys_b.ensure(N)); CU(h->d_vals_a.ensure(N)); CU(h->d_vals_b.ensure(N));
+    CRANE_LAUNCH(k_qos_keys, (N + 255) / 256, 256, 0, h->stream, q, h->d_keys_a.p, h->d_vals_a.p, sentinel);
+    uint64_t* keys;
+    uint32_t* list;
+    int rc = radix_sort(h, N, bits, &keys, &list);
+    if (rc != CRANE_OK) return rc;
+    CU(h->d_q_off.ensure((size_t)Q + 1));
+    CRANE_LAUNCH(k_qos_offsets, (Q + 1 + 127) / 128, 128, 0, h->stream, keys, N, Q, h->d_q_off.p);
+    // the usage column of one qos in shared memory when it fits beside the job buffers
+    const size_t table_bytes = ((size_t)U + A) * sizeof(crane_meta_resource_t);
+    const bool force_global = getenv("CRANE_QOS_TABLES_GLOBAL") != nullptr;  // tests: the path of tables that do not fit
+    const uint32_t in_smem = !force_global && table_bytes + 40 * 1024 <= h->v2_budget ? 1u : 0u;
+    const size_t dyn = in_smem ? table_bytes : 0;
+    CU(cudaFuncSetAttribute(k_qos_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CRANE_LAUNCH(k_qos_chain, Q, kQosThreads, dyn, h->stream, q, h->dict, list, h->d_q_off.p, in_smem);
     CU(cudaGetLastError());
-    h->timing.kernel_launches += 1;
+    CU(cudaEventRecord(h->ev[9], h->stream));
+    h->timing.kernel_launches += 3;
   }
   if (N) CU(cudaMemcpyAsync(reason, h->d_reason.p, N, cudaMemcpyDeviceToHost, h->stream));
   if ((size_t)U * Q) CU(cudaMemcpyAsync(qt->user_usage, h->d_q_user_usage.p, (size_t)U * Q * sizeof(crane_meta_resource_t), cudaMemcpyDeviceToHost, h->stream));
   if ((size_t)A * Q) CU(cudaMemcpyAsync(qt->account_usage, h->d_q_acct_usage.p, (size_t)A * Q * sizeof(crane_meta_resource_t), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(qt->qos_usage, h->d_q_qos_usage.p, (size_t)Q * sizeof(crane_meta_resource_t), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  h->timing.qos_ms = 0.f;
+  if (N) cudaEventElapsedTime(&h->timing.qos_ms, h->ev[8], h->ev[9]);
   return CRANE_OK;
 }
 

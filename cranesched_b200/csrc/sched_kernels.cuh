@@ -89,7 +89,11 @@ constexpr int kMaxClasses = 16;  // distinct res_total rows cached per partition
 struct ClusterDev {
   uint32_t n_slots;           // node states: usable nodes of the partitions, then the nodes of every reservation
   uint32_t n_parts;           // partitions of the cluster
-  uint32_t n_vparts;          // schedulers: n_parts + one per reservation (JobScheduler.cpp:5757-5766)
+  uint32_t n_comp;            // schedulers of partitions: one per connected group of overlapping partitions
+  uint32_t n_vparts;          // schedulers: n_comp + one per reservation (JobScheduler.cpp:5757-5766)
+  const uint32_t* part_comp;  // [n_parts] scheduler of a partition
+  const uint32_t* part_cidx;  // [n_parts] index of the partition inside its scheduler
+  const uint8_t* slot_memb;   // [n_slots] bit i: the node is in partition i of its scheduler (null: no overlap)
   uint32_t n_resv;
   uint32_t max_part_slots;
   const uint32_t* part_base;  // [n_vparts+1] slot ranges
@@ -484,7 +488,9 @@ __global__ void k_queue_keys(PendingDev pd, const uint32_t* order, const double*
   if (rv != 0xffffffffu) {
     miss = CRANE_REASON_RESV_NOT_FOUND;
     found = rv < cl.n_resv && now >= cl.resv_start[rv] && now < cl.resv_end[rv];
-    p = cl.n_parts + rv;
+    p = cl.n_comp + rv;
+  } else if (found) {
+    p = cl.part_comp[p];
   }
   uint64_t k = 0;
   if (pd.dead && pd.dead[j]) {
@@ -519,7 +525,8 @@ __global__ void k_part_offsets(const uint32_t* part_count, uint32_t n_parts, uin
 
 // JobQ records in final queue order (coalesced 96-byte records for the commit
 // kernel); min_res_view of JobScheduler.cpp:5190-5192.
-__global__ void k_build_jobq(PendingDev pd, const uint32_t* queue, const uint32_t* n_queued_ptr, JobQ* jobq, uint32_t dslot, const uint32_t* vpart) {
+__global__ void k_build_jobq(PendingDev pd, const uint32_t* queue, const uint32_t* n_queued_ptr, JobQ* jobq, uint32_t dslot, const uint32_t* vpart,
+                             uint32_t cl_n_comp, const uint32_t* part_cidx) {
   const GresDict& c_dict = c_dicts[dslot];
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= *n_queued_ptr) return;
@@ -536,6 +543,8 @@ __global__ void k_build_jobq(PendingDev pd, const uint32_t* queue, const uint32_
   q.ntpn_max = pd.ntasks_per_node_max[j];
   q.ntasks = pd.ntasks[j];
   q.vpart = vpart[j];
+  // partition inside a scheduler of overlapping partitions (bits 16-18)
+  if (q.vpart < cl_n_comp && part_cidx) q.flags |= (part_cidx[pd.partition[j]] & 7u) << 16;
   // anything but "exactly ntasks_per_node tasks on each of node_num nodes" takes the general
   // task distribution (JobScheduler.cpp:5193-5222, 5340-5361)
   if (q.ntpn_max != t || (uint64_t)t * q.node_num != q.ntasks) q.flags |= 4u;
@@ -676,7 +685,8 @@ __global__ void k_feas_bitmap(ClusterDev cl, PendingDev pd, const JobQ* jobq, co
   for (uint32_t r = blockIdx.x * warps_per_block + warp_id(); r < n_queued; r += gridDim.x * warps_per_block) {
     JobQ jq = jobq[r];
     uint32_t p = jq.vpart;
-    if (part_owner && (p < cl.n_parts ? part_owner[p] : 0u) != rank) continue;  // another GPU commits this partition
+    if (part_owner && part_owner[p] != rank) continue;  // another GPU commits this scheduler
+    const uint32_t cidx = (jq.flags >> 16) & 7u;
     uint32_t base = cl.part_base[p], mp = cl.part_base[p + 1] - base;
     const uint32_t row_words = (mp + 31) / 32;          // words beyond the job's own partition are never read
     uint32_t il = 0, ih = 0, el = 0, eh = 0;
@@ -687,8 +697,8 @@ __global__ void k_feas_bitmap(ClusterDev cl, PendingDev pd, const JobQ* jobq, co
       bool ok = false;
       if (q < mp) {
         uint32_t node = cl.slot_node[base + q];
-        ok = true;
-        if (ih > il) {  // included_nodes non-empty: node must be listed
+        ok = !cl.slot_memb || ((cl.slot_memb[base + q] >> cidx) & 1u);  // overlapping partitions: a member of the job's own
+        if (ok && ih > il) {  // included_nodes non-empty: node must be listed
           ok = false;
           for (uint32_t k = il; k < ih; ++k) ok |= pd.incl_nodes[k] == node;
         }

@@ -39,18 +39,46 @@ def shard_workload(config_id: int, rank: int, world: int, n_jobs: int = 0, n_nod
     return gen(**kw)
 
 
-def deal_partitions(pending: abi.Pending, n_partitions: int, world: int) -> np.ndarray:
+def partition_groups(cluster: abi.Cluster) -> np.ndarray:
+    """partition -> group id; partitions that share a node (directly or through a
+    chain of partitions) are one group: they are one scheduler of the library and
+    must have one owner."""
+    n = cluster.n_partitions
+    parent = list(range(n))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    first = {}
+    for p in range(n):
+        for node in cluster.part_nodes[cluster.part_off[p]:cluster.part_off[p + 1]].tolist():
+            q = first.setdefault(node, p)
+            a, b = find(q), find(p)
+            if a != b:
+                parent[max(a, b)] = min(a, b)
+    return np.array([find(p) for p in range(n)], np.uint32)
+
+
+def deal_partitions(pending: abi.Pending, n_partitions: int, world: int, cluster: abi.Cluster = None) -> np.ndarray:
     """partition -> rank, longest processing time first on the job counts (the
     tick of a rank is the longest job loop among its partitions, and one GPU
-    runs its partitions concurrently, so what matters is to spread the big ones)."""
+    runs its partitions concurrently, so what matters is to spread the big ones).
+    With `cluster`, groups of overlapping partitions are dealt as one."""
     njobs = np.bincount(pending.partition[pending.partition < n_partitions], minlength=n_partitions)
+    group = partition_groups(cluster) if cluster is not None else np.arange(n_partitions, dtype=np.uint32)
+    gjobs = np.bincount(group, weights=njobs, minlength=n_partitions)
     load = np.zeros(world, np.int64)
-    owner = np.zeros(n_partitions, np.uint32)
-    for p in np.argsort(-njobs, kind="stable"):
+    gowner = np.zeros(n_partitions, np.uint32)
+    for g in np.argsort(-gjobs, kind="stable"):
+        if not (group == g).any():
+            continue
         r = int(np.argmin(load))
-        owner[p] = r
-        load[r] += njobs[p]
-    return owner
+        gowner[g] = r
+        load[r] += int(gjobs[g])
+    return gowner[group].astype(np.uint32)
 
 
 class _DevArray:

@@ -425,6 +425,26 @@ def random_case(seed, n_jobs=300, n_nodes=48, n_parts=3, n_running=40, fifo=Fals
     return cfg, cluster, running, pend, NOW
 
 
+def overlap_partitions(case, seed, frac=0.4, which=None):
+    """The same case with overlapping partitions: every partition (or only those in
+    `which`) also lists a share of the previous partition's nodes, so those nodes have
+    ONE NodeState seen by two LocalSchedulers (JobScheduler.cpp:5597-5651)."""
+    import dataclasses
+    cfg, cl, rn, pd, now = case
+    rng = np.random.Generator(np.random.PCG64(seed * 31 + 5))
+    lists = [cl.part_nodes[cl.part_off[p]:cl.part_off[p + 1]].tolist() for p in range(cl.n_partitions)]
+    out = [list(lists[0])]
+    for p in range(1, cl.n_partitions):
+        prev = lists[p - 1]
+        k = int(len(prev) * frac) if which is None or p in which else 0
+        extra = rng.choice(prev, k, replace=False).tolist() if k else []
+        out.append(sorted(set(lists[p]) | set(extra)))
+    off = np.cumsum([0] + [len(x) for x in out]).astype(np.uint32)
+    nodes = np.array([n for x in out for n in x], np.uint32)
+    cl2 = dataclasses.replace(cl, part_off=off, part_nodes=nodes)
+    return cfg, cl2, rn, pd, now
+
+
 def random_reservations(seed, case, n_resv=4, frac_jobs=0.15, single_node=False):
     """Reservations over a random_case-style case: a mix of expired, active and
     later ones (ResvMeta, Node/NodeDefs.h:81-97); each reserves part of a few

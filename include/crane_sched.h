@@ -228,6 +228,7 @@ typedef struct crane_sched_timing {
   float d2h_ms;
   float total_ms;
   uint32_t kernel_launches;
+  float qos_ms;      /* device time of the last crane_sched_qos_filter (R12)     */
 } crane_sched_timing_t;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -240,7 +241,12 @@ const char* crane_sched_last_error(const crane_sched_t* h);
 
 /* Replaces: the node/partition snapshot NodeSelect takes from
  * g_meta_container every tick (JobScheduler.cpp:5603-5651). Call when the node
- * set, alive/drain flags or partition membership change. */
+ * set, alive/drain flags or partition membership change.
+ * A node may be listed by several partitions: it then has ONE state shared by
+ * their LocalSchedulers (JobScheduler.cpp:5622), and every connected group of
+ * such partitions is scheduled as one unit, job by job in priority order, each
+ * job in its own partition's node order (at most 8 partitions per group, else
+ * CRANE_ENOSYS). Partitions that share nothing keep their independent loops. */
 int crane_sched_set_cluster(crane_sched_t* h, const crane_cluster_t* cluster);
 
 /* Replaces: the reservation snapshot of NodeSelect (JobScheduler.cpp:5655-5713).
@@ -301,7 +307,8 @@ int crane_sched_get_timing(const crane_sched_t* h, crane_sched_timing_t* t);
  * rank does not own (a job without a valid partition belongs to rank 0), which
  * makes the union over ranks a plain sum: one all-reduce(sum) per column of
  * crane_sched_device_placements(), then crane_sched_fetch on any rank returns the
- * whole tick. n_ranks == 1 (the default) switches sharding off. */
+ * whole tick. n_ranks == 1 (the default) switches sharding off. Partitions
+ * that share nodes are one unit and must have one owner (CRANE_EINVAL). */
 int crane_sched_set_shard(crane_sched_t* h, uint32_t rank, uint32_t n_ranks,
                           const uint32_t* part_owner /* [n_partitions] */);
 

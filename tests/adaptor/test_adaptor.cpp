@@ -7,7 +7,10 @@
 #include <cstring>
 #include <map>
 #include <random>
+#include <climits>
+#include <cstdint>
 #include <set>
+#include <string>
 
 #include "../../cranesched_b200/adaptor/crane_adaptor.h"
 #include "../../oracle/crane_oracle.h"
@@ -61,7 +64,8 @@ int main() {
   std::vector<uint8_t> excl_flag(N, 0);
   std::vector<double> mand(N, 0.0);
   std::vector<crane_res_view_t> rn_(N), rt(N), rtot(N);
-  std::map<std::string, uint32_t> acc_id;
+  std::map<std::string, uint32_t> acc_id, user_id;
+  std::vector<uint32_t> user(N);
   for (int i = 0; i < N; ++i) {
     auto j = std::make_unique<PdJobInScheduler>();
     const bool gpu = U(0, 2) == 0;
@@ -102,6 +106,10 @@ int main() {
     node_num[i] = j->node_num; ntasks[i] = j->ntasks; ntpn[i] = 1; pp[i] = j->partition_priority; qp[i] = j->qos_priority;
     if (!acc_id.count(j->account)) { uint32_t id = (uint32_t)acc_id.size(); acc_id[j->account] = id; }
     acc[i] = acc_id[j->account];
+    if (!user_id.count(j->username)) { uint32_t id = (uint32_t)user_id.size(); user_id[j->username] = id; }
+    user[i] = user_id[j->username];
+    // account chain: the job's account, its department, the root (PdJobInScheduler::account_chain)
+    j->account_chain = {j->account, std::string("dept") + (j->account.back() < '2' ? "A" : "B"), "root"};
     tl[i] = j->time_limit; sub[i] = j->submit_time;
     for (const auto& id : j->excluded_nodes) excl.push_back((uint32_t)atoi(id.c_str() + 2));
     excl_off[i + 1] = (uint32_t)excl.size();
@@ -124,7 +132,7 @@ int main() {
   memset(&pd, 0, sizeof pd);
   pd.n = N; pd.partition = partition.data(); pd.time_limit = tl.data(); pd.submit_time = sub.data(); pd.node_num = node_num.data();
   pd.ntasks = ntasks.data(); pd.ntasks_per_node_min = ntpn.data(); pd.ntasks_per_node_max = ntpn.data(); pd.exclusive = excl_flag.data();
-  pd.partition_priority = pp.data(); pd.qos_priority = qp.data(); pd.account = acc.data(); pd.qos = zero.data(); pd.user = zero.data();
+  pd.partition_priority = pp.data(); pd.qos_priority = qp.data(); pd.account = acc.data(); pd.qos = zero.data(); pd.user = user.data();
   pd.mandated_priority = mand.data(); pd.req_node = rn_.data(); pd.req_task = rt.data(); pd.req_total = rtot.data();
   pd.incl_off = incl_off.data(); pd.incl_nodes = incl.data(); pd.excl_off = excl_off.data(); pd.excl_nodes = excl.data();
   crane_running_t rnj;
@@ -171,5 +179,90 @@ int main() {
     reserved += !j.is_scheduled() && !j.craned_ids.empty();
   }
   printf("adaptor: %d jobs, %d start now, %d reserved, %d mismatches vs oracle\n", N, started, reserved, bad);
-  return bad ? 1 : 0;
+  if (bad) return 1;
+
+  // ---- the QoS stage behind NodeSelect (JobScheduler.cpp:1262) ---------------------------
+  // adaptor: reference-style objects; oracle: the same limits and usage as C-ABI tables
+  std::map<std::string, Qos> qos_table;
+  Qos normal;
+  normal.max_jobs_per_user = 9;
+  normal.max_jobs_per_account = 14;
+  normal.max_cpus_per_user_raw = 40 * 256;
+  normal.max_wall = 400000;
+  normal.max_tres_per_account.cpu_count_raw = 70 * 256;
+  normal.max_tres.memory_bytes = 300ull << 30;
+  normal.max_tres_per_user.gres_map["gpu"].total = 6;
+  normal.max_tres_per_user.gres_map["gpu"].specified["h100"] = 2;
+  qos_table["normal"] = normal;
+  QosUsage usage;
+  usage.user["user1"]["normal"].jobs_count = 7;            // close to its job limit before the pass
+  usage.user["user1"]["normal"].resource.cpu_count_raw = 8 * 256;
+  usage.account["root"]["normal"].wall_time = 1000;
+  algo.CheckAndMallocQosResource(qos_table, usage, pending);
+
+  // account ids: job accounts in first-appearance order (as for the fair-share column), then chain parents
+  for (int i = 0; i < N; ++i)
+    for (const auto& a : pending[i]->account_chain)
+      if (!acc_id.count(a)) { uint32_t id = (uint32_t)acc_id.size(); acc_id[a] = id; }
+  const uint32_t Q = 1, NU = (uint32_t)user_id.size(), NA = (uint32_t)acc_id.size();
+  std::vector<uint32_t> chain_off(N + 1, 0), chain;
+  for (int i = 0; i < N; ++i) {
+    for (const auto& a : pending[i]->account_chain) chain.push_back(acc_id[a]);
+    chain_off[i + 1] = (uint32_t)chain.size();
+  }
+  uint8_t valid = 1;
+  crane_tres_limit_t tu, ta, tq;
+  memset(&tu, 0, sizeof tu); memset(&ta, 0, sizeof ta); memset(&tq, 0, sizeof tq);
+  tu.view.cpu_raw = ta.view.cpu_raw = tq.view.cpu_raw = INT64_MAX;
+  tu.view.mem = ta.view.mem = tq.view.mem = UINT64_MAX;
+  tu.view.mem_sw = ta.view.mem_sw = tq.view.mem_sw = UINT64_MAX;
+  ta.view.cpu_raw = 70 * 256;
+  tq.view.mem = 300ull << 30;
+  tu.gres_name_present = 1; tu.view.gres_total[0] = 6;
+  tu.gres_spec_present = 2; tu.view.gres_spec[1] = 2;
+  std::vector<crane_meta_resource_t> uu(NU), au(NA), qu(Q);
+  memset(uu.data(), 0, sizeof(crane_meta_resource_t) * NU);
+  memset(au.data(), 0, sizeof(crane_meta_resource_t) * NA);
+  memset(qu.data(), 0, sizeof(crane_meta_resource_t) * Q);
+  uu[user_id["user1"]].jobs_count = 7;
+  uu[user_id["user1"]].cpu_raw = 8 * 256;
+  au[acc_id["root"]].wall_time = 1000;
+  crane_qos_table_t qt;
+  memset(&qt, 0, sizeof qt);
+  qt.n_qos = Q; qt.n_users = NU; qt.n_accounts = NA; qt.valid = &valid;
+  qt.max_jobs_per_user = &normal.max_jobs_per_user; qt.max_jobs_per_account = &normal.max_jobs_per_account; qt.max_jobs = &normal.max_jobs;
+  qt.max_cpus_per_user_raw = &normal.max_cpus_per_user_raw; qt.max_wall = &normal.max_wall;
+  qt.max_tres_per_user = &tu; qt.max_tres_per_account = &ta; qt.max_tres = &tq;
+  qt.chain_off = chain_off.data(); qt.chain_acct = chain.data();
+  qt.user_usage = uu.data(); qt.account_usage = au.data(); qt.qos_usage = qu.data();
+  if (crane_oracle_qos_filter(&cl, &pd, &out, &qt) != 0) { printf("oracle qos filter failed\n"); return 2; }
+  auto qos_str = [&](uint8_t c) -> std::string {
+    switch (c) {
+      case 16: return "QosCpuResourceLimit"; case 17: return "QosJobsResourceLimit"; case 18: return "QosWallTimeLimit";
+      case 19: return "QosMemResourceLimit"; case 20: return "QosGresResourceLimit"; case 21: return "InvalidQOS";
+      default: return reason_str[c];
+    }
+  };
+  int qbad = 0, refused = 0;
+  std::set<std::string> kinds;
+  for (int i = 0; i < N; ++i) {
+    if (pending[i]->reason != qos_str(o_reason[i])) { if (qbad < 5) printf("QOS MISMATCH job %d: '%s' vs '%s'\n", i, pending[i]->reason.c_str(), qos_str(o_reason[i]).c_str()); ++qbad; }
+    if (o_reason[i] >= 16) { ++refused; kinds.insert(qos_str(o_reason[i])); }
+  }
+  auto same = [&](const MetaResource& a, const crane_meta_resource_t& b) {
+    uint64_t gt = 0, a100 = 0, h100 = 0;
+    auto it = a.resource.gres_map.find("gpu");
+    if (it != a.resource.gres_map.end()) {
+      gt = it->second.total;
+      if (it->second.specified.count("a100")) a100 = it->second.specified.at("a100");
+      if (it->second.specified.count("h100")) h100 = it->second.specified.at("h100");
+    }
+    return a.resource.cpu_count_raw == b.cpu_raw && a.resource.memory_bytes == b.mem && a.jobs_count == b.jobs_count && a.wall_time == b.wall_time &&
+           gt == b.gres_total[0] && a100 == b.gres_spec[0] && h100 == b.gres_spec[1];
+  };
+  for (const auto& [name, id] : user_id) if (!same(usage.user[name]["normal"], uu[id])) { printf("QOS usage of user %s differs\n", name.c_str()); ++qbad; }
+  for (const auto& [name, id] : acc_id) if (!same(usage.account[name]["normal"], au[id])) { printf("QOS usage of account %s differs\n", name.c_str()); ++qbad; }
+  if (!same(usage.qos["normal"], qu[0])) { printf("QOS usage of the qos differs\n"); ++qbad; }
+  printf("adaptor qos: %d refused (%zu kinds), %d mismatches vs oracle\n", refused, kinds.size(), qbad);
+  return qbad || refused == 0 ? 1 : 0;
 }

@@ -24,11 +24,11 @@ def _build_and_run(lib_path, exe):
 def test_adaptor_on_emulated_kernels(oracle, emu_lib):
     r = _build_and_run(emu_lib, "test_adaptor_emu")
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "0 mismatches" in r.stdout
+    assert "0 mismatches" in r.stdout and "adaptor qos:" in r.stdout
 
 
 @pytest.mark.gpu
 def test_adaptor_on_gpu(oracle, gpu_lib):
     r = _build_and_run(gpu_lib, "test_adaptor_gpu")
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "0 mismatches" in r.stdout
+    assert "0 mismatches" in r.stdout and "adaptor qos:" in r.stdout

@@ -37,6 +37,31 @@ def test_emulated_reservations(oracle, emu_lib):
         assert_same(ref, got)
 
 
+def test_emulated_overlapping_partitions(oracle, emu_lib):
+    """Partitions sharing nodes: one NodeState per node seen by several LocalSchedulers
+    (JobScheduler.cpp:5597-5651) — one scheduler per connected group here, one order per
+    partition, jobs one by one in global priority order."""
+    for seed, which in ((601, None), (604, {1}), (606, None)):
+        base = synth.random_case(seed, n_jobs=120, n_nodes=28, n_parts=2 + seed % 3, n_running=10, short=bool(seed & 1))
+        case = synth.overlap_partitions(base, seed, frac=0.3 + 0.1 * (seed % 4), which=which)
+        ref, _, _ = oracle.node_select(*case[:4], case[4])
+        got, _ = run_sched(case, emu_lib)
+        assert_same(ref, got)
+        check_invariants(case, got)
+
+
+def test_too_many_overlapping_partitions_is_refused(emu_lib):
+    """More than 8 partitions in one connected group: CRANE_ENOSYS from set_cluster."""
+    from cranesched_b200 import abi
+    from cranesched_b200.scheduler import CraneSchedError, GpuScheduler
+    case = synth.overlap_partitions(synth.random_case(610, n_jobs=20, n_nodes=40, n_parts=10, n_running=0), 610, 1.0)
+    s = GpuScheduler(case[0], 0, emu_lib)
+    with pytest.raises(CraneSchedError) as e:
+        s.set_cluster(case[1])
+    assert e.value.code == abi.ENOSYS and "overlap" in str(e.value)
+    s.close()
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_emulated_kernels_match_oracle(oracle, emu_lib, name):
     case = CASES[name]()

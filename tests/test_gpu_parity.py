@@ -101,6 +101,24 @@ def test_reservations(oracle, gpu_lib, seed):
     assert_same(ref, got)
 
 
+@pytest.mark.parametrize("seed", range(600, 612))
+def test_overlapping_partitions(oracle, gpu_lib, seed):
+    """Partitions that share nodes (one NodeState seen by several LocalSchedulers,
+    JobScheduler.cpp:5597-5651): one scheduler per connected group, one order per
+    partition; also with reservations on top and groups beside stand-alone partitions."""
+    base = synth.random_case(seed, n_jobs=500, n_nodes=90, n_parts=2 + seed % 4, n_running=30,
+                             fifo=bool(seed % 5 == 0), ntpn_range=bool(seed % 3 == 0), short=bool(seed & 1))
+    case = synth.overlap_partitions(base, seed, frac=0.2 + 0.15 * (seed % 4), which=None if seed % 3 else {1})
+    cfg, cl, rn, pd, now = case
+    resv = None
+    if seed % 4 == 1:
+        resv, pd, rn = synth.random_reservations(seed, case, n_resv=4)
+    ref, _, _ = oracle.node_select(cfg, cl, rn, pd, now, resv=resv)
+    got, _ = run_sched((cfg, cl, rn, pd, now), gpu_lib, resv=resv)
+    assert_same(ref, got)
+    check_invariants((cfg, cl, rn, pd, now), got)
+
+
 def test_batch_limit(oracle, gpu_lib):
     """ScheduledBatchSize: ranks beyond the limit get "Priority"."""
     case = synth.random_case(50, n_jobs=500, n_nodes=40, n_running=20, limit=137)

@@ -149,8 +149,12 @@ def _parity(oracle, lib_path, case, table, device=0):
     return ref
 
 
-def test_emulated_kernel_matches_oracle(oracle, emu_lib):
-    case = synth.random_case(21, n_jobs=120, n_nodes=24, n_running=8)
+@pytest.mark.parametrize("in_global", [False, True])
+def test_emulated_kernel_matches_oracle(oracle, emu_lib, monkeypatch, in_global):
+    if in_global:
+        monkeypatch.setenv("CRANE_QOS_TABLES_GLOBAL", "1")
+    # more than one prepared batch (96 jobs) per qos
+    case = synth.random_case(21, n_jobs=420, n_nodes=60, n_running=8)
     table = synth.random_qos(21, case[1], case[3], tight=1.0)
     ref = _parity(oracle, emu_lib, case, table)
     assert (ref.reason >= 16).any()
@@ -164,6 +168,16 @@ def test_gpu_matches_oracle(oracle, seed, tight, invalid):
     ref = _parity(oracle, None, case, table)
     codes = set(np.unique(ref.reason).tolist())
     assert codes & {16, 17, 18, 19, 20, 21}
+
+
+@pytest.mark.gpu
+def test_gpu_usage_tables_in_global_memory(oracle, monkeypatch):
+    """The path of usage tables too large for shared memory (forced here)."""
+    monkeypatch.setenv("CRANE_QOS_TABLES_GLOBAL", "1")
+    case = synth.random_case(34, n_jobs=1500, n_nodes=160, n_parts=4, n_running=60)
+    table = synth.random_qos(34, case[1], case[3], tight=1.5, invalid_frac=0.1)
+    ref = _parity(oracle, None, case, table)
+    assert set(np.unique(ref.reason).tolist()) & {16, 17, 18, 19, 20, 21}
 
 
 @pytest.mark.gpu

@@ -166,3 +166,18 @@ def test_reservations(oracle, seed):
     d = a.diff(b)
     assert not d, "oracle differs from the reference's own NodeSelect:\n" + "\n".join(d[:8])
     assert (a.reason == abi.REASON_RESERVED).any() or (a.reason == 5).any() or seed % 4
+
+
+@pytest.mark.parametrize("seed", range(700, 712))
+def test_overlapping_partitions(oracle, seed):
+    """Partitions that share nodes: one NodeState per node, referenced by every
+    LocalScheduler whose partition lists it (JobScheduler.cpp:5597-5651), so a placement
+    in one partition changes what the others can start on the node (their own costs stay)."""
+    base = synth.random_case(seed, n_jobs=220, n_nodes=36, n_parts=2 + seed % 3, n_running=14,
+                             one_type_per_name=True, lists=bool(seed % 2), short=bool(seed % 3 == 0))
+    case = synth.overlap_partitions(base, seed, frac=0.25 + 0.15 * (seed % 4), which=None if seed % 3 else {1})
+    cfg, cl, rn, pd, now = case
+    a, _, _ = oracle.node_select(cfg, cl, rn, pd, now)
+    b, _ = pyref.node_select(cfg, cl, rn, pd, now)
+    d = a.diff(b)
+    assert not d, "oracle differs from the reference's own NodeSelect:\n" + "\n".join(d[:8])
