@@ -36,7 +36,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
 
 def build_prof(force: bool = True) -> str:
     """Profiling variant (-DCRANE_PROFILE: clock64 phase counters in k_commit); tools only."""
-    so = os.path.join(CSRC, "libcrane_sched_prof.so")
+    os.makedirs(os.path.join(ROOT, "tools", "variants"), exist_ok=True)
+    so = os.path.join(ROOT, "tools", "variants", "libcrane_sched_prof.so")
     cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--fmad=false",
            "-DCRANE_PROFILE", "-Xcompiler", "-fPIC", "-shared", "-o", so, os.path.join(CSRC, "sched_api.cu")]
     subprocess.check_call(cmd)

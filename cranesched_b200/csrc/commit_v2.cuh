@@ -403,6 +403,8 @@ __shared__ uint32_t s2_rk_node[kRK];
 __shared__ double s2_rk_nc[kRK];
 __shared__ uint32_t s2_ip[kRK], s2_rp[kRK], s2_np[kRK];
 __shared__ uint32_t s2_w[kT2 / 32];
+__shared__ uint32_t s2_ev_a[2 * kRK];  // re-key: sorted places where the survivors' shift changes (bit 31: a removal)
+__shared__ int s2_ev_d[2 * kRK];       // shift behind the event
 __shared__ long long s2_e[2][kNG];        // earliest fits: per task (batch) / per group max (one-job path)
 __shared__ long long s2_e2[2][kNG];       // per group min (one-job path)
 __shared__ long long s2_T0[kMaxJ];
@@ -636,16 +638,17 @@ __device__ __noinline__ void order_sort2() {
 // Re-key the `cnt` (<= kRK) distinct nodes s2_rk_node[] to the costs
 // s2_rk_nc[] (all threads; NodeSelector::UpdateCost, JobScheduler.h:520-532, for
 // every placed node at once). A surviving entry at old position p moves to
-// p - #removed before p + #new keys at or before p: one prefix sum over marks
-// in sm.scratch (zero on entry and exit), each warp scanning a contiguous
-// stretch of the affected range [first event, last event] — outside it nothing
-// moves, as many nodes are removed as inserted. A re-keyed node lands at
-// (survivors before its lower bound) + (its rank among the new keys).
+// p - #removed before p + #new keys at or before p, a shift that is constant
+// between the 2*cnt places where a node leaves or arrives: the events are
+// sorted and the affected range [first event, last event] is copied segment by
+// segment — outside it nothing moves, as many nodes are removed as inserted.
+// A re-keyed node lands at (survivors before its lower bound) + (its rank
+// among the new keys).
 __device__ __noinline__ void order_rekey2(uint32_t cnt, uint32_t nthr) {
   const Smem2 sm = SM2();
   const uint32_t mp = s2_cx.npos, tid = threadIdx.x, lane = lane_id(), wid = warp_id();  // positions of the current order
   if (cnt == 0) return;
-  const uint32_t ngr = nthr / kGL, nwp = nthr / 32;  // the first nthr threads of the CTA take part (named barrier 1)
+  const uint32_t ngr = nthr / kGL;  // the first nthr threads of the CTA take part (named barrier 1)
   if (tid == 0) { s2_pmin = mp; s2_pmax = 0; }
   named_bar_sync(1, nthr);
   const uint32_t gl = g_lane();
@@ -680,8 +683,6 @@ __device__ __noinline__ void order_rekey2(uint32_t cnt, uint32_t nthr) {
       const uint32_t rp = sm.posn[u];
       s2_ip[w] = lo;
       s2_rp[w] = rp;
-      atomicAdd(&sm.scratch[lo], 1u << 16);
-      atomicAdd(&sm.scratch[rp + 1], 1u);
       atomicMin(&s2_pmin, lo < rp ? lo : rp);
       atomicMax(&s2_pmax, lo > rp + 1 ? lo : rp + 1);
     }
@@ -706,53 +707,47 @@ __device__ __noinline__ void order_rekey2(uint32_t cnt, uint32_t nthr) {
     }
     if (act && gl == 0) s2_np[w] = s2_ip[w] - rem + rank;
   }
-  // marks [pmin, pmax] (pmax <= mp): warp w scans chunk w, lanes on consecutive words
+  // The survivors of [pmin, pmax) shift by (insertions at or before) - (removals before), which is
+  // constant between the 2*cnt places where it changes: sort those events (removals first at equal
+  // positions, so the vacated position ends the segment before it), then copy segment by segment.
   const uint32_t pmin = s2_pmin, pmax = s2_pmax;
-  const uint32_t len = pmax - pmin + 1;
-  const uint32_t chunk = ((len + nwp - 1) / nwp + 31u) & ~31u;
-  const uint32_t w0 = pmin + wid * chunk;
-  const uint32_t w1 = w0 + chunk < pmax + 1 ? w0 + chunk : pmax + 1;
-  uint32_t local = 0;
-  for (uint32_t p = w0 + lane; p < w1; p += 32) local += sm.scratch[p];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(kFullMask, local, o);
-  if (lane == 0) s2_w[wid] = local;
-  named_bar_sync(1, nthr);
-  uint32_t carry = 0;
-#pragma unroll
-  for (uint32_t w = 0; w < kT2 / 32; ++w) {
-    const uint32_t x = s2_w[w];
-    if (w < wid && w < nwp) carry += x;
-  }
-  for (uint32_t p0 = w0; p0 < w1; p0 += 32) {  // warp-uniform
-    const uint32_t p = p0 + lane;
-    const uint32_t d = p < w1 ? sm.scratch[p] : 0u;
-    uint32_t inc = d;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t up = __shfl_up_sync(kFullMask, inc, o);
-      if ((int)lane >= o) inc += up;
+  const uint32_t nev = 2u * cnt;
+  if (tid < nev) {
+    const bool is_ins = tid >= cnt;
+    const uint32_t x = is_ins ? tid - cnt : tid;
+    const uint32_t key = is_ins ? 2u * s2_ip[x] + 1u : 2u * (s2_rp[x] + 1u);
+    uint32_t rank = 0;
+    int d = is_ins ? 1 : -1;  // shift behind this event: every event up to and including it
+    for (uint32_t y = 0; y < cnt; ++y) {
+      const uint32_t kr = 2u * (s2_rp[y] + 1u), ki = 2u * s2_ip[y] + 1u;
+      const bool rb = kr < key || (kr == key && y < tid);
+      const bool ib = ki < key || (ki == key && y + cnt < tid);
+      rank += (rb ? 1u : 0u) + (ib ? 1u : 0u);
+      d += (ib ? 1 : 0) - (rb ? 1 : 0);
     }
-    const uint32_t run = carry + inc;
-    carry += __shfl_sync(kFullMask, inc, 31);
-    if (p < w1 && p < mp && (sm.scratch[p + 1] & 0xffffu) == 0) {  // not one of the re-keyed nodes
+    s2_ev_a[rank] = (key >> 1) | (is_ins ? 0u : 0x80000000u);
+    s2_ev_d[rank] = d;
+  }
+  named_bar_sync(1, nthr);
+  for (uint32_t k = 0; k + 1 < nev; ++k) {
+    const uint32_t a = s2_ev_a[k] & 0x7fffffffu, nx = s2_ev_a[k + 1];
+    const uint32_t b = (nx & 0x7fffffffu) - (nx >> 31);  // a removal event at e: position e - 1 is the vacated one
+    const int d = s2_ev_d[k];
+    for (uint32_t p = a + tid; p < b; p += nthr) {
       const uint32_t q = sm.ord[p];
-      const uint32_t np = p - (run & 0xffffu) + (run >> 16);
+      const uint32_t np = (uint32_t)((int)p + d);
       sm.tmp[np] = (uint16_t)q;
       sm.posn[q] = (uint16_t)np;
     }
   }
-  named_bar_sync(1, nthr);
-  if (tid < cnt) {
+  if (tid < cnt) {  // (tmp slots no survivor takes; s2_np is complete since the barrier above)
     const uint32_t u = s2_rk_node[tid];
     sm.tmp[s2_np[tid]] = (uint16_t)u;
     sm.posn[u] = (uint16_t)s2_np[tid];
     sm.cost[u] = s2_rk_nc[tid];
-    sm.scratch[s2_ip[tid]] = 0;
-    sm.scratch[s2_rp[tid] + 1] = 0;
   }
   named_bar_sync(1, nthr);
-  for (uint32_t p = pmin + tid; p < pmax && p < mp; p += nthr) sm.ord[p] = sm.tmp[p];
+  for (uint32_t p = pmin + tid; p < pmax; p += nthr) sm.ord[p] = sm.tmp[p];
   named_bar_sync(1, nthr);
 }
 // bounds of the blocks a re-key touched (all threads, after order_rekey2)

@@ -68,23 +68,29 @@ struct QosUse {
 // AccountMetaContainer::CheckTres_ / CheckGres_ (AccountMetaContainer.cpp:493-531).
 // A name / type is "in the request map" iff its count is non-zero; names and
 // types are walked in dictionary order (deviation D8).
-__device__ __forceinline__ uint8_t qos_check_tres(const GresDict& d, const QosUse& u, const crane_tres_limit_t& L) {
+__device__ __forceinline__ uint8_t qos_check_tres(const GresDict& d, uint32_t n_names, const QosUse& u, const crane_tres_limit_t& L) {
   if (u.cpu_raw > L.view.cpu_raw) return CRANE_REASON_QOS_CPU;
   if (u.mem > L.view.mem) return CRANE_REASON_QOS_MEM;
-  // (all loops have constant bounds and are unrolled: u stays in registers)
+  // (all loops have constant bounds and are unrolled: u stays in registers; the uniform
+  // early exits keep the work proportional to the cluster's dictionary)
+  const uint32_t n_entries = d.n_entries;
 #pragma unroll
   for (int g = 0; g < CRANE_GRES_NAMES; ++g) {
+    if ((uint32_t)g >= n_names) continue;
     const uint32_t first = d.name_first[g], cnt = d.name_count[g];
     if (cnt == 0) continue;
     bool in_req = u.tot[g] != 0;
 #pragma unroll
-    for (int e = 0; e < CRANE_GRES_ENTRIES; ++e)
+    for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) {
+      if ((uint32_t)e >= n_entries) continue;
       if ((uint32_t)e >= first && (uint32_t)e < first + cnt) in_req |= u.spec[e] != 0;
+    }
     if (!in_req) continue;
     if (!((L.gres_name_present >> g) & 1u)) return CRANE_REASON_NONE;
     if (u.tot[g] > L.view.gres_total[g]) return CRANE_REASON_QOS_GRES;
 #pragma unroll
     for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) {
+      if ((uint32_t)e >= n_entries) continue;
       if ((uint32_t)e < first || (uint32_t)e >= first + cnt || u.spec[e] == 0) continue;
       if (!((L.gres_spec_present >> e) & 1u)) return CRANE_REASON_NONE;
       if (u.spec[e] > L.view.gres_spec[e]) return CRANE_REASON_QOS_GRES;
@@ -163,6 +169,11 @@ __global__ void __launch_bounds__(kQosThreads) k_qos_chain(QosDev q, GresDict di
   const int64_t max_wall = q.max_wall[w];
   const uint32_t mj_user = q.max_jobs_per_user[w], mj_acct = q.max_jobs_per_account[w], mj_qos = q.max_jobs[w];
   const int64_t max_cpus_user = q.max_cpus_per_user_raw[w];
+  uint32_t n_names = 0;  // names beyond the last entry's have no entries: nothing to check or to count
+#pragma unroll
+  for (int e = 0; e < CRANE_GRES_ENTRIES; ++e)
+    if ((uint32_t)e < dict.n_entries && n_names < dict.entry_name[e] + 1u) n_names = dict.entry_name[e] + 1u;
+  const uint32_t n_entries = dict.n_entries;
 
   // allocated_res.View() of the jobs [b0, b0 + kQosBatch) of the list, one job per thread of warps 1-3
   auto prepare = [&](uint32_t b0, uint32_t buf) {
@@ -233,17 +244,25 @@ __global__ void __launch_bounds__(kQosThreads) k_qos_chain(QosDev q, GresDict di
           max_jobs = mj_qos;
         }
         uint8_t result = CRANE_REASON_NONE;
+        QosUse u = a;  // resource_use = allocated view + val.resource
         if (val) {
-          QosUse u = a;  // resource_use = allocated view + val.resource
           u.cpu_raw += val->cpu_raw; u.mem += val->mem; u.mem_sw += val->mem_sw;
-#pragma unroll
-          for (int g = 0; g < CRANE_GRES_NAMES; ++g) u.tot[g] += val->gres_total[g];
-#pragma unroll
-          for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) u.spec[e] += val->gres_spec[e];
           if (lane == 0 && u.cpu_raw > max_cpus_user) result = CRANE_REASON_QOS_CPU;
           else if ((uint64_t)val->jobs_count + 1ull > (uint64_t)max_jobs) result = CRANE_REASON_QOS_JOBS;
           else if (max_wall > 0 && val->wall_time + tl > max_wall) result = CRANE_REASON_QOS_WALL;
-          else result = qos_check_tres(dict, u, *lim);
+        }
+        // the reason is the lowest failing level's: levels behind one that already failed
+        // the cheap tests need no tres check
+        const uint32_t early = __ballot_sync(0xffffffffu, result != CRANE_REASON_NONE);
+        const uint32_t lowest = early ? (uint32_t)__ffs((int)early) - 1u : 32u;
+        if (val && result == CRANE_REASON_NONE && lane < lowest) {
+#pragma unroll
+          for (int g = 0; g < CRANE_GRES_NAMES; ++g)
+            if ((uint32_t)g < n_names) u.tot[g] += val->gres_total[g];
+#pragma unroll
+          for (int e = 0; e < CRANE_GRES_ENTRIES; ++e)
+            if ((uint32_t)e < n_entries) u.spec[e] += val->gres_spec[e];
+          result = qos_check_tres(dict, n_names, u, *lim);
         }
         const uint32_t failed = __ballot_sync(0xffffffffu, result != CRANE_REASON_NONE);
         if (failed) {
@@ -253,9 +272,11 @@ __global__ void __launch_bounds__(kQosThreads) k_qos_chain(QosDev q, GresDict di
           // DoMallocResource_ / MetaResource::operator+= (AccountMetaContainer.cpp:33-39, 546-587)
           val->cpu_raw += a.cpu_raw; val->mem += a.mem; val->mem_sw += a.mem_sw;
 #pragma unroll
-          for (int g = 0; g < CRANE_GRES_NAMES; ++g) val->gres_total[g] += a.tot[g];
+          for (int g = 0; g < CRANE_GRES_NAMES; ++g)
+            if ((uint32_t)g < n_names) val->gres_total[g] += a.tot[g];
 #pragma unroll
-          for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) val->gres_spec[e] += a.spec[e];
+          for (int e = 0; e < CRANE_GRES_ENTRIES; ++e)
+            if ((uint32_t)e < n_entries) val->gres_spec[e] += a.spec[e];
           val->jobs_count += 1;
           val->wall_time += tl;
         }

@@ -45,6 +45,15 @@ for r in data:
     a["inst"] += int(r[ix["Instructions Executed"]])
     for h in stalls:
         a[h] += int(r[ix[h]])
+# NCU_LINES_WORK=1: rank by the samples that are NOT barrier waits — with one warp (or half the CTA)
+# working while the rest waits at a barrier, these are the critical path
+work = bool(os.environ.get("NCU_LINES_WORK"))
+bar = [h for h in stalls if "barrier" in h]
+if work:
+    for a in agg.values():
+        a["samples_all"] = a["samples"]
+        a["samples"] = a["samples"] - sum(a[h] for h in bar)
+    tot = sum(a["samples"] for a in agg.values())
 src = {}
 for (f, n), a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
     if f not in src:

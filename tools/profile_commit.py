@@ -17,7 +17,7 @@ if len(sys.argv) > 3:
 if os.environ.get("SEED_ID"):
     kw["seed_id"] = int(os.environ["SEED_ID"])
 cfg, cl, rn, pd, now = synth.CONFIGS[cfg_id](**kw)
-s = GpuScheduler(cfg, 0, os.path.join(CSRC, "libcrane_sched_prof.so"))
+s = GpuScheduler(cfg, 0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "variants", "libcrane_sched_prof.so"))
 s.set_cluster(cl)
 for _ in range(2):
     out = s.node_select(now, rn, pd)
