@@ -405,6 +405,9 @@ __shared__ uint32_t s2_ip[kRK], s2_rp[kRK], s2_np[kRK];
 __shared__ uint32_t s2_w[kT2 / 32];
 __shared__ uint32_t s2_ev_a[2 * kRK];  // re-key: sorted places where the survivors' shift changes (bit 31: a removal)
 __shared__ int s2_ev_d[2 * kRK];       // shift behind the event
+__shared__ uint16_t s2_long[2 * kRK];  // re-key: the segments copied by all threads
+__shared__ uint32_t s2_nlong;
+constexpr int kShortSeg = 12;          // longest segment its own thread copies
 __shared__ long long s2_e[2][kNG];        // earliest fits: per task (batch) / per group max (one-job path)
 __shared__ long long s2_e2[2][kNG];       // per group min (one-job path)
 __shared__ long long s2_T0[kMaxJ];
@@ -729,9 +732,31 @@ __device__ __noinline__ void order_rekey2(uint32_t cnt, uint32_t nthr) {
     s2_ev_d[rank] = d;
   }
   named_bar_sync(1, nthr);
-  for (uint32_t k = 0; k + 1 < nev; ++k) {
-    const uint32_t a = s2_ev_a[k] & 0x7fffffffu, nx = s2_ev_a[k + 1];
+  // segment k = [event k, event k+1): a short one is copied by its own thread, the long ones
+  // (usually the one stretch between where the nodes left and where they arrive) by everybody
+  if (tid == 0) s2_nlong = 0;
+  named_bar_sync(1, nthr);
+  if (tid + 1 < nev) {
+    const uint32_t a = s2_ev_a[tid] & 0x7fffffffu, nx = s2_ev_a[tid + 1];
     const uint32_t b = (nx & 0x7fffffffu) - (nx >> 31);  // a removal event at e: position e - 1 is the vacated one
+    const int d = s2_ev_d[tid];
+    if (b > a + (uint32_t)kShortSeg) {
+      s2_long[atomicAdd(&s2_nlong, 1u)] = (uint16_t)tid;
+    } else {
+      for (uint32_t p = a; p < b; ++p) {
+        const uint32_t q = sm.ord[p];
+        const uint32_t np = (uint32_t)((int)p + d);
+        sm.tmp[np] = (uint16_t)q;
+        sm.posn[q] = (uint16_t)np;
+      }
+    }
+  }
+  named_bar_sync(1, nthr);
+  const uint32_t nlong = s2_nlong;
+  for (uint32_t i = 0; i < nlong; ++i) {
+    const uint32_t k = s2_long[i];
+    const uint32_t a = s2_ev_a[k] & 0x7fffffffu, nx = s2_ev_a[k + 1];
+    const uint32_t b = (nx & 0x7fffffffu) - (nx >> 31);
     const int d = s2_ev_d[k];
     for (uint32_t p = a + tid; p < b; p += nthr) {
       const uint32_t q = sm.ord[p];

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for tool in racecheck synccheck memcheck; do
   timeout 900 compute-sanitizer --tool $tool --kernel-name kns=k_commit2 --print-limit 30 \
-    python -m pytest tests/test_gpu_parity.py -q -x -k "(random_sweep and (100 or 103 or 104 or 107)) or (general_task and 201) or (bestfit and 301)" > gpurun_out/sanitizer_$tool.log 2>&1
+    python -m pytest tests/test_gpu_parity.py -q -x -k "(random_sweep and (100 or 103 or 104 or 107)) or (general_task and 201) or (bestfit and 301) or (overlapping and 601) or (test_reservations and 501)" > gpurun_out/sanitizer_$tool.log 2>&1
   tail -3 gpurun_out/sanitizer_$tool.log
 done
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
