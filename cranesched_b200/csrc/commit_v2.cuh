@@ -652,7 +652,7 @@ __device__ __noinline__ void order_rekey2(uint32_t cnt, uint32_t nthr) {
   const uint32_t mp = s2_cx.npos, tid = threadIdx.x, lane = lane_id(), wid = warp_id();  // positions of the current order
   if (cnt == 0) return;
   const uint32_t ngr = nthr / kGL;  // the first nthr threads of the CTA take part (named barrier 1)
-  if (tid == 0) { s2_pmin = mp; s2_pmax = 0; }
+  if (tid == 0) { s2_pmin = mp; s2_pmax = 0; s2_nlong = 0; }
   named_bar_sync(1, nthr);
   const uint32_t gl = g_lane();
   // lower bound of every new key among the old keys: one group per node, nine-way search
@@ -734,8 +734,6 @@ __device__ __noinline__ void order_rekey2(uint32_t cnt, uint32_t nthr) {
   named_bar_sync(1, nthr);
   // segment k = [event k, event k+1): a short one is copied by its own thread, the long ones
   // (usually the one stretch between where the nodes left and where they arrive) by everybody
-  if (tid == 0) s2_nlong = 0;
-  named_bar_sync(1, nthr);
   if (tid + 1 < nev) {
     const uint32_t a = s2_ev_a[tid] & 0x7fffffffu, nx = s2_ev_a[tid + 1];
     const uint32_t b = (nx & 0x7fffffffu) - (nx >> 31);  // a removal event at e: position e - 1 is the vacated one
@@ -758,11 +756,14 @@ __device__ __noinline__ void order_rekey2(uint32_t cnt, uint32_t nthr) {
     const uint32_t a = s2_ev_a[k] & 0x7fffffffu, nx = s2_ev_a[k + 1];
     const uint32_t b = (nx & 0x7fffffffu) - (nx >> 31);
     const int d = s2_ev_d[k];
-    for (uint32_t p = a + tid; p < b; p += nthr) {
-      const uint32_t q = sm.ord[p];
-      const uint32_t np = (uint32_t)((int)p + d);
-      sm.tmp[np] = (uint16_t)q;
-      sm.posn[q] = (uint16_t)np;
+    for (uint32_t p0 = a + tid; p0 < b; p0 += 2u * nthr) {  // two loads in flight
+      const uint32_t p1 = p0 + nthr;
+      const bool h1 = p1 < b;
+      const uint32_t q0 = sm.ord[p0], q1 = h1 ? sm.ord[p1] : 0u;
+      const uint32_t n0 = (uint32_t)((int)p0 + d), n1 = (uint32_t)((int)p1 + d);
+      sm.tmp[n0] = (uint16_t)q0;
+      sm.posn[q0] = (uint16_t)n0;
+      if (h1) { sm.tmp[n1] = (uint16_t)q1; sm.posn[q1] = (uint16_t)n1; }
     }
   }
   if (tid < cnt) {  // (tmp slots no survivor takes; s2_np is complete since the barrier above)
@@ -772,7 +773,13 @@ __device__ __noinline__ void order_rekey2(uint32_t cnt, uint32_t nthr) {
     sm.cost[u] = s2_rk_nc[tid];
   }
   named_bar_sync(1, nthr);
-  for (uint32_t p = pmin + tid; p < pmax; p += nthr) sm.ord[p] = sm.tmp[p];
+  for (uint32_t p0 = pmin + tid; p0 < pmax; p0 += 2u * nthr) {
+    const uint32_t p1 = p0 + nthr;
+    const bool h1 = p1 < pmax;
+    const uint16_t v0 = sm.tmp[p0], v1 = h1 ? sm.tmp[p1] : (uint16_t)0;
+    sm.ord[p0] = v0;
+    if (h1) sm.ord[p1] = v1;
+  }
   named_bar_sync(1, nthr);
 }
 // bounds of the blocks a re-key touched (all threads, after order_rekey2)
