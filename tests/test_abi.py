@@ -31,7 +31,7 @@ def test_struct_sizes_match_header():
     assert abi.RES_IN_NODE.itemsize == 72
     assert abi.RES_VIEW.itemsize == 56
     assert C.sizeof(abi.SchedConfig) == 56
-    assert C.sizeof(abi.TimingC) == 32
+    assert C.sizeof(abi.TimingC) == 36  # + qos_ms
 
 
 def test_no_cpu_fallback_without_device(gpu_lib):
