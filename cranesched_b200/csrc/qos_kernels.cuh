@@ -222,7 +222,10 @@ __global__ void __launch_bounds__(kQosThreads) k_qos_chain(QosDev q, GresDict di
       const uint32_t cnt = end - b0 < (uint32_t)kQosBatch ? end - b0 : (uint32_t)kQosBatch;
       for (uint32_t k = 0; k < cnt; ++k) {
         const QosPrep& P = s_prep[buf][k];
-        const QosUse a = P.a;
+        // (the gres counts of the allocation are read only where they are needed: most
+        // refusals are decided by the cpu / job-count / wall-time limits)
+        const int64_t a_cpu = P.a.cpu_raw;
+        const uint64_t a_mem = P.a.mem, a_mem_sw = P.a.mem_sw;
         const int64_t tl = P.tl;
         const uint32_t C = P.C;
         // ---- CheckQosResource_: one level per lane ---------------------------
@@ -244,10 +247,11 @@ __global__ void __launch_bounds__(kQosThreads) k_qos_chain(QosDev q, GresDict di
           max_jobs = mj_qos;
         }
         uint8_t result = CRANE_REASON_NONE;
-        QosUse u = a;  // resource_use = allocated view + val.resource
+        int64_t u_cpu = a_cpu;  // resource_use = allocated view + val.resource
+        uint64_t u_mem = a_mem, u_mem_sw = a_mem_sw;
         if (val) {
-          u.cpu_raw += val->cpu_raw; u.mem += val->mem; u.mem_sw += val->mem_sw;
-          if (lane == 0 && u.cpu_raw > max_cpus_user) result = CRANE_REASON_QOS_CPU;
+          u_cpu += val->cpu_raw; u_mem += val->mem; u_mem_sw += val->mem_sw;
+          if (lane == 0 && u_cpu > max_cpus_user) result = CRANE_REASON_QOS_CPU;
           else if ((uint64_t)val->jobs_count + 1ull > (uint64_t)max_jobs) result = CRANE_REASON_QOS_JOBS;
           else if (max_wall > 0 && val->wall_time + tl > max_wall) result = CRANE_REASON_QOS_WALL;
         }
@@ -256,12 +260,12 @@ __global__ void __launch_bounds__(kQosThreads) k_qos_chain(QosDev q, GresDict di
         const uint32_t early = __ballot_sync(0xffffffffu, result != CRANE_REASON_NONE);
         const uint32_t lowest = early ? (uint32_t)__ffs((int)early) - 1u : 32u;
         if (val && result == CRANE_REASON_NONE && lane < lowest) {
+          QosUse u;
+          u.cpu_raw = u_cpu; u.mem = u_mem; u.mem_sw = u_mem_sw;
 #pragma unroll
-          for (int g = 0; g < CRANE_GRES_NAMES; ++g)
-            if ((uint32_t)g < n_names) u.tot[g] += val->gres_total[g];
+          for (int g = 0; g < CRANE_GRES_NAMES; ++g) u.tot[g] = (uint32_t)g < n_names ? P.a.tot[g] + val->gres_total[g] : 0u;
 #pragma unroll
-          for (int e = 0; e < CRANE_GRES_ENTRIES; ++e)
-            if ((uint32_t)e < n_entries) u.spec[e] += val->gres_spec[e];
+          for (int e = 0; e < CRANE_GRES_ENTRIES; ++e) u.spec[e] = (uint32_t)e < n_entries ? P.a.spec[e] + val->gres_spec[e] : 0u;
           result = qos_check_tres(dict, n_names, u, *lim);
         }
         const uint32_t failed = __ballot_sync(0xffffffffu, result != CRANE_REASON_NONE);
@@ -270,13 +274,13 @@ __global__ void __launch_bounds__(kQosThreads) k_qos_chain(QosDev q, GresDict di
           if (lane == 0) q.reason[P.job] = first;
         } else if (val) {
           // DoMallocResource_ / MetaResource::operator+= (AccountMetaContainer.cpp:33-39, 546-587)
-          val->cpu_raw += a.cpu_raw; val->mem += a.mem; val->mem_sw += a.mem_sw;
+          val->cpu_raw += a_cpu; val->mem += a_mem; val->mem_sw += a_mem_sw;
 #pragma unroll
           for (int g = 0; g < CRANE_GRES_NAMES; ++g)
-            if ((uint32_t)g < n_names) val->gres_total[g] += a.tot[g];
+            if ((uint32_t)g < n_names) val->gres_total[g] += P.a.tot[g];
 #pragma unroll
           for (int e = 0; e < CRANE_GRES_ENTRIES; ++e)
-            if ((uint32_t)e < n_entries) val->gres_spec[e] += a.spec[e];
+            if ((uint32_t)e < n_entries) val->gres_spec[e] += P.a.spec[e];
           val->jobs_count += 1;
           val->wall_time += tl;
         }
