@@ -13,12 +13,13 @@
 //             window test because availability only shrinks inside a tick;
 //             with fewer than node_num of them, the first capable nodes,
 //             which is where a backfill goes (JobScheduler.cpp:5269-5278);
-//   resolve   in job order every job takes its first node_num free candidates;
-//             solved for all jobs at once as a fixed point over a claim word
-//             per node (job t is final after round t+1; the first guess is
-//             right when the lists coincide). A job that could use a node
-//             taken by an earlier job of the batch at that node's NEW place in
-//             the order ends the batch: it needs the updated timeline;
+//   resolve   in job order every job takes its first node_num free candidates:
+//             warp 0 walks the jobs (lane = list entry, a taken node is marked
+//             in its scratch word, the next job's list is prefetched). A job
+//             that could use a node taken by an earlier job of the batch at
+//             that node's NEW place in the order ends the batch: it needs the
+//             updated timeline. Warps 1-7 meanwhile test every slot's first
+//             guess (the entry taken if the jobs before take the entries before);
 //   evaluate  group w runs the exact test of task w = (job, node) without
 //             touching state: window minimum (JobScheduler.cpp:5285-5334) or
 //             allocation against res_total + earliest common start
@@ -29,8 +30,10 @@
 //             (JobScheduler.h:334-453), outputs, reason label
 //             (JobScheduler.cpp:5829-5848);
 //   re-key    UpdateCost (JobScheduler.h:520-532) for all placed nodes at once:
-//             the order is a flat array; every entry's shift is a prefix sum
-//             over removal / insertion marks, computed by the whole CTA.
+//             the order is a flat array; a surviving entry's shift is constant
+//             between the sorted places where nodes leave or arrive, so the
+//             affected range is copied segment by segment (warps 0-3, while
+//             warps 4-7 commit, when the batch has at most 16 tasks).
 //
 // The job at which a batch stops (its pick failed the exact test, so the walk
 // has to continue past it), jobs wider than a batch and tiny partitions take
@@ -55,7 +58,7 @@ constexpr int kMaxJ = 32;          // jobs per batch
 constexpr int kMaxT = kNG;         // (job, node) tasks per batch: one group each
 constexpr int kBlk = 32;           // order positions per bounds block
 constexpr int kRingMax = 64;       // prefetch ring depth (jobs)
-constexpr int kRK = 64;
+constexpr int kRK = 64;             // nodes re-keyed at once (more: full sort)
 constexpr int kHeapMax = 128;      // general task distribution: top-K heaps of up to 127 nodes
 constexpr int kDeltaClasses = 4;
 #ifndef CRANE_SPEC_EVAL
