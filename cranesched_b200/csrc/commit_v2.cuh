@@ -58,6 +58,8 @@ constexpr int kMaxJ = 32;          // jobs per batch
 constexpr int kMaxT = kNG;         // (job, node) tasks per batch: one group each
 constexpr int kBlk = 32;           // order positions per bounds block
 constexpr int kRingMax = 64;       // prefetch ring depth (jobs)
+constexpr int kValidateFor = 8;     // batches with up-front validation after a pick failed the exact test
+constexpr int kSpare = 12;          // ... during which every job lists this many candidates more than it needs
 constexpr int kRK = 64;             // nodes re-keyed at once (more: full sort)
 constexpr int kHeapMax = 128;      // general task distribution: top-K heaps of up to 127 nodes
 constexpr int kDeltaClasses = 4;
@@ -1119,6 +1121,124 @@ __device__ __noinline__ void single2(uint32_t ji) {
   }
 }
 
+// ---- validation of the candidate lists (all threads) ---------------------------------
+// In an over-subscribed partition most nodes that pass the pre-filter (first timeline
+// segment) fail the window test — backfill reservations sit on every node — so the
+// speculative pick fails, the batch is cut and the job walks the order alone. For a
+// few batches after such a failure every immediate-start job lists kSpare candidates
+// more than it needs and every listed candidate gets the exact test of the batch-start
+// state at once (one group per (job, entry) pair). The list keeps the passing ones, so
+// a failing candidate is replaced inside the batch; a job with fewer than node_num
+// passing ones in a COMPLETE list (select2 walked to the end of the order) is a backfill
+// job (JobScheduler.cpp:5269-5278) right away. Exact: a node that fails now fails in
+// every later state of the tick; a listed node that passes and is not touched by an
+// earlier job of the batch still is in its batch-start state when the job picks it; and
+// everything in front of a pick is either listed (tested) or fails the pre-filter.
+__shared__ uint32_t s2_vok[kMaxJ], s2_voff[kMaxJ + 1];
+__device__ __noinline__ void validate2(uint32_t nj) {
+  const Smem2 sm = SM2S();
+  const uint32_t tid = threadIdx.x, lane = lane_id(), gl = g_lane(), gi = g_index();
+  const TimelineDev& tl = s2_cx.tl;
+  const int64_t now = s2_cx.now;
+  if (tid < 32) {  // pairs per job, exclusive prefix
+    uint32_t c = 0;
+    if (lane < nj) {
+      const BJob2 b = s2_bj[lane];
+      if (b.state == 0 && b.mode == 0) c = b.n0;
+      s2_vok[lane] = 0;
+    }
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(kFullMask, inc, o);
+      if ((int)lane >= o) inc += up;
+    }
+    if (lane < nj) s2_voff[lane] = inc - c;
+    if (lane == 31) s2_voff[kMaxJ] = inc;
+  }
+  __syncthreads();
+  const uint32_t npairs = s2_voff[kMaxJ];
+  if (npairs == 0) return;
+  for (uint32_t x0 = 0; x0 < npairs; x0 += kNG) {
+    const uint32_t x = x0 + gi;
+    const bool act = x < npairs;
+    // the job of pair x: the last job whose offset is <= x (jobs without pairs share the next one's offset)
+    uint32_t t = 0;
+    {
+      uint32_t best = 0;
+      for (uint32_t j = gl; j < nj; j += kGL)
+        if (s2_voff[j] <= x) best = j + 1u;
+#pragma unroll
+      for (int o = 1; o < kGL; o <<= 1) {
+        const uint32_t ob = __shfl_xor_sync(kFullMask, best, o);
+        best = ob > best ? ob : best;
+      }
+      t = best ? best - 1u : 0u;
+    }
+    const uint32_t e = act ? x - s2_voff[t] : 0u;
+    const JobQ& jq = s2_jobs[s2_bj[t].slot];
+    const bool exclusive = jq.flags & 1u;
+    const View req = jq.req;
+    uint32_t q = 0, g = s2_cx.base, ns = 0;
+    Row tot, a0;
+    row_zero(tot);
+    row_zero(a0);
+    if (act) {
+      q = s2_cl[0][t][e];
+      g = s2_cx.base + q;
+      ns = sm.nseg[q];
+      if (exclusive) tot = node_total2(q);
+      else a0 = tl.avail0[g];
+    }
+    Win2 w;
+    g_window(tl.ent + (size_t)g * tl.cap, ns, now + jq.time_limit, req.cpu_raw, req.mem, exclusive, (jq.flags & 2u) != 0, tot, act, w);
+    bool ok = act && w.ok;
+    if (ok && !exclusive) {
+      ok = a0.cpu_raw >= req.cpu_raw && a0.mem >= req.mem;  // res_avail itself (JobScheduler.cpp:5310)
+      if (ok) {
+        Row wr;
+        win_row(w, a0, req, wr);
+        ok = feasible<false>(req, wr, C_DICT2, nullptr);
+      }
+    }
+    if (ok && gl == 0) atomicOr(&s2_vok[t], 1u << e);
+  }
+  __syncthreads();
+  // group t compacts the list of job t (every lane of the warp takes part in the ballots)
+  {
+    BJob2 b;
+    b.slot = 0; b.K = 0; b.need = 0; b.tfirst = 0; b.n0 = 0; b.n1 = 0; b.mode = 0; b.state = 0;
+    if (gi < nj) b = s2_bj[gi];
+    const bool qual = gi < nj && b.state == 0 && b.mode == 0;
+    const uint32_t want = b.need + (uint32_t)kSpare < (uint32_t)kMaxT ? b.need + (uint32_t)kSpare : (uint32_t)kMaxT;  // what select2 was asked for
+    const bool complete = b.n0 < want;  // the walk reached the end of the order: nothing passes the pre-filter beyond the list
+    const uint32_t n0 = qual ? b.n0 : 0u;
+    const uint32_t mask = qual ? s2_vok[gi] : 0u;
+    uint32_t kept = 0;
+    for (uint32_t e0 = 0; e0 < (uint32_t)kMaxT; e0 += kGL) {
+      const uint32_t e = e0 + gl;
+      const bool keep = e < n0 && ((mask >> e) & 1u);
+      const uint16_t v = e < n0 ? s2_cl[0][gi][e] : (uint16_t)0;
+      const uint32_t gb = g_ballot(keep);
+      __syncwarp();
+      if (keep) s2_cl[0][gi][kept + (uint32_t)__popc(gb & ((1u << gl) - 1u))] = v;
+      kept += (uint32_t)__popc(gb);
+      __syncwarp();
+    }
+    if (qual && gl == 0) {
+      // fewer than K passing ones in a complete list: a backfill job; in a truncated list: the
+      // resolve will stop the batch at this job (its walk has to go on past the list)
+      const uint32_t mode = (complete && kept < b.K) ? 1u : 0u;
+      const uint32_t state = (mode && b.n1 < b.K) ? 2u : 0u;
+      s2_bj[gi].n0 = kept; s2_bj[gi].mode = mode; s2_bj[gi].state = state;
+      const uint32_t nl = state ? 0u : (mode ? b.n1 : kept);
+      s2_jw[gi] = b.K | b.tfirst << 8 | mode << 16 | state << 17 | nl << 24;
+      s2_jst[gi] = (state == 0 && mode == 1u && b.K > 1u) ? 0u : 3u;
+    }
+  }
+  __syncthreads();
+}
+
 // ---- general task distribution (ntasks_per_node_max > min or an uneven ntasks) --------
 // JobScheduler.cpp:5193-5222, 5258-5361: every capable node can take between
 // ntasks_per_node_min and _max tasks; the K nodes with the most tasks are kept in a
@@ -1559,6 +1679,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
   uint32_t ji = 0;
   uint32_t jcap = kMaxJ;     // jobs offered to the next batch: twice what the last one placed (a batch that is cut
                              // early wastes the selection of the jobs behind the cut)
+  uint32_t vcredit = 0;      // batches for which complete candidate lists are validated before the resolve (validate2)
   bool want_single = s2_cx.ncp > 1;  // the job at ji goes down the one-job path (overlapping partitions: every job,
                                      // each in its own partition's order)
   while (ji < njobs) {
@@ -1616,7 +1737,9 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
         jsel_load(s2_jobs[bj.slot], sm.bits_ring + (size_t)bj.slot * words, js);
       }
       uint32_t n0, n1;
-      select2(sm, mp, js, bj.need, jact, s2_cl[0][gi], s2_cl[1][gi], n0, n1);
+      // (while lists are validated, a job lists spare candidates: the ones that fail are replaced inside the batch)
+      const uint32_t want = vcredit ? (bj.need + (uint32_t)kSpare < (uint32_t)kMaxT ? bj.need + (uint32_t)kSpare : (uint32_t)kMaxT) : bj.need;
+      select2(sm, mp, js, jact ? want : 0u, jact, s2_cl[0][gi], s2_cl[1][gi], n0, n1);
       bj.n0 = n0; bj.n1 = n1;
       // fewer than K pre-filter candidates: only a backfill is possible (taken
       // nodes lose resources, they never gain candidates); fewer than K capable
@@ -1642,6 +1765,10 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
       }
     }
     __syncthreads();
+    if (vcredit) {  // a pick failed the exact test a few batches ago: complete lists are validated up front
+      validate2(nj);
+      --vcredit;
+    }
     PROF(2);
 
     // ---- resolve (warp 0)  ||  speculative evaluation (warps 1-7) ---------------------
@@ -1918,6 +2045,7 @@ __global__ void __launch_bounds__(kT2, 1) k_commit2(Commit2Args a) {
         PROF_CNT(12, 1);
       } else {
         want_single = true;
+        vcredit = kValidateFor;
         PROF_CNT(11, 1);
       }
     }
