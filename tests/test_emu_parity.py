@@ -20,6 +20,9 @@ CASES = {
     # BestFit cost policy: keys move down on allocation
     "bestfit": lambda: synth.random_case(301, n_jobs=120, n_nodes=26, n_parts=2, n_running=12, cost_policy=1),
     "config4_tiny": lambda: synth.config4(n_jobs=150, n_nodes=24),
+    # over-subscribed gres partition: picks that pass the pre-filter fail the window test, lists are
+    # validated up front, failing candidates replaced inside the batch (validate2)
+    "contended": lambda: synth.config2(n_jobs=420, n_nodes=32, seed_id=3002),
     "random_fifo_cap": lambda: synth.random_case(12, n_jobs=90, n_nodes=10, n_parts=2, n_running=6, fifo=True,
                                                  max_jobs_per_node=12, short=True),
 }
