@@ -181,3 +181,19 @@ def test_overlapping_partitions(oracle, seed):
     b, _ = pyref.node_select(cfg, cl, rn, pd, now)
     d = a.diff(b)
     assert not d, "oracle differs from the reference's own NodeSelect:\n" + "\n".join(d[:8])
+
+
+@pytest.mark.parametrize("seed", range(720, 728))
+def test_overlapping_partitions_with_reservations(oracle, seed):
+    """Both at once: reservations cut out of nodes that two partitions share."""
+    base = synth.random_case(seed, n_jobs=200, n_nodes=34, n_parts=2 + seed % 2, n_running=12,
+                             one_type_per_name=True, lists=bool(seed % 2))
+    case = synth.overlap_partitions(base, seed, frac=0.3 + 0.1 * (seed % 3))
+    resv, pd2, rn2 = synth.random_reservations(seed, case, n_resv=5, single_node=True)
+    cfg, cl, rn, pd, now = case
+    a, _, _ = oracle.node_select(cfg, cl, rn2, pd2, now, resv=resv)
+    ex = pyref.RefExtra(resv_start=resv.start_time, resv_end=resv.end_time, resv_off=resv.node_off, resv_node=resv.node,
+                        resv_res=resv.res, pd_resv=pd2.reservation, rn_resv=rn2.reservation)
+    b, _ = pyref.node_select(cfg, cl, rn2, pd2, now, ex)
+    d = a.diff(b)
+    assert not d, "oracle differs from the reference's own NodeSelect:\n" + "\n".join(d[:8])
