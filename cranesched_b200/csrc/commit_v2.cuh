@@ -13,6 +13,9 @@
 //             window test because availability only shrinks inside a tick;
 //             with fewer than node_num of them, the first capable nodes,
 //             which is where a backfill goes (JobScheduler.cpp:5269-5278);
+//   validate  (for a few batches after a pick failed the exact test) every listed
+//             candidate of the immediate-start jobs is tested exactly, at once;
+//             the lists keep the passing ones (validate2);
 //   resolve   in job order every job takes its first node_num free candidates:
 //             warp 0 walks the jobs (lane = list entry, a taken node is marked
 //             in its scratch word, the next job's list is prefetched). A job

@@ -22,7 +22,7 @@ CASES = {
     "config4_tiny": lambda: synth.config4(n_jobs=150, n_nodes=24),
     # over-subscribed gres partition: picks that pass the pre-filter fail the window test, lists are
     # validated up front, failing candidates replaced inside the batch (validate2)
-    "contended": lambda: synth.config2(n_jobs=420, n_nodes=32, seed_id=3002),
+    "contended": lambda: synth.config2(n_jobs=320, n_nodes=28, seed_id=3002),
     "random_fifo_cap": lambda: synth.random_case(12, n_jobs=90, n_nodes=10, n_parts=2, n_running=6, fifo=True,
                                                  max_jobs_per_node=12, short=True),
 }
@@ -45,7 +45,7 @@ def test_emulated_overlapping_partitions(oracle, emu_lib):
     (JobScheduler.cpp:5597-5651) — one scheduler per connected group here, one order per
     partition, jobs one by one in global priority order."""
     for seed, which in ((601, None), (604, {1})):
-        base = synth.random_case(seed, n_jobs=100, n_nodes=28, n_parts=2 + seed % 3, n_running=10, short=bool(seed & 1))
+        base = synth.random_case(seed, n_jobs=80, n_nodes=26, n_parts=2 + seed % 3, n_running=10, short=bool(seed & 1))
         case = synth.overlap_partitions(base, seed, frac=0.3 + 0.1 * (seed % 4), which=which)
         ref, _, _ = oracle.node_select(*case[:4], case[4])
         got, _ = run_sched(case, emu_lib)

@@ -39,12 +39,12 @@ def _worker(rank, world, port, emu_lib, q):
 
     # (2) ONE queue over the ranks: partitions dealt out, columns all-reduced
     bad = []
-    cases = [synth.config2(n_jobs=120, n_nodes=24, seed_id=77),
-             synth.random_case(32, n_jobs=120, n_nodes=33, n_parts=4, n_running=20, limit=80),
-             synth.random_case(33, n_jobs=100, n_nodes=20, n_parts=1, n_running=5),     # fewer partitions than ranks
-             synth.random_case(35, n_jobs=100, n_nodes=30, n_parts=3, n_running=16, fifo=True),
+    cases = [synth.config2(n_jobs=90, n_nodes=20, seed_id=77),
+             synth.random_case(32, n_jobs=90, n_nodes=30, n_parts=4, n_running=16, limit=60),
+             synth.random_case(33, n_jobs=70, n_nodes=18, n_parts=1, n_running=5),     # fewer partitions than ranks
+             synth.random_case(35, n_jobs=80, n_nodes=27, n_parts=3, n_running=12, fifo=True),
              # partitions 1 and 2 share nodes: one scheduler, one owner; 0 and 3 stand alone
-             synth.overlap_partitions(synth.random_case(36, n_jobs=110, n_nodes=36, n_parts=4, n_running=12), 36, 0.5, which={2})]
+             synth.overlap_partitions(synth.random_case(36, n_jobs=90, n_nodes=32, n_parts=4, n_running=10), 36, 0.5, which={2})]
     for k, full in enumerate(cases):
         cfg, cl, rn, pd, now = full
         owner = sharding.deal_partitions(pd, cl.n_partitions, world, cl)

@@ -154,7 +154,7 @@ def test_emulated_kernel_matches_oracle(oracle, emu_lib, monkeypatch, in_global)
     if in_global:
         monkeypatch.setenv("CRANE_QOS_TABLES_GLOBAL", "1")
     # more than one prepared batch (96 jobs) per qos
-    case = synth.random_case(21, n_jobs=300, n_nodes=60, n_running=8)
+    case = synth.random_case(21, n_jobs=150 if in_global else 300, n_nodes=60, n_running=8)
     table = synth.random_qos(21, case[1], case[3], tight=1.0)
     ref = _parity(oracle, emu_lib, case, table)
     assert (ref.reason >= 16).any()

@@ -51,9 +51,9 @@ def _check(oracle, out, again, dead, case):
     assert ref.alloc_res.tobytes() == out.alloc_res[rows].tobytes()
 
 
-@pytest.mark.parametrize("seed,kw", [(61, dict(fifo=False)), (62, dict(fifo=True, limit=70)), (63, dict(fifo=False, limit=60))])
+@pytest.mark.parametrize("seed,kw", [(61, dict(fifo=False)), (62, dict(fifo=True, limit=60))])
 def test_resident_table_emulated(oracle, emu_lib, seed, kw):
-    case = synth.random_case(seed, n_jobs=90, n_nodes=24, n_parts=2, n_running=10, **kw)
+    case = synth.random_case(seed, n_jobs=80, n_nodes=24, n_parts=2, n_running=10, **kw)
     out, again, dead = _resident_tick(emu_lib, case, seed)
     _check(oracle, out, again, dead, case)
 
