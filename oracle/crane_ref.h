@@ -44,6 +44,10 @@ int crane_ref_feasible(const crane_cluster_t* dict, const crane_res_view_t* req,
                        const crane_res_in_node_t* avail, crane_res_in_node_t* alloc);
 void crane_ref_ckmin(const crane_cluster_t* dict, crane_res_in_node_t* a, const crane_res_in_node_t* b);
 int crane_ref_res_le(const crane_cluster_t* dict, const crane_res_in_node_t* a, const crane_res_in_node_t* b);
+/* AccountMetaContainer::CheckAndMallocQosResource (Accounting/AccountMetaContainer.cpp:164-191, 382-531,
+ * 546-587; the reference's own text) over the jobs a tick starts; same contract as crane_oracle_qos_filter. */
+int crane_ref_qos_filter(const crane_cluster_t* dict, const crane_pending_t* pending,
+                         crane_placements_t* placements, const crane_qos_table_t* qos);
 const char* crane_ref_describe(void);
 
 #ifdef __cplusplus

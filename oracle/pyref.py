@@ -72,6 +72,9 @@ def lib():
         _lib.crane_ref_feasible.argtypes = [C.POINTER(abi.ClusterC), _p, _p, _p]
         _lib.crane_ref_ckmin.restype = None
         _lib.crane_ref_ckmin.argtypes = [C.POINTER(abi.ClusterC), _p, _p]
+        _lib.crane_ref_qos_filter.restype = C.c_int
+        _lib.crane_ref_qos_filter.argtypes = [C.POINTER(abi.ClusterC), C.POINTER(abi.PendingC), C.POINTER(abi.PlacementsC),
+                                              C.POINTER(abi.QosTableC)]
         _lib.crane_ref_res_le.restype = C.c_int
         _lib.crane_ref_res_le.argtypes = [C.POINTER(abi.ClusterC), _p, _p]
     return _lib
@@ -112,3 +115,13 @@ def res_le(cluster, a, b) -> bool:
     b = np.ascontiguousarray(b, abi.RES_IN_NODE)
     c = cluster.as_c()
     return bool(lib().crane_ref_res_le(C.byref(c), a.ctypes.data, b.ctypes.data))
+
+
+def qos_filter(cluster, pending, out, qos):
+    """The reference's own CheckAndMallocQosResource (Accounting/AccountMetaContainer.cpp) over the jobs
+    `out` starts now; in place on out.reason and qos.*_usage (same contract as pyoracle.qos_filter)."""
+    c_cl, c_pd, c_out, c_q = cluster.as_c(), pending.as_c(), out.as_c(), qos.as_c()
+    rc = lib().crane_ref_qos_filter(C.byref(c_cl), C.byref(c_pd), C.byref(c_out), C.byref(c_q))
+    if rc != 0:
+        raise RuntimeError(f"crane_ref_qos_filter rc={rc}")
+    return out

@@ -15,12 +15,14 @@ daemon's singletons. This recipe
                                           SchedulerAlgo::NodeSelect, and MultiFactorPriority::*
         src/Utilities/PublicHeader/include/crane/PublicHeader.h   SlotId .. ResourceView operators
         src/Utilities/PublicHeader/PublicHeader.cpp               the non-protobuf member functions
+        src/CraneCtld/Accounting/AccountMetaContainer.{h,cpp}     MetaResource, CheckAndMallocQosResource,
+                                          CheckQosResource_, CheckTres_, CheckGres_, DoMallocResource_
      into oracle/_ref/gen/*.inc (git-ignored: reference text is never committed);
   2. compiles oracle/ref_shim/ref_harness.cpp, which includes those slices
      UNMODIFIED between small shim headers (oracle/ref_shim/*.h: absl::Time as
      saturating int64 seconds, flat_hash_map as an ordered map on a bump arena,
      the fpm::fixed subset, stub singletons), with g++ -std=c++23;
-  3. exposes crane_ref_node_select() with the oracle's C signature.
+  3. exposes crane_ref_node_select() and crane_ref_qos_filter() with the oracle's C signatures.
 
 What the shims decide (documented deviations): hash-container
 iteration order becomes key order and NodeState addresses follow insertion
@@ -110,6 +112,21 @@ def extract():
         else:
             i += 1
     _write("ph_cpp.inc", "src/Utilities/PublicHeader/PublicHeader.cpp", out)
+    # ---- AccountMetaContainer: the QoS check + malloc of the commit loop (JobScheduler.cpp:1262) ----
+    ah = _lines("src/CraneCtld/Accounting/AccountMetaContainer.h")
+    a = _find(ah, r"^struct MetaResource \{")
+    _write("amc_h.inc", "src/CraneCtld/Accounting/AccountMetaContainer.h", ah[a:_func_end(ah, a) + 1])
+    ac = _lines("src/CraneCtld/Accounting/AccountMetaContainer.cpp")
+    body = []
+    for pat in (r"^bool MetaResource::operator<=\(", r"^MetaResource& MetaResource::operator\+=\(",
+                r"^MetaResource& MetaResource::operator-=\(", r"^void MetaResource::SetToZero\(",
+                r"^AccountMetaContainer::CheckAndMallocQosResource\(", r"^std::expected<void, std::string> AccountMetaContainer::CheckQosResource_\(",
+                r"^std::expected<void, std::string> AccountMetaContainer::CheckTres_\(", r"^bool AccountMetaContainer::CheckGres_\(",
+                r"^AccountMetaContainer::LockAccountStripes_\(", r"^void AccountMetaContainer::DoMallocResource_\("):
+        a = _find(ac, pat)
+        first = a - 1 if not ac[a].startswith(("bool", "void", "MetaResource&", "std::expected")) else a  # return type on the line above
+        body += ac[first:_func_end(ac, a) + 1] + [""]
+    _write("amc_cpp.inc", "src/CraneCtld/Accounting/AccountMetaContainer.cpp", body)
     return skipped
 
 

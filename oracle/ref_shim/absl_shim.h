@@ -50,6 +50,8 @@ constexpr Duration operator+(Duration a, Duration b) {
 constexpr Duration operator-(Duration a, Duration b) {
   return a.is_inf() ? a : Duration::FromSeconds(a.seconds() - b.seconds());
 }
+constexpr Duration& operator+=(Duration& a, Duration b) { a = a + b; return a; }
+constexpr Duration& operator-=(Duration& a, Duration b) { a = a - b; return a; }
 constexpr Duration operator/(Duration a, int64_t k) { return a.is_inf() ? a : Duration::FromSeconds(a.seconds() / k); }
 constexpr Duration operator*(Duration a, int64_t k) { return a.is_inf() ? a : Duration::FromSeconds(a.seconds() * k); }
 

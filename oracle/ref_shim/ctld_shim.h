@@ -7,14 +7,17 @@
 // the harness fills from the C-ABI tables. TEST INFRASTRUCTURE ONLY.
 #pragma once
 #include <algorithm>
+#include <array>
 #include <cassert>
 #include <cstdint>
 #include <cstdio>
+#include <expected>
 #include <functional>
 #include <limits>
 #include <list>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <queue>
 #include <ranges>
 #include <set>

@@ -75,14 +75,28 @@ struct CranedMetaContainer {
   const std::map<ResvId, Guarded<ResvMeta>>* GetResvMetaMapPtr() const { return &resvs; }
 };
 
-// Account/AccountDefs.h:27-50 (only the two fields NodeSelect reads)
+// Account/AccountDefs.h:27-50: the fields NodeSelect (deleted, preempt) and
+// AccountMetaContainer::CheckQosResource_ (the limits) read
 struct Qos {
   bool deleted = false;
   std::set<std::string> preempt;
+  uint32_t max_jobs_per_user{0};
+  uint32_t max_jobs_per_account{0};
+  cpu_t max_cpus_per_user{};
+  uint32_t max_jobs{0};
+  absl::Duration max_wall;
+  ResourceView max_tres;
+  ResourceView max_tres_per_user;
+  ResourceView max_tres_per_account;
 };
 struct AccountManager {
   std::map<std::string, std::unique_ptr<Qos>> qos_map;
   const std::map<std::string, std::unique_ptr<Qos>>* GetAllQosInfo() const { return &qos_map; }
+  // AccountManager::GetExistedQosInfo: the qos if it exists and is not deleted
+  const Qos* GetExistedQosInfo(const std::string& name) const {
+    auto it = qos_map.find(name);
+    return it != qos_map.end() && !it->second->deleted ? it->second.get() : nullptr;
+  }
 };
 struct LicensesManager {
   void CheckLicenseCountSufficient(std::vector<PdJobInScheduler*>*) {}  // no licenses in scope

@@ -40,6 +40,13 @@
 namespace Ctld {
 #include "js_h.inc"
 #include "js_cpp.inc"
+// ---------------- reference text: the QoS check + malloc of the commit loop -------------------
+//   amc_h.inc    Accounting/AccountMetaContainer.h    struct MetaResource                    (:30-47)
+//   amc_cpp.inc  Accounting/AccountMetaContainer.cpp  MetaResource operators, CheckAndMallocQosResource,
+//                CheckQosResource_, CheckTres_, CheckGres_, LockAccountStripes_, DoMallocResource_
+#include "amc_h.inc"
+#include "ctld_shim3.h"
+#include "amc_cpp.inc"
 }  // namespace Ctld
 #undef private
 #undef protected
@@ -368,4 +375,126 @@ extern "C" int crane_ref_earliest_start(const crane_cluster_t* cl, uint32_t n_no
   if (!sel.CalcEarliestStartTime(absl::FromUnixSeconds(now_s), &job)) return 0;
   *start = absl::ToUnixSeconds(job.start_time);
   return 1;
+}
+
+// ---- AccountMetaContainer::CheckAndMallocQosResource over the jobs a tick starts ------------------
+// Same contract as crane_oracle_qos_filter: job-id order, jobs with reason NONE and an
+// allocation; placements->reason and the usage tables of `qt` are updated in place. Names are
+// zero-padded (map order == index order); a usage entry lists a gres name / type only when its
+// count is non-zero (the oracle's reading of "is in the map", deviation D8).
+namespace {
+std::string QosName(uint32_t i) { char b[24]; snprintf(b, sizeof b, "qos%06u", i); return b; }
+std::string UserName(uint32_t i) { char b[24]; snprintf(b, sizeof b, "user%07u", i); return b; }
+std::string AcctName(uint32_t i) { char b[24]; snprintf(b, sizeof b, "acct%07u", i); return b; }
+
+ResourceView LimitFromAbi(const Dict& d, const crane_tres_limit_t& L) {
+  ResourceView x;
+  x.SetCpuCount(cpu_t::from_raw_value(L.view.cpu_raw));
+  x.SetMemoryBytes(L.view.mem);
+  x.SetMemorySwBytes(L.view.mem_sw);
+  for (int g = 0; g < CRANE_GRES_NAMES; ++g) {
+    if (!((L.gres_name_present >> g) & 1u)) continue;
+    GresCount& gc = x.GetGresMap()[d.name_str[g]];
+    gc.total = L.view.gres_total[g];
+    for (uint32_t e = 0; e < d.n_entries; ++e)
+      if (d.entry_name[e] == g && ((L.gres_spec_present >> e) & 1u)) gc.specified[d.type_str[e]] = L.view.gres_spec[e];
+  }
+  return x;
+}
+Ctld::MetaResource MetaFromAbi(const Dict& d, const crane_meta_resource_t& m) {
+  Ctld::MetaResource r;
+  r.resource.SetCpuCount(cpu_t::from_raw_value(m.cpu_raw));
+  r.resource.SetMemoryBytes(m.mem);
+  r.resource.SetMemorySwBytes(m.mem_sw);
+  for (int g = 0; g < CRANE_GRES_NAMES; ++g) {
+    bool any = m.gres_total[g] != 0;
+    for (uint32_t e = 0; e < d.n_entries; ++e)
+      if (d.entry_name[e] == g && m.gres_spec[e]) any = true;
+    if (!any) continue;
+    GresCount& gc = r.resource.GetGresMap()[d.name_str[g]];
+    gc.total = m.gres_total[g];
+    for (uint32_t e = 0; e < d.n_entries; ++e)
+      if (d.entry_name[e] == g && m.gres_spec[e]) gc.specified[d.type_str[e]] = m.gres_spec[e];
+  }
+  r.jobs_count = m.jobs_count;
+  r.wall_time = absl::Seconds(m.wall_time);
+  return r;
+}
+void MetaToAbi(const Dict& d, const Ctld::MetaResource& r, crane_meta_resource_t* m) {
+  memset(m, 0, sizeof *m);
+  m->cpu_raw = r.resource.GetCpuCount().raw_value();
+  m->mem = r.resource.GetMemoryBytes();
+  m->mem_sw = r.resource.GetMemorySwBytes();
+  for (int g = 0; g < CRANE_GRES_NAMES; ++g) {
+    auto it = r.resource.GetGresMap().find(d.name_str[g]);
+    if (it == r.resource.GetGresMap().end()) continue;
+    m->gres_total[g] = (uint32_t)it->second.total;
+    for (uint32_t e = 0; e < d.n_entries; ++e) {
+      if (d.entry_name[e] != g) continue;
+      auto tit = it->second.specified.find(d.type_str[e]);
+      if (tit != it->second.specified.end()) m->gres_spec[e] = (uint32_t)tit->second;
+    }
+  }
+  m->jobs_count = r.jobs_count;
+  m->wall_time = absl::ToInt64Seconds(r.wall_time);
+}
+int QosReasonCode(const std::string& s) {
+  if (s == "QosCpuResourceLimit") return CRANE_REASON_QOS_CPU;
+  if (s == "QosJobsResourceLimit") return CRANE_REASON_QOS_JOBS;
+  if (s == "QosWallTimeLimit") return CRANE_REASON_QOS_WALL;
+  if (s == "QosMemResourceLimit") return CRANE_REASON_QOS_MEM;
+  if (s == "QosGresResourceLimit") return CRANE_REASON_QOS_GRES;
+  if (s == "InvalidQOS") return CRANE_REASON_QOS_INVALID;
+  return 255;  // "QosResourceLimit": an entry missing from a map — cannot happen with dense tables
+}
+}  // namespace
+
+extern "C" int crane_ref_qos_filter(const crane_cluster_t* cl, const crane_pending_t* pending,
+                                    crane_placements_t* pl, const crane_qos_table_t* qt) {
+  if (!cl || !pending || !pl || !qt || !pending->qos || !pending->user) return CRANE_EINVAL;
+  using namespace Ctld;
+  Dict dict(cl);
+  const uint32_t N = pending->n, Q = qt->n_qos, U = qt->n_users, A = qt->n_accounts;
+  absl::shim_internal::arena().reset();
+  g_account_manager = std::make_unique<AccountManager>();
+  for (uint32_t q = 0; q < Q; ++q) {
+    auto qp = std::make_unique<Qos>();
+    qp->deleted = !qt->valid[q];
+    qp->max_jobs_per_user = qt->max_jobs_per_user[q];
+    qp->max_jobs_per_account = qt->max_jobs_per_account[q];
+    qp->max_jobs = qt->max_jobs[q];
+    qp->max_cpus_per_user = cpu_t::from_raw_value(qt->max_cpus_per_user_raw[q]);
+    qp->max_wall = absl::Seconds(qt->max_wall[q]);
+    qp->max_tres = LimitFromAbi(dict, qt->max_tres[q]);
+    qp->max_tres_per_user = LimitFromAbi(dict, qt->max_tres_per_user[q]);
+    qp->max_tres_per_account = LimitFromAbi(dict, qt->max_tres_per_account[q]);
+    g_account_manager->qos_map[QosName(q)] = std::move(qp);
+  }
+  AccountMetaContainer amc;
+  for (uint32_t u = 0; u < U; ++u)
+    for (uint32_t q = 0; q < Q; ++q) amc.m_user_meta_map_[UserName(u)][QosName(q)] = MetaFromAbi(dict, qt->user_usage[(size_t)u * Q + q]);
+  for (uint32_t a = 0; a < A; ++a)
+    for (uint32_t q = 0; q < Q; ++q) amc.m_account_meta_map_[AcctName(a)][QosName(q)] = MetaFromAbi(dict, qt->account_usage[(size_t)a * Q + q]);
+  for (uint32_t q = 0; q < Q; ++q) amc.m_qos_meta_map_[QosName(q)] = MetaFromAbi(dict, qt->qos_usage[q]);
+
+  for (uint32_t i = 0; i < N; ++i) {
+    if (pl->reason[i] != CRANE_REASON_NONE || pl->n_alloc[i] == 0) continue;
+    JobInCtld j;
+    j.job_id = i + 1;
+    j.time_limit = absl::Seconds(pending->time_limit[i]);
+    j.qos = pending->qos[i] < Q ? QosName(pending->qos[i]) : std::string("no-such-qos");
+    j.username = UserName(pending->user[i]);
+    for (uint32_t c = qt->chain_off[i]; c < qt->chain_off[i + 1]; ++c) j.account_chain.push_back(AcctName(qt->chain_acct[c]));
+    PdJobInScheduler job(&j);
+    for (uint32_t k = pl->alloc_off[i]; k < pl->alloc_off[i] + pl->n_alloc[i]; ++k)
+      job.allocated_res.AddResourceInNode(NodeName(pl->alloc_node[k]), FromAbi(dict, pl->alloc_res[k]));
+    auto r = amc.CheckAndMallocQosResource(job);
+    if (!r) pl->reason[i] = (uint8_t)QosReasonCode(r.error());
+  }
+  for (uint32_t u = 0; u < U; ++u)
+    for (uint32_t q = 0; q < Q; ++q) MetaToAbi(dict, amc.m_user_meta_map_[UserName(u)][QosName(q)], &qt->user_usage[(size_t)u * Q + q]);
+  for (uint32_t a = 0; a < A; ++a)
+    for (uint32_t q = 0; q < Q; ++q) MetaToAbi(dict, amc.m_account_meta_map_[AcctName(a)][QosName(q)], &qt->account_usage[(size_t)a * Q + q]);
+  for (uint32_t q = 0; q < Q; ++q) MetaToAbi(dict, amc.m_qos_meta_map_[QosName(q)], &qt->qos_usage[q]);
+  return CRANE_OK;
 }

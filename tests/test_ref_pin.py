@@ -197,3 +197,27 @@ def test_overlapping_partitions_with_reservations(oracle, seed):
     b, _ = pyref.node_select(cfg, cl, rn2, pd2, now, ex)
     d = a.diff(b)
     assert not d, "oracle differs from the reference's own NodeSelect:\n" + "\n".join(d[:8])
+
+
+@pytest.mark.parametrize("seed,tight,invalid", [(801, 1.0, 0.0), (802, 3.0, 0.1), (803, 0.5, 0.4), (804, 8.0, 0.0),
+                                                (805, 1.5, 0.2), (806, 0.8, 0.0), (807, 2.0, 0.05), (808, 20.0, 0.3)])
+def test_qos_filter_matches_reference(oracle, seed, tight, invalid):
+    """R12: the oracle's QoS pass against the reference's own CheckAndMallocQosResource / CheckQosResource_ /
+    CheckTres_ / CheckGres_ / DoMallocResource_ (Accounting/AccountMetaContainer.cpp:164-191, 382-587),
+    compiled from its text: reasons of every job and the three usage tables, byte for byte. (CheckGres_ walks
+    an unordered_map and stops at the first name the limit does not list; the oracle walks names in dictionary
+    order, deviation D8 — the two can only differ for a job holding two gres names of which the limit lists
+    one, which these draws do not produce.)"""
+    case = synth.random_case(seed, n_jobs=600, n_nodes=60, n_parts=3, n_running=20, one_type_per_name=True)
+    cfg, cl, rn, pd, now = case
+    table = synth.random_qos(seed, cl, pd, tight=tight, invalid_frac=invalid)
+    out, _, _ = oracle.node_select(cfg, cl, rn, pd, now)
+    a = abi.Placements(**{f: getattr(out, f).copy() for f in out.__dataclass_fields__})
+    b = abi.Placements(**{f: getattr(out, f).copy() for f in out.__dataclass_fields__})
+    ta, tb = table.copy(), table.copy()
+    oracle.qos_filter(cl, pd, a, ta)
+    pyref.qos_filter(cl, pd, b, tb)
+    assert np.array_equal(a.reason, b.reason), np.flatnonzero(a.reason != b.reason)[:10]
+    for f in ("user_usage", "account_usage", "qos_usage"):
+        assert getattr(ta, f).tobytes() == getattr(tb, f).tobytes(), f
+    assert (a.reason >= 16).any() or tight >= 8.0
